@@ -1,0 +1,977 @@
+// build.cu — device-side KdTree construction (sm_100a).
+//
+// Replaces the reference's recursive, single-threaded builder
+// (internal/kd_tree_builder.hpp:351-396 create_node, :143-280 splitters, :471-494 driver)
+// by a level-synchronous top-down pass over a BFS node table followed by a bottom-up pass
+// for the tight child bounds and a pre-order renumbering:
+//
+//   1. root box      : min/max reduction over all points   (space_wrapper.hpp:34-40)
+//   2. per level     : every node of the level is handled by one cooperating group —
+//                      a warp (count <= kWarpNodeMax) or a whole CTA (big nodes, listed
+//                      separately) — which either finishes it as a leaf (tight box,
+//                      kd_tree_builder.hpp:399-407) or splits it: max_side of the CUT box
+//                      (box.hpp:71-82), split_val, partition of the index range, slide
+//                      fix-up, two children appended to the next level.
+//   3. bottom-up     : tight box of a branch = fit(left, right) (:392); left_max/right_min
+//                      (kd_tree_node.hpp:86-92); subtree sizes.
+//   4. top-down      : pre-order numbers; emit 16-B nodes; gather points into leaf order.
+//
+// The index array is partitioned in place exactly like libstdc++'s std::partition would
+// leave it (the j-th misplaced element from the left is exchanged with the j-th misplaced
+// element from the right), so the order inside a leaf — which decides which of two
+// equidistant points a query reports — matches the reference wherever no slide happened.
+// A slide moves the extreme element next to the split by a single exchange; libstdc++'s
+// nth_element would additionally shuffle the remainder (tie-class difference only,
+// DESIGN.md §6).
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+namespace pico {
+namespace {
+
+constexpr int kWarpNodeMax = 1024;  // nodes up to this many points are split by one warp
+constexpr int kBigThreads = 1024;   // CTA size for bigger nodes
+
+template <typename T>
+struct BNode {
+  int32_t begin, end;
+  int32_t left, right;   // BFS ids, -1 for a leaf
+  int32_t split_dim;     // -1 for a leaf
+  int32_t depth;
+  uint32_t subtree;      // nodes in this subtree (bottom-up)
+  uint32_t preorder;     // final index (top-down)
+  T left_max, right_min;
+};
+
+template <typename T>
+struct BuildState {
+  const T* raw;        // [n][sdim] packed row-major
+  int32_t sdim;
+  int32_t* idx;        // [n]
+  int32_t* tmp;        // [n] scratch for the partition
+  BNode<T>* nodes;     // BFS table
+  T* boxes;            // [cap][2*sdim]: cut box on the way down, tight box on the way up
+  uint32_t* counters;  // [0] n_nodes  [1] n_big_next  [2] n_leaves
+  uint32_t* big_next;  // ids of next-level nodes that need a CTA
+  int32_t rule, stop_kind, stop_value;
+};
+
+// ------------------------------------------------------------------ cooperative groups
+// G == 32: one warp. G > 32: the whole CTA (blockDim.x == G).
+template <int G>
+struct Grp {
+  __device__ static int tid() { return threadIdx.x; }
+  __device__ static void sync() { __syncthreads(); }
+  __device__ static int sum(int v) {
+    __shared__ int s_w[G / 32];
+    __shared__ int s_tot;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int t = 0;
+      for (int w = 0; w < G / 32; ++w) t += s_w[w];
+      s_tot = t;
+    }
+    __syncthreads();
+    return s_tot;
+  }
+  // exclusive rank of `flag` among the group's threads (thread order) and the total
+  __device__ static int excl(int flag, int& total) {
+    __shared__ int s_w[G / 32];
+    const unsigned b = __ballot_sync(0xffffffffu, flag);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) s_w[w] = __popc(b);
+    __syncthreads();
+    int before = 0, tot = 0;
+    for (int i = 0; i < G / 32; ++i) {
+      const int c = s_w[i];
+      if (i < w) before += c;
+      tot += c;
+    }
+    total = tot;
+    return before + __popc(b & ((1u << lane) - 1u));
+  }
+  // extreme of (value, position): larger value wins if MAX (smaller if !MAX), ties -> lower position
+  template <typename T, bool MAX>
+  __device__ static void arg_extreme(T& v, int& pos) {
+    __shared__ T s_v[G / 32];
+    __shared__ int s_p[G / 32];
+    for (int o = 16; o > 0; o >>= 1) {
+      const T ov = __shfl_xor_sync(0xffffffffu, v, o);
+      const int op = __shfl_xor_sync(0xffffffffu, pos, o);
+      const bool better = MAX ? (ov > v) : (ov < v);
+      if (better || (ov == v && op < pos)) {
+        v = ov;
+        pos = op;
+      }
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) {
+      s_v[threadIdx.x >> 5] = v;
+      s_p[threadIdx.x >> 5] = pos;
+    }
+    __syncthreads();
+    v = s_v[0];
+    pos = s_p[0];
+    for (int w = 1; w < G / 32; ++w) {
+      const T ov = s_v[w];
+      const int op = s_p[w];
+      const bool better = MAX ? (ov > v) : (ov < v);
+      if (better || (ov == v && op < pos)) {
+        v = ov;
+        pos = op;
+      }
+    }
+    __syncthreads();
+  }
+};
+
+template <>
+struct Grp<32> {
+  __device__ static int tid() { return threadIdx.x & 31; }
+  __device__ static void sync() { __syncwarp(); }
+  __device__ static int sum(int v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+  }
+  __device__ static int excl(int flag, int& total) {
+    const unsigned b = __ballot_sync(0xffffffffu, flag);
+    total = __popc(b);
+    return __popc(b & ((1u << (threadIdx.x & 31)) - 1u));
+  }
+  template <typename T, bool MAX>
+  __device__ static void arg_extreme(T& v, int& pos) {
+    for (int o = 16; o > 0; o >>= 1) {
+      const T ov = __shfl_xor_sync(0xffffffffu, v, o);
+      const int op = __shfl_xor_sync(0xffffffffu, pos, o);
+      const bool better = MAX ? (ov > v) : (ov < v);
+      if (better || (ov == v && op < pos)) {
+        v = ov;
+        pos = op;
+      }
+    }
+  }
+};
+
+// ------------------------------------------------------------------ one node
+template <typename T, int G>
+__device__ void finish_leaf(const BuildState<T>& s, BNode<T>& nd, T* box) {
+  const int tid = Grp<G>::tid();
+  const int begin = nd.begin, end = nd.end, sdim = s.sdim;
+  // "Keep the original box in case it is empty" (midpoint only, kd_tree_builder.hpp:363-371);
+  // the other rules never produce an empty range.
+  if (begin < end) {
+    if (end - begin <= 64) {
+      // few points: one thread per dimension, points visited in order
+      for (int d = tid; d < sdim; d += G) {
+        T mn = Limits<T>::max(), mx = -Limits<T>::max();
+        for (int i = begin; i < end; ++i) {
+          const T x = s.raw[(size_t)s.idx[i] * sdim + d];
+          if (x < mn) mn = x;
+          if (x > mx) mx = x;
+        }
+        box[d] = mn;
+        box[sdim + d] = mx;
+      }
+    } else {
+      for (int d = 0; d < sdim; ++d) {
+        T mn = Limits<T>::max(), mx = -Limits<T>::max();
+        int pn = 0, px = 0;
+        for (int i = begin + tid; i < end; i += G) {
+          const T x = s.raw[(size_t)s.idx[i] * sdim + d];
+          if (x < mn) mn = x;
+          if (x > mx) mx = x;
+        }
+        Grp<G>::template arg_extreme<T, false>(mn, pn);
+        Grp<G>::template arg_extreme<T, true>(mx, px);
+        if (tid == 0) {
+          box[d] = mn;
+          box[sdim + d] = mx;
+        }
+      }
+    }
+  }
+  if (tid == 0) {
+    nd.left = nd.right = -1;
+    nd.split_dim = -1;
+    nd.subtree = 1;
+    atomicAdd(&s.counters[2], 1u);
+  }
+}
+
+template <typename T, int G>
+__device__ void process_node(const BuildState<T>& s, uint32_t node_id) {
+  BNode<T>& nd = s.nodes[node_id];
+  const int tid = Grp<G>::tid();
+  const int begin = nd.begin, end = nd.end, cnt = end - begin, depth = nd.depth;
+  const int sdim = s.sdim;
+  T* box = s.boxes + (size_t)node_id * 2 * sdim;
+
+  // is_leaf, kd_tree_builder.hpp:410-425
+  const bool leaf = (s.stop_kind == PICO_B200_STOP_MAX_LEAF_SIZE) ? (cnt <= s.stop_value)
+                                                                  : (depth == s.stop_value || cnt <= 1);
+  if (leaf) {
+    finish_leaf<T, G>(s, nd, box);
+    return;
+  }
+
+  // box_base::max_side, box.hpp:71-82 — strict '>' keeps the first longest side.
+  int sd = 0;
+  T max_delta = -Limits<T>::max();
+  for (int d = 0; d < sdim; ++d) {
+    const T delta = box[sdim + d] - box[d];
+    if (delta > max_delta) {
+      max_delta = delta;
+      sd = d;
+    }
+  }
+  const T box_min_sd = box[sd];
+  const T* col = s.raw + sd;  // coordinate `sd` of point p is col[p * sdim]
+  int32_t* idx = s.idx;
+  int split;
+  T split_val;
+
+  {
+    // kd_tree_builder.hpp:204 (midpoint: * 0.5) and :240 (sliding: / 2.0) — identical in
+    // IEEE arithmetic, kept apart for the record.
+    split_val = (s.rule == PICO_B200_RULE_MIDPOINT_MAX_SIDE) ? (max_delta * T(0.5) + box_min_sd)
+                                                             : (max_delta / T(2.0) + box_min_sd);
+    int nl = 0;
+    for (int base = begin; base < end; base += G) {
+      const int i = base + tid;
+      nl += (i < end) && (col[(size_t)idx[i] * sdim] < split_val);
+    }
+    nl = Grp<G>::sum(nl);
+    split = begin + nl;
+
+    if (s.rule == PICO_B200_RULE_SLIDING_MIDPOINT_MAX_SIDE && nl == cnt) {
+      // all left: the largest coordinate slides right (kd_tree_builder.hpp:255-264)
+      T v = -Limits<T>::max();
+      int p = 0x7fffffff;
+      for (int i = begin + tid; i < end; i += G) {
+        const T x = col[(size_t)idx[i] * sdim];
+        if (x > v) {
+          v = x;
+          p = i;
+        }
+      }
+      Grp<G>::template arg_extreme<T, true>(v, p);
+      if (tid == 0) {
+        const int32_t a = idx[p];
+        idx[p] = idx[end - 1];
+        idx[end - 1] = a;
+      }
+      split = end - 1;
+      split_val = v;
+      Grp<G>::sync();
+    } else if (s.rule == PICO_B200_RULE_SLIDING_MIDPOINT_MAX_SIDE && nl == 0) {
+      // all right: the smallest coordinate slides left; split_val becomes the second
+      // smallest coordinate (kd_tree_builder.hpp:265-275)
+      T v = Limits<T>::max();
+      int p = 0x7fffffff;
+      for (int i = begin + tid; i < end; i += G) {
+        const T x = col[(size_t)idx[i] * sdim];
+        if (x < v) {
+          v = x;
+          p = i;
+        }
+      }
+      Grp<G>::template arg_extreme<T, false>(v, p);
+      if (tid == 0) {
+        const int32_t a = idx[p];
+        idx[p] = idx[begin];
+        idx[begin] = a;
+      }
+      Grp<G>::sync();
+      T v2 = Limits<T>::max();
+      int p2 = 0x7fffffff;
+      for (int i = begin + 1 + tid; i < end; i += G) {
+        const T x = col[(size_t)idx[i] * sdim];
+        if (x < v2) {
+          v2 = x;
+          p2 = i;
+        }
+      }
+      Grp<G>::template arg_extreme<T, false>(v2, p2);
+      split = begin + 1;
+      split_val = v2;
+    } else if (nl > 0 && nl < cnt) {
+      // std::partition order: j-th misplaced from the left <-> j-th misplaced from the right
+      int32_t* tmp = s.tmp;
+      int m = 0;
+      for (int base = begin; base < split; base += G) {
+        const int i = base + tid;
+        const int f = (i < split) && !(col[(size_t)idx[i] * sdim] < split_val);
+        int tot;
+        const int ex = Grp<G>::excl(f, tot);
+        if (f) tmp[begin + m + ex] = i;
+        m += tot;
+      }
+      if (m > 0) {
+        int r = 0;
+        for (int base = split; base < end; base += G) {
+          const int i = base + tid;
+          const int f = (i < end) && (col[(size_t)idx[i] * sdim] < split_val);
+          int tot;
+          const int ex = Grp<G>::excl(f, tot);
+          if (f) tmp[end - 1 - (r + ex)] = i;
+          r += tot;
+        }
+        Grp<G>::sync();
+        for (int j = tid; j < m; j += G) {
+          const int a = tmp[begin + j], b = tmp[end - m + j];
+          const int32_t va = idx[a];
+          idx[a] = idx[b];
+          idx[b] = va;
+        }
+        Grp<G>::sync();
+      }
+    }
+    // midpoint with nl == 0 or nl == cnt: one child is empty, nothing moves.
+  }
+
+  if (tid == 0) {
+    const uint32_t c = atomicAdd(&s.counters[0], 2u);
+    nd.left = (int32_t)c;
+    nd.right = (int32_t)c + 1;
+    nd.split_dim = sd;
+    BNode<T>& l = s.nodes[c];
+    BNode<T>& r = s.nodes[c + 1];
+    l.begin = begin;
+    l.end = split;
+    l.depth = depth + 1;
+    r.begin = split;
+    r.end = end;
+    r.depth = depth + 1;
+    l.left = l.right = r.left = r.right = -1;
+    l.split_dim = r.split_dim = -1;
+    if (split - begin > kWarpNodeMax) s.big_next[atomicAdd(&s.counters[1], 1u)] = c;
+    if (end - split > kWarpNodeMax) s.big_next[atomicAdd(&s.counters[1], 1u)] = c + 1;
+  }
+  Grp<G>::sync();
+  // children's cut boxes: kd_tree_builder.hpp:379-383
+  {
+    const uint32_t cc = (uint32_t)nd.left;
+    T* lb = s.boxes + (size_t)cc * 2 * sdim;
+    T* rb = lb + 2 * sdim;
+    for (int d = tid; d < 2 * sdim; d += G) {
+      const T v = box[d];
+      lb[d] = (d == sdim + sd) ? split_val : v;
+      rb[d] = (d == sd) ? split_val : v;
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) split_level_warp(BuildState<T> s, uint32_t level_begin, uint32_t level_end) {
+  const uint32_t node = level_begin + (blockIdx.x * blockDim.x + threadIdx.x) / 32;
+  if (node >= level_end) return;
+  if (s.nodes[node].end - s.nodes[node].begin > kWarpNodeMax) return;  // a CTA takes it
+  process_node<T, 32>(s, node);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kBigThreads) split_level_block(BuildState<T> s, const uint32_t* big_list) {
+  process_node<T, kBigThreads>(s, big_list[blockIdx.x]);
+}
+
+// ------------------------------------------------------------------ median rule
+// nth_element at the middle (kd_tree_builder.hpp:153-176): the split position is fixed, the
+// value is the (cnt/2)-th order statistic on split_dim. One warp per node: repeated
+// three-way narrowing on the value range (exact, works on the bit pattern order).
+// Membership among equal coordinates is libstdc++-defined in the reference; here elements
+// equal to split_val fill the left side in index-array order.
+template <typename T>
+__device__ __forceinline__ unsigned long long order_bits(T x);
+template <>
+__device__ __forceinline__ unsigned long long order_bits<float>(float x) {
+  unsigned u = __float_as_uint(x);
+  u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  return u;
+}
+template <>
+__device__ __forceinline__ unsigned long long order_bits<double>(double x) {
+  unsigned long long u = (unsigned long long)__double_as_longlong(x);
+  u = (u & 0x8000000000000000ull) ? ~u : (u | 0x8000000000000000ull);
+  return u;
+}
+
+template <typename T, int G>
+__device__ void median_node(const BuildState<T>& s, uint32_t node_id) {
+  BNode<T>& nd = s.nodes[node_id];
+  const int tid = Grp<G>::tid();
+  const int begin = nd.begin, end = nd.end, cnt = end - begin, depth = nd.depth;
+  const int sdim = s.sdim;
+  T* box = s.boxes + (size_t)node_id * 2 * sdim;
+  const bool leaf = (s.stop_kind == PICO_B200_STOP_MAX_LEAF_SIZE) ? (cnt <= s.stop_value)
+                                                                  : (depth == s.stop_value || cnt <= 1);
+  if (leaf) {
+    finish_leaf<T, G>(s, nd, box);
+    return;
+  }
+  int sd = 0;
+  T max_delta = -Limits<T>::max();
+  for (int d = 0; d < sdim; ++d) {
+    const T delta = box[sdim + d] - box[d];
+    if (delta > max_delta) {
+      max_delta = delta;
+      sd = d;
+    }
+  }
+  const T* col = s.raw + sd;
+  int32_t* idx = s.idx;
+  const int kth = cnt / 2;  // rank of the split element inside [begin, end)
+  // bitwise radix select on the order-preserving key, MSB first
+  constexpr int kBits = sizeof(T) * 8;
+  unsigned long long prefix = 0, mask = 0;
+  int rank = kth;
+  for (int b = kBits - 1; b >= 0; --b) {
+    const unsigned long long bit = 1ull << b;
+    int zeros = 0;
+    for (int base = begin; base < end; base += G) {
+      const int i = base + tid;
+      if (i < end) {
+        const unsigned long long key = order_bits<T>(col[(size_t)idx[i] * sdim]);
+        zeros += ((key & mask) == prefix) && !(key & bit);
+      }
+    }
+    zeros = Grp<G>::sum(zeros);
+    if (rank >= zeros) {
+      rank -= zeros;
+      prefix |= bit;
+    }
+    mask |= bit;
+  }
+  // prefix is now the key of the kth element; `rank` = how many equal keys belong left of it
+  // stable three-way arrangement into tmp, then copy back
+  int32_t* tmp = s.tmp;
+  int n_less = 0, n_eq = 0;
+  for (int base = begin; base < end; base += G) {
+    const int i = base + tid;
+    int lt = 0, eq = 0;
+    if (i < end) {
+      const unsigned long long key = order_bits<T>(col[(size_t)idx[i] * sdim]);
+      lt = key < prefix;
+      eq = key == prefix;
+    }
+    n_less += lt;
+    n_eq += eq;
+  }
+  n_less = Grp<G>::sum(n_less);
+  n_eq = Grp<G>::sum(n_eq);
+  int o_lt = 0, o_eq = 0, o_gt = 0;
+  T split_val = 0;
+  for (int base = begin; base < end; base += G) {
+    const int i = base + tid;
+    int lt = 0, eq = 0, gt = 0;
+    int32_t v = 0;
+    if (i < end) {
+      v = idx[i];
+      const T x = col[(size_t)v * sdim];
+      const unsigned long long key = order_bits<T>(x);
+      lt = key < prefix;
+      eq = key == prefix;
+      gt = key > prefix;
+      if (eq) split_val = x;
+    }
+    int t0, t1, t2;
+    const int e0 = Grp<G>::excl(lt, t0);
+    const int e1 = Grp<G>::excl(eq, t1);
+    const int e2 = Grp<G>::excl(gt, t2);
+    if (lt) tmp[begin + o_lt + e0] = v;
+    if (eq) tmp[begin + n_less + o_eq + e1] = v;
+    if (gt) tmp[begin + n_less + n_eq + o_gt + e2] = v;
+    o_lt += t0;
+    o_eq += t1;
+    o_gt += t2;
+  }
+  Grp<G>::sync();
+  for (int i = begin + tid; i < end; i += G) idx[i] = tmp[i];
+  Grp<G>::sync();
+  const int split = begin + kth;
+  split_val = col[(size_t)idx[split] * sdim];
+
+  if (tid == 0) {
+    const uint32_t c = atomicAdd(&s.counters[0], 2u);
+    nd.left = (int32_t)c;
+    nd.right = (int32_t)c + 1;
+    nd.split_dim = sd;
+    BNode<T>& l = s.nodes[c];
+    BNode<T>& r = s.nodes[c + 1];
+    l.begin = begin;
+    l.end = split;
+    l.depth = depth + 1;
+    r.begin = split;
+    r.end = end;
+    r.depth = depth + 1;
+    l.left = l.right = r.left = r.right = -1;
+    l.split_dim = r.split_dim = -1;
+    if (split - begin > kWarpNodeMax) s.big_next[atomicAdd(&s.counters[1], 1u)] = c;
+    if (end - split > kWarpNodeMax) s.big_next[atomicAdd(&s.counters[1], 1u)] = c + 1;
+  }
+  Grp<G>::sync();
+  {
+    const uint32_t cc = (uint32_t)nd.left;
+    T* lb = s.boxes + (size_t)cc * 2 * sdim;
+    T* rb = lb + 2 * sdim;
+    for (int d = tid; d < 2 * sdim; d += G) {
+      const T v = box[d];
+      lb[d] = (d == sdim + sd) ? split_val : v;
+      rb[d] = (d == sd) ? split_val : v;
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) median_level_warp(BuildState<T> s, uint32_t level_begin, uint32_t level_end) {
+  const uint32_t node = level_begin + (blockIdx.x * blockDim.x + threadIdx.x) / 32;
+  if (node >= level_end) return;
+  if (s.nodes[node].end - s.nodes[node].begin > kWarpNodeMax) return;
+  median_node<T, 32>(s, node);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kBigThreads) median_level_block(BuildState<T> s, const uint32_t* big_list) {
+  median_node<T, kBigThreads>(s, big_list[blockIdx.x]);
+}
+
+// ------------------------------------------------------------------ small kernels
+template <typename T>
+__global__ void root_box_kernel(const T* raw, size_t n, int sdim, T* partial /* [grid][2*sdim] */) {
+  // one CTA computes min/max of every dimension over a grid-strided slice
+  __shared__ T s_mn[32], s_mx[32];
+  for (int d = 0; d < sdim; ++d) {
+    T mn = Limits<T>::max(), mx = -Limits<T>::max();
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+      const T x = raw[i * sdim + d];
+      if (x < mn) mn = x;
+      if (x > mx) mx = x;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const T a = __shfl_xor_sync(0xffffffffu, mn, o), b = __shfl_xor_sync(0xffffffffu, mx, o);
+      if (a < mn) mn = a;
+      if (b > mx) mx = b;
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) {
+      s_mn[threadIdx.x >> 5] = mn;
+      s_mx[threadIdx.x >> 5] = mx;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < (int)blockDim.x / 32; ++w) {
+        if (s_mn[w] < mn) mn = s_mn[w];
+        if (s_mx[w] > mx) mx = s_mx[w];
+      }
+      partial[(size_t)blockIdx.x * 2 * sdim + d] = mn;
+      partial[(size_t)blockIdx.x * 2 * sdim + sdim + d] = mx;
+    }
+  }
+}
+
+template <typename T>
+__global__ void root_box_final(const T* partial, int parts, int sdim, T* out) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= sdim) return;
+  T mn = Limits<T>::max(), mx = -Limits<T>::max();
+  for (int p = 0; p < parts; ++p) {
+    const T a = partial[(size_t)p * 2 * sdim + d], b = partial[(size_t)p * 2 * sdim + sdim + d];
+    if (a < mn) mn = a;
+    if (b > mx) mx = b;
+  }
+  out[d] = mn;
+  out[sdim + d] = mx;
+}
+
+__global__ void iota_kernel(int32_t* idx, size_t n) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) idx[i] = (int32_t)i;
+}
+
+// bottom-up over one level: tight boxes, stored bounds, subtree sizes (kd_tree_builder.hpp:388-392)
+template <typename T>
+__global__ void merge_level(BNode<T>* nodes, T* boxes, int sdim, uint32_t level_begin, uint32_t level_end) {
+  const uint32_t node = level_begin + blockIdx.x * blockDim.x + threadIdx.x;
+  if (node >= level_end) return;
+  BNode<T>& nd = nodes[node];
+  if (nd.split_dim < 0) return;
+  const T* lb = boxes + (size_t)nd.left * 2 * sdim;
+  const T* rb = boxes + (size_t)nd.right * 2 * sdim;
+  T* box = boxes + (size_t)node * 2 * sdim;
+  nd.left_max = lb[sdim + nd.split_dim];
+  nd.right_min = rb[nd.split_dim];
+  for (int d = 0; d < sdim; ++d) {
+    T mn = lb[d], mx = lb[sdim + d];
+    if (rb[d] < mn) mn = rb[d];
+    if (rb[sdim + d] > mx) mx = rb[sdim + d];
+    box[d] = mn;
+    box[sdim + d] = mx;
+  }
+  nd.subtree = 1 + nodes[nd.left].subtree + nodes[nd.right].subtree;
+}
+
+template <typename T>
+__global__ void number_level(BNode<T>* nodes, uint32_t level_begin, uint32_t level_end) {
+  const uint32_t node = level_begin + blockIdx.x * blockDim.x + threadIdx.x;
+  if (node >= level_end) return;
+  BNode<T>& nd = nodes[node];
+  if (nd.split_dim < 0) return;
+  nodes[nd.left].preorder = nd.preorder + 1;
+  nodes[nd.right].preorder = nd.preorder + 1 + nodes[nd.left].subtree;
+}
+
+template <typename T>
+__global__ void emit_nodes(const BNode<T>* nodes, uint32_t n_nodes, typename NodeOf<T>::type* out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_nodes) return;
+  const BNode<T>& nd = nodes[i];
+  typename NodeOf<T>::type o;
+  memset(&o, 0, sizeof(o));
+  if (nd.split_dim < 0) {
+    o.a.begin_idx = nd.begin;
+    o.b.end_idx = nd.end;
+    o.right = PICO_B200_LEAF;
+    o.split_dim = PICO_B200_LEAF;
+  } else {
+    o.a.left_max = nd.left_max;
+    o.b.right_min = nd.right_min;
+    o.right = nodes[nd.right].preorder;
+    o.split_dim = (uint32_t)nd.split_dim;
+  }
+  out[nd.preorder] = o;
+}
+
+// leaf-ordered point storage
+template <typename T>
+__global__ void pack_points4(const T* raw, const int32_t* idx, size_t n, int sdim, typename Vec4Of<T>::type* out) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int32_t p = idx[i];
+  typename Vec4Of<T>::type v;
+  v.x = raw[(size_t)p * sdim];
+  v.y = sdim > 1 ? raw[(size_t)p * sdim + 1] : T(0);
+  v.z = sdim > 2 ? raw[(size_t)p * sdim + 2] : T(0);
+  if (sizeof(T) == 4) {
+    v.w = (T)__int_as_float(p);
+  } else {
+    v.w = (T)__longlong_as_double((long long)p);
+  }
+  out[i] = v;
+}
+
+template <typename T>
+__global__ void pack_pointsN(const T* raw, const int32_t* idx, size_t n, int sdim, T* out) {
+  // one warp per point row keeps both sides coalesced
+  const size_t row = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) / 32;
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const T* src = raw + (size_t)idx[row] * sdim;
+  T* dst = out + row * sdim;
+  for (int d = lane; d < sdim; d += 32) dst[d] = src[d];
+}
+
+struct DevBuf {
+  void* p = nullptr;
+  ~DevBuf() {
+    if (p) cudaFree(p);
+  }
+  template <typename U>
+  U* as() {
+    return static_cast<U*>(p);
+  }
+};
+
+int alloc(DevBuf& b, size_t bytes) {
+  PICO_CUDA(cudaMalloc(&b.p, bytes ? bytes : 16));
+  return 0;
+}
+
+// Staging: host rows (any stride) -> packed device rows.
+template <typename T>
+int stage_points(const T* h_pts, size_t n, size_t sdim, size_t stride, T* d_raw, cudaStream_t st) {
+  PICO_CUDA(cudaMemcpy2DAsync(d_raw, sdim * sizeof(T), h_pts, stride * sizeof(T), sdim * sizeof(T), n,
+                              cudaMemcpyHostToDevice, st));
+  return 0;
+}
+
+template <typename T>
+int finalize_storage(pico_b200_tree* t, const T* d_raw, cudaStream_t st) {
+  const size_t n = t->n;
+  const int sdim = (int)t->sdim;
+  PICO_CUDA(cudaMalloc(&t->d_pts, t->pts_bytes() ? t->pts_bytes() : 16));
+  if (t->packed()) {
+    pack_points4<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_raw, t->d_indices, n, sdim,
+                                                                  static_cast<typename Vec4Of<T>::type*>(t->d_pts));
+  } else {
+    pack_pointsN<T><<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(d_raw, t->d_indices, n, sdim,
+                                                                      static_cast<T*>(t->d_pts));
+  }
+  PICO_CUDA(cudaGetLastError());
+  t->device_bytes = t->pts_bytes() + t->n_nodes * t->node_size() + n * 4 + 2 * t->sdim * sizeof(T);
+  return 0;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ host driver
+template <typename T>
+int build_tree(pico_b200_tree* t, const T* h_pts, size_t stride, int rule, int stop_kind, size_t stop_value,
+               const T* bounds_min, const T* bounds_max) {
+  const size_t n = t->n;
+  const int sdim = (int)t->sdim;
+  if (n >= (size_t)0x7fffffff) return fail(PICO_B200_ERR_UNSUPPORTED, "more than 2^31-2 points");
+  cudaStream_t st;
+  PICO_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  struct StreamGuard {
+    cudaStream_t s;
+    ~StreamGuard() { cudaStreamDestroy(s); }
+  } guard{st};
+
+  DevBuf raw, tmp, nodes, boxes, counters, big_a, big_b, partial;
+  PICO_TRY(alloc(raw, n * sdim * sizeof(T)));
+  PICO_TRY(stage_points(h_pts, n, sdim, stride, raw.as<T>(), st));
+  PICO_CUDA(cudaMalloc(&t->d_indices, n * sizeof(int32_t)));
+  PICO_CUDA(cudaMalloc(&t->d_root_box, 2 * sdim * sizeof(T)));
+  PICO_TRY(alloc(tmp, n * sizeof(int32_t)));
+
+  cudaEvent_t ev0, ev1;
+  PICO_CUDA(cudaEventCreate(&ev0));
+  PICO_CUDA(cudaEventCreate(&ev1));
+  PICO_CUDA(cudaEventRecord(ev0, st));
+
+  // --- root box
+  T* d_root = static_cast<T*>(t->d_root_box);
+  std::vector<T> h_root(2 * sdim);
+  if (bounds_min && bounds_max) {
+    // bbox.fit(min); bbox.fit(max)  kd_tree_builder.hpp:502-511
+    for (int d = 0; d < sdim; ++d) {
+      T mn = Limits<T>::max(), mx = -Limits<T>::max();
+      const T xs[2] = {bounds_min[d], bounds_max[d]};
+      for (T x : xs) {
+        if (x < mn) mn = x;
+        if (x > mx) mx = x;
+      }
+      h_root[d] = mn;
+      h_root[sdim + d] = mx;
+    }
+    PICO_CUDA(cudaMemcpyAsync(d_root, h_root.data(), 2 * sdim * sizeof(T), cudaMemcpyHostToDevice, st));
+  } else {
+    const int parts = (int)std::min<size_t>((n + 1023) / 1024, (size_t)t->sm_count * 4);
+    PICO_TRY(alloc(partial, (size_t)parts * 2 * sdim * sizeof(T)));
+    root_box_kernel<T><<<parts, 1024, 0, st>>>(raw.as<T>(), n, sdim, partial.as<T>());
+    root_box_final<T><<<(sdim + 127) / 128, 128, 0, st>>>(partial.as<T>(), parts, sdim, d_root);
+    PICO_CUDA(cudaGetLastError());
+    PICO_CUDA(cudaMemcpyAsync(h_root.data(), d_root, 2 * sdim * sizeof(T), cudaMemcpyDeviceToHost, st));
+    PICO_CUDA(cudaStreamSynchronize(st));
+  }
+  for (int d = 0; d < sdim && d < 4; ++d) {
+    t->root_box_host[d] = (double)h_root[d];
+    t->root_box_host[4 + d] = (double)h_root[sdim + d];
+  }
+
+  iota_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(t->d_indices, n);
+
+  // --- BFS node table
+  size_t cap = 2 * n + 1024;
+  PICO_TRY(alloc(nodes, cap * sizeof(BNode<T>)));
+  PICO_TRY(alloc(boxes, cap * 2 * sdim * sizeof(T)));
+  PICO_TRY(alloc(counters, 4 * sizeof(uint32_t)));
+  PICO_TRY(alloc(big_a, cap * sizeof(uint32_t)));
+  PICO_TRY(alloc(big_b, cap * sizeof(uint32_t)));
+
+  BuildState<T> s;
+  s.raw = raw.as<T>();
+  s.sdim = sdim;
+  s.idx = t->d_indices;
+  s.tmp = tmp.as<int32_t>();
+  s.nodes = nodes.as<BNode<T>>();
+  s.boxes = boxes.as<T>();
+  s.counters = counters.as<uint32_t>();
+  s.rule = rule;
+  s.stop_kind = stop_kind;
+  s.stop_value = (int32_t)std::min<size_t>(stop_value, 0x7fffffff);
+
+  {
+    BNode<T> root;
+    memset(&root, 0, sizeof(root));
+    root.begin = 0;
+    root.end = (int32_t)n;
+    root.left = root.right = -1;
+    root.split_dim = -1;
+    root.depth = 0;
+    root.preorder = 0;
+    PICO_CUDA(cudaMemcpyAsync(s.nodes, &root, sizeof(root), cudaMemcpyHostToDevice, st));
+    PICO_CUDA(cudaMemcpyAsync(s.boxes, d_root, 2 * sdim * sizeof(T), cudaMemcpyDeviceToDevice, st));
+    const uint32_t h_cnt[4] = {1u, 0u, 0u, 0u};
+    PICO_CUDA(cudaMemcpyAsync(s.counters, h_cnt, sizeof(h_cnt), cudaMemcpyHostToDevice, st));
+    const uint32_t zero = 0;
+    PICO_CUDA(cudaMemcpyAsync(big_a.p, &zero, sizeof(zero), cudaMemcpyHostToDevice, st));
+  }
+
+  std::vector<uint32_t> level_start;  // BFS id of the first node of each level
+  level_start.push_back(0);
+  uint32_t level_begin = 0, level_end = 1;
+  uint32_t n_big = (n > (size_t)kWarpNodeMax) ? 1u : 0u;  // the root
+  uint32_t* big_cur = big_a.as<uint32_t>();
+  uint32_t* big_nxt = big_b.as<uint32_t>();
+  uint32_t* h_counters = nullptr;
+  PICO_CUDA(cudaMallocHost(&h_counters, 4 * sizeof(uint32_t)));
+  struct PinGuard {
+    uint32_t* p;
+    ~PinGuard() { cudaFreeHost(p); }
+  } pin_guard{h_counters};
+
+  while (level_begin < level_end) {
+    const uint32_t width = level_end - level_begin;
+    if ((size_t)level_end + 2 * (size_t)width > cap) {
+      // grow the tables (midpoint rule can create many empty leaves)
+      const size_t ncap = std::max(cap * 2, (size_t)level_end + 2 * (size_t)width + 1024);
+      DevBuf nn, nb, na, nbb;
+      PICO_TRY(alloc(nn, ncap * sizeof(BNode<T>)));
+      PICO_TRY(alloc(nb, ncap * 2 * sdim * sizeof(T)));
+      PICO_TRY(alloc(na, ncap * sizeof(uint32_t)));
+      PICO_TRY(alloc(nbb, ncap * sizeof(uint32_t)));
+      PICO_CUDA(cudaMemcpyAsync(nn.p, nodes.p, cap * sizeof(BNode<T>), cudaMemcpyDeviceToDevice, st));
+      PICO_CUDA(cudaMemcpyAsync(nb.p, boxes.p, cap * 2 * sdim * sizeof(T), cudaMemcpyDeviceToDevice, st));
+      PICO_CUDA(cudaMemcpyAsync(na.p, big_cur, (size_t)n_big * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+      PICO_CUDA(cudaStreamSynchronize(st));
+      std::swap(nodes.p, nn.p);
+      std::swap(boxes.p, nb.p);
+      std::swap(big_a.p, na.p);
+      std::swap(big_b.p, nbb.p);
+      big_cur = big_a.as<uint32_t>();
+      big_nxt = big_b.as<uint32_t>();
+      s.nodes = nodes.as<BNode<T>>();
+      s.boxes = boxes.as<T>();
+      cap = ncap;
+    }
+    s.big_next = big_nxt;
+    PICO_CUDA(cudaMemsetAsync(s.counters + 1, 0, sizeof(uint32_t), st));
+    const unsigned warp_blocks = (unsigned)(((size_t)width * 32 + 255) / 256);
+    if (rule == PICO_B200_RULE_MEDIAN_MAX_SIDE) {
+      median_level_warp<T><<<warp_blocks, 256, 0, st>>>(s, level_begin, level_end);
+      if (n_big) median_level_block<T><<<n_big, kBigThreads, 0, st>>>(s, big_cur);
+    } else {
+      split_level_warp<T><<<warp_blocks, 256, 0, st>>>(s, level_begin, level_end);
+      if (n_big) split_level_block<T><<<n_big, kBigThreads, 0, st>>>(s, big_cur);
+    }
+    PICO_CUDA(cudaGetLastError());
+    PICO_CUDA(cudaMemcpyAsync(h_counters, s.counters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    PICO_CUDA(cudaStreamSynchronize(st));
+    level_begin = level_end;
+    level_end = h_counters[0];
+    n_big = h_counters[1];
+    std::swap(big_cur, big_nxt);
+    if (level_begin < level_end) level_start.push_back(level_begin);
+    if ((size_t)level_end >= 0x7ffffff0u) return fail(PICO_B200_ERR_UNSUPPORTED, "node table overflow");
+    if (level_start.size() > (1u << 20))
+      return fail(PICO_B200_ERR_UNSUPPORTED, "tree deeper than 2^20 levels (degenerate input for this split rule)");
+  }
+  const uint32_t n_nodes = level_end;
+  level_start.push_back(n_nodes);
+  const size_t levels = level_start.size() - 1;
+  t->n_nodes = n_nodes;
+  t->n_leaves = h_counters[2];
+  t->height = levels - 1;
+
+  // --- bottom-up (tight boxes, bounds, subtree sizes), then pre-order numbers
+  for (size_t l = levels; l-- > 0;) {
+    const uint32_t lb = level_start[l], le = level_start[l + 1];
+    merge_level<T><<<(le - lb + 127) / 128, 128, 0, st>>>(s.nodes, s.boxes, sdim, lb, le);
+  }
+  for (size_t l = 0; l < levels; ++l) {
+    const uint32_t lb = level_start[l], le = level_start[l + 1];
+    number_level<T><<<(le - lb + 127) / 128, 128, 0, st>>>(s.nodes, lb, le);
+  }
+  PICO_CUDA(cudaMalloc(&t->d_nodes, (size_t)n_nodes * t->node_size()));
+  emit_nodes<T><<<(n_nodes + 255) / 256, 256, 0, st>>>(s.nodes, n_nodes,
+                                                        static_cast<typename NodeOf<T>::type*>(t->d_nodes));
+  PICO_CUDA(cudaGetLastError());
+  PICO_TRY(finalize_storage<T>(t, raw.as<T>(), st));
+  PICO_CUDA(cudaEventRecord(ev1, st));
+  PICO_CUDA(cudaStreamSynchronize(st));
+  float ms = 0;
+  PICO_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+  t->build_ms = ms;
+  cudaEventDestroy(ev0);
+  cudaEventDestroy(ev1);
+  return 0;
+}
+
+// Upload of an existing tree (kd_tree::load path).
+template <typename T>
+int upload_tree(pico_b200_tree* t, const T* h_pts, size_t stride, const void* h_nodes, size_t n_nodes,
+                const int32_t* indices, const T* root_box) {
+  using NodeT = typename NodeOf<T>::type;
+  const size_t n = t->n;
+  const int sdim = (int)t->sdim;
+  const NodeT* nodes = static_cast<const NodeT*>(h_nodes);
+  // validate links and measure height / leaves on the host (cheap, once)
+  size_t leaves = 0, height = 0;
+  {
+    std::vector<std::pair<uint32_t, uint32_t>> stack;
+    if (n_nodes == 0) return fail(PICO_B200_ERR_INVALID_ARGUMENT, "tree has no nodes");
+    stack.emplace_back(0u, 0u);
+    size_t visited = 0;
+    while (!stack.empty()) {
+      auto [i, d] = stack.back();
+      stack.pop_back();
+      if (i >= n_nodes || ++visited > n_nodes) return fail(PICO_B200_ERR_INVALID_ARGUMENT, "corrupt node links");
+      height = std::max<size_t>(height, d);
+      if (nodes[i].split_dim == PICO_B200_LEAF) {
+        ++leaves;
+        const int64_t b = nodes[i].a.begin_idx, e = nodes[i].b.end_idx;
+        if (b < 0 || e < b || (size_t)e > n) return fail(PICO_B200_ERR_INVALID_ARGUMENT, "leaf range out of bounds");
+      } else {
+        if (nodes[i].split_dim >= (uint32_t)sdim) return fail(PICO_B200_ERR_INVALID_ARGUMENT, "split_dim >= sdim");
+        stack.emplace_back(nodes[i].right, d + 1);
+        stack.emplace_back(i + 1, d + 1);
+      }
+    }
+  }
+  for (size_t i = 0; i < n; ++i)
+    if (indices[i] < 0 || (size_t)indices[i] >= n) return fail(PICO_B200_ERR_INVALID_ARGUMENT, "index out of range");
+  t->n_nodes = n_nodes;
+  t->n_leaves = leaves;
+  t->height = height;
+
+  cudaStream_t st;
+  PICO_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  struct StreamGuard {
+    cudaStream_t s;
+    ~StreamGuard() { cudaStreamDestroy(s); }
+  } guard{st};
+  DevBuf raw;
+  PICO_TRY(alloc(raw, n * sdim * sizeof(T)));
+  PICO_TRY(stage_points(h_pts, n, sdim, stride, raw.as<T>(), st));
+  PICO_CUDA(cudaMalloc(&t->d_indices, n * sizeof(int32_t)));
+  PICO_CUDA(cudaMalloc(&t->d_root_box, 2 * sdim * sizeof(T)));
+  PICO_CUDA(cudaMalloc(&t->d_nodes, n_nodes * sizeof(NodeT)));
+  PICO_CUDA(cudaMemcpyAsync(t->d_indices, indices, n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  PICO_CUDA(cudaMemcpyAsync(t->d_root_box, root_box, 2 * sdim * sizeof(T), cudaMemcpyHostToDevice, st));
+  PICO_CUDA(cudaMemcpyAsync(t->d_nodes, nodes, n_nodes * sizeof(NodeT), cudaMemcpyHostToDevice, st));
+  for (int d = 0; d < sdim && d < 4; ++d) {
+    t->root_box_host[d] = (double)root_box[d];
+    t->root_box_host[4 + d] = (double)root_box[sdim + d];
+  }
+  PICO_TRY(finalize_storage<T>(t, raw.as<T>(), st));
+  PICO_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+template int build_tree<float>(pico_b200_tree*, const float*, size_t, int, int, size_t, const float*, const float*);
+template int build_tree<double>(pico_b200_tree*, const double*, size_t, int, int, size_t, const double*,
+                                const double*);
+template int upload_tree<float>(pico_b200_tree*, const float*, size_t, const void*, size_t, const int32_t*,
+                                const float*);
+template int upload_tree<double>(pico_b200_tree*, const double*, size_t, const void*, size_t, const int32_t*,
+                                 const double*);
+
+}  // namespace pico

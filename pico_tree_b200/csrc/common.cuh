@@ -1,0 +1,128 @@
+// common.cuh — shared declarations of libpico_b200.so (host + device).
+//
+// Data layout in HBM:
+//   nodes   : Node<T>[n_nodes], pre-order, 16 B (f32) / 32 B (f64) records
+//   pts4    : Vec4<T>[n] for sdim <= 3, LEAF ORDER, .w carries the original index
+//   ptsN    : T[n * sdim] row-major for sdim > 3, LEAF ORDER
+//   indices : int32[n], leaf position -> original index (kd_tree_data::indices)
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/pico_b200.h"
+
+namespace pico {
+
+// ---------------------------------------------------------------- errors
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+
+#define PICO_CUDA(expr)                                                                         \
+  do {                                                                                          \
+    cudaError_t e__ = (expr);                                                                   \
+    if (e__ != cudaSuccess) {                                                                   \
+      return ::pico::fail(                                                                      \
+          e__ == cudaErrorMemoryAllocation ? PICO_B200_ERR_OUT_OF_MEMORY : PICO_B200_ERR_CUDA,  \
+          std::string(#expr) + ": " + cudaGetErrorString(e__));                                 \
+    }                                                                                           \
+  } while (0)
+
+#define PICO_TRY(expr)           \
+  do {                           \
+    int rc__ = (expr);           \
+    if (rc__ != 0) return rc__;  \
+  } while (0)
+
+// ---------------------------------------------------------------- node / point records
+template <typename T>
+struct NodeOf;
+template <>
+struct NodeOf<float> {
+  using type = pico_b200_node_f32;
+};
+template <>
+struct NodeOf<double> {
+  using type = pico_b200_node_f64;
+};
+
+template <typename T>
+struct Vec4Of;
+template <>
+struct Vec4Of<float> {
+  using type = float4;
+};
+template <>
+struct Vec4Of<double> {
+  using type = double4;
+};
+
+template <typename T>
+struct Neighbor {
+  int32_t index;
+  T distance;
+};
+static_assert(sizeof(Neighbor<float>) == 8, "neighbor<int,float> is 8 bytes");
+static_assert(sizeof(Neighbor<double>) == 16, "neighbor<int,double> is 16 bytes");
+
+template <typename T>
+struct Limits;
+template <>
+struct Limits<float> {
+  __host__ __device__ static constexpr float max() { return 3.402823466e+38f; }
+};
+template <>
+struct Limits<double> {
+  __host__ __device__ static constexpr double max() { return 1.7976931348623158e+308; }
+};
+
+constexpr int kMaxPackedDim = 3;   // sdim <= 3 uses the Vec4 layout
+constexpr int kLocalStack = 64;    // traversal stack kept in per-thread local memory
+constexpr int kSmBlocks = 148;     // B200 SM count (grid sizing; queried at runtime too)
+
+}  // namespace pico
+
+// ---------------------------------------------------------------- the handle
+struct pico_b200_tree {
+  int device = 0;
+  int scalar = PICO_B200_F32;
+  int metric = PICO_B200_METRIC_L2_SQUARED;
+  size_t n = 0, sdim = 0, n_nodes = 0, n_leaves = 0, height = 0;
+  void* d_nodes = nullptr;
+  void* d_pts = nullptr;       // pts4 or ptsN (see above)
+  int32_t* d_indices = nullptr;
+  void* d_root_box = nullptr;  // min[sdim] then max[sdim], device copy
+  double root_box_host[2 * 4] = {0};  // first min(sdim,4) dims, as double, for query ordering
+  double build_ms = 0.0;
+  size_t device_bytes = 0;
+  int sm_count = pico::kSmBlocks;
+  size_t scalar_size() const { return scalar == PICO_B200_F64 ? 8 : 4; }
+  size_t node_size() const { return scalar == PICO_B200_F64 ? 32 : 16; }
+  bool packed() const { return sdim <= (size_t)pico::kMaxPackedDim; }
+  size_t pts_bytes() const { return packed() ? n * 4 * scalar_size() : n * sdim * scalar_size(); }
+};
+
+namespace pico {
+
+// build.cu
+template <typename T>
+int build_tree(pico_b200_tree* t, const T* h_pts, size_t stride, int rule, int stop_kind, size_t stop_value,
+               const T* bounds_min, const T* bounds_max);
+template <typename T>
+int upload_tree(pico_b200_tree* t, const T* h_pts, size_t stride, const void* nodes, size_t n_nodes,
+                const int32_t* indices, const T* root_box);
+
+// search.cu
+template <typename T>
+int knn_batch(const pico_b200_tree* t, const T* q, size_t nq, size_t stride, size_t k, double e, Neighbor<T>* out,
+              unsigned flags, pico_b200_search_stats* stats);
+template <typename T>
+int radius_batch(const pico_b200_tree* t, const T* q, size_t nq, size_t stride, double radius, double e,
+                 uint64_t* offsets_out, void** out, unsigned flags, pico_b200_search_stats* stats);
+template <typename T>
+int box_batch(const pico_b200_tree* t, const T* mins, const T* maxs, size_t nb, size_t stride,
+              uint64_t* offsets_out, int32_t** out, unsigned flags, pico_b200_search_stats* stats);
+
+}  // namespace pico

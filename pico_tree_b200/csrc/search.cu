@@ -1,0 +1,848 @@
+// search.cu — batched knn / radius / box kernels and their host drivers.
+//
+// Batch entry points replace the per-query loops of the reference
+// (src/pyco_tree/pico_tree/_pyco_tree/kd_tree.hpp:117-268, examples/benchmark/bm_pico_kd_tree.cpp:63-78).
+// Two traversal families (traverse.cuh / traverse_warp.cuh):
+//   * thread-per-query for sdim <= 3 and k <= 16: queries are Z-ordered first, so the 32
+//     threads of a warp walk almost the same root-to-leaf path — node and leaf loads become
+//     warp-wide broadcasts served by L1/L2;
+//   * warp-per-query for everything else (any sdim, any k), also selectable with
+//     PICO_B200_WARP_PER_QUERY for comparison.
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <vector>
+
+#include "traverse_warp.cuh"
+
+namespace pico {
+namespace {
+
+constexpr int kThreadsPerBlock = 128;
+constexpr int kWarpsPerBlock = 8;
+
+// ------------------------------------------------------------------ query ordering
+// 30-bit (3 x 10) Morton code of the query inside the tree's root box; queries outside are
+// clamped. Only the first min(sdim, 3) coordinates take part.
+__device__ __forceinline__ uint32_t spread10(uint32_t v) {
+  v &= 0x3ffu;
+  v = (v | (v << 16)) & 0x030000ffu;
+  v = (v | (v << 8)) & 0x0300f00fu;
+  v = (v | (v << 4)) & 0x030c30c3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
+
+template <typename T>
+__global__ void morton_kernel(const T* __restrict__ q, size_t stride, uint32_t nq, int dims, double3 lo, double3 inv,
+                              uint32_t* __restrict__ codes, uint32_t* __restrict__ ids) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq) return;
+  const T* p = q + (size_t)i * stride;
+  const double l[3] = {lo.x, lo.y, lo.z}, s[3] = {inv.x, inv.y, inv.z};
+  uint32_t code = 0;
+  for (int j = 0; j < dims; ++j) {
+    double f = ((double)p[j] - l[j]) * s[j];
+    f = f < 0.0 ? 0.0 : (f > 1023.0 ? 1023.0 : f);
+    code |= spread10((uint32_t)f) << j;
+  }
+  codes[i] = code;
+  ids[i] = i;
+}
+
+// ------------------------------------------------------------------ thread-per-query kernels
+template <typename T>
+struct KnnArgs {
+  const typename NodeOf<T>::type* nodes;
+  const typename Vec4Of<T>::type* pts4;
+  const T* rows;
+  const int32_t* indices;
+  const T* q;
+  size_t q_stride;
+  uint32_t nq;
+  const uint32_t* perm;  // nullptr = identity
+  Neighbor<T>* out;
+  int k, sdim, metric, approx;
+  T e_inv;
+  // deep-tree workspace (GlobalStack) or warp stacks
+  void* ws;
+  size_t ws_stride, ws_depth;
+};
+
+template <typename T, int DIM, int KMAX, bool FAST, bool DEEP>
+__global__ void __launch_bounds__(kThreadsPerBlock) knn_thread_kernel(KnnArgs<T> a) {
+  const size_t total = (size_t)gridDim.x * blockDim.x;
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (size_t slot = tid; slot < a.nq; slot += total) {
+    const uint32_t qi = a.perm ? a.perm[slot] : (uint32_t)slot;
+    T q[DIM];
+    const T* qp = a.q + (size_t)qi * a.q_stride;
+#pragma unroll
+    for (int j = 0; j < DIM; ++j) q[j] = qp[j];
+    Neighbor<T>* out = a.out + (size_t)qi * a.k;
+    if (KMAX == 1) {
+      VisitNn<T> vis;
+      if (DEEP) {
+        GlobalStack<T, DIM> st;
+        st.stride = a.ws_stride;
+        st.depth = a.ws_depth;
+        st.node = static_cast<uint32_t*>(a.ws) + tid;
+        st.dist = reinterpret_cast<T*>(static_cast<uint32_t*>(a.ws) + a.ws_stride * a.ws_depth) + tid;
+        st.off = st.dist + a.ws_stride * a.ws_depth;
+        traverse_packed<T, DIM, FAST>(a.nodes, a.pts4, q, a.metric, a.approx != 0, a.e_inv, st, vis);
+      } else {
+        LocalStack<T, DIM, kLocalStack> st;
+        traverse_packed<T, DIM, FAST>(a.nodes, a.pts4, q, a.metric, a.approx != 0, a.e_inv, st, vis);
+      }
+      out->index = vis.idx;
+      out->distance = vis.best;
+    } else {
+      VisitKnn<T, KMAX> vis;
+      vis.init(a.k);
+      if (DEEP) {
+        GlobalStack<T, DIM> st;
+        st.stride = a.ws_stride;
+        st.depth = a.ws_depth;
+        st.node = static_cast<uint32_t*>(a.ws) + tid;
+        st.dist = reinterpret_cast<T*>(static_cast<uint32_t*>(a.ws) + a.ws_stride * a.ws_depth) + tid;
+        st.off = st.dist + a.ws_stride * a.ws_depth;
+        traverse_packed<T, DIM, FAST>(a.nodes, a.pts4, q, a.metric, a.approx != 0, a.e_inv, st, vis);
+      } else {
+        LocalStack<T, DIM, kLocalStack> st;
+        traverse_packed<T, DIM, FAST>(a.nodes, a.pts4, q, a.metric, a.approx != 0, a.e_inv, st, vis);
+      }
+#pragma unroll
+      for (int i = 0; i < KMAX; ++i) {
+        if (i < a.k) {
+          out[i].index = vis.id[i];
+          out[i].distance = vis.d[i];
+        }
+      }
+    }
+  }
+}
+
+template <typename T>
+struct RadiusArgs {
+  KnnArgs<T> base;        // out unused
+  T radius;               // already scaled by 1/e for the approximate visitor
+  uint32_t* counts;       // pass 1: per-query hit count
+  const uint64_t* offsets;  // pass 2: exclusive scan of counts
+  Neighbor<T>* hits;      // pass 2: packed results
+};
+
+template <typename T, int DIM, bool FILL, bool DEEP>
+__global__ void __launch_bounds__(kThreadsPerBlock) radius_thread_kernel(RadiusArgs<T> r) {
+  const KnnArgs<T>& a = r.base;
+  const size_t total = (size_t)gridDim.x * blockDim.x;
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (size_t slot = tid; slot < a.nq; slot += total) {
+    const uint32_t qi = a.perm ? a.perm[slot] : (uint32_t)slot;
+    T q[DIM];
+    const T* qp = a.q + (size_t)qi * a.q_stride;
+#pragma unroll
+    for (int j = 0; j < DIM; ++j) q[j] = qp[j];
+    GlobalStack<T, DIM> gst;
+    if (DEEP) {
+      gst.stride = a.ws_stride;
+      gst.depth = a.ws_depth;
+      gst.node = static_cast<uint32_t*>(a.ws) + tid;
+      gst.dist = reinterpret_cast<T*>(static_cast<uint32_t*>(a.ws) + a.ws_stride * a.ws_depth) + tid;
+      gst.off = gst.dist + a.ws_stride * a.ws_depth;
+    }
+    LocalStack<T, DIM, DEEP ? 1 : kLocalStack> lst;
+    if (FILL) {
+      VisitRadiusFill<T> vis;
+      vis.radius = r.radius;
+      vis.out = r.hits + r.offsets[qi];
+      if (DEEP)
+        traverse_packed<T, DIM, false>(a.nodes, a.pts4, q, a.metric, a.approx != 0, a.e_inv, gst, vis);
+      else
+        traverse_packed<T, DIM, false>(a.nodes, a.pts4, q, a.metric, a.approx != 0, a.e_inv, lst, vis);
+    } else {
+      VisitRadiusCount<T> vis;
+      vis.radius = r.radius;
+      if (DEEP)
+        traverse_packed<T, DIM, false>(a.nodes, a.pts4, q, a.metric, a.approx != 0, a.e_inv, gst, vis);
+      else
+        traverse_packed<T, DIM, false>(a.nodes, a.pts4, q, a.metric, a.approx != 0, a.e_inv, lst, vis);
+      r.counts[qi] = vis.count;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ warp-per-query kernels
+// dynamic shared memory per warp: query[sdim] + offsets[sdim]
+template <typename T, bool PACKED, bool REGLIST>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) knn_warp_kernel(KnnArgs<T> a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* smem = reinterpret_cast<T*>(smem_raw);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  T* sq = smem + (size_t)w * 2 * a.sdim;
+  T* so = sq + a.sdim;
+  const size_t warp_global = (size_t)blockIdx.x * kWarpsPerBlock + w;
+  const size_t total_warps = (size_t)gridDim.x * kWarpsPerBlock;
+  WarpFrame<T>* stack = static_cast<WarpFrame<T>*>(a.ws) + warp_global * a.ws_depth;
+  PointSet<T, PACKED> ps{a.pts4, a.rows, a.indices, a.sdim};
+  for (size_t slot = warp_global; slot < a.nq; slot += total_warps) {
+    const uint32_t qi = a.perm ? a.perm[slot] : (uint32_t)slot;
+    const T* qp = a.q + (size_t)qi * a.q_stride;
+    __syncwarp();
+    for (int j = lane; j < a.sdim; j += 32) {
+      sq[j] = qp[j];
+      so[j] = T(0);
+    }
+    __syncwarp();
+    Neighbor<T>* row = a.out + (size_t)qi * a.k;
+    if (REGLIST) {
+      WarpVisitKnn<T, WarpKnnReg<T>> vis;
+      vis.list.init(a.k);
+      traverse_warp<T, PACKED>(a.nodes, ps, sq, so, stack, a.metric, a.approx != 0, a.e_inv, vis);
+      vis.list.store(row);
+    } else {
+      WarpVisitKnn<T, WarpKnnMem<T>> vis;
+      vis.list.init(row, a.k);
+      traverse_warp<T, PACKED>(a.nodes, ps, sq, so, stack, a.metric, a.approx != 0, a.e_inv, vis);
+    }
+  }
+}
+
+template <typename T, bool PACKED>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) radius_warp_kernel(RadiusArgs<T> r) {
+  const KnnArgs<T>& a = r.base;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* smem = reinterpret_cast<T*>(smem_raw);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  T* sq = smem + (size_t)w * 2 * a.sdim;
+  T* so = sq + a.sdim;
+  const size_t warp_global = (size_t)blockIdx.x * kWarpsPerBlock + w;
+  const size_t total_warps = (size_t)gridDim.x * kWarpsPerBlock;
+  WarpFrame<T>* stack = static_cast<WarpFrame<T>*>(a.ws) + warp_global * a.ws_depth;
+  PointSet<T, PACKED> ps{a.pts4, a.rows, a.indices, a.sdim};
+  for (size_t slot = warp_global; slot < a.nq; slot += total_warps) {
+    const uint32_t qi = a.perm ? a.perm[slot] : (uint32_t)slot;
+    const T* qp = a.q + (size_t)qi * a.q_stride;
+    __syncwarp();
+    for (int j = lane; j < a.sdim; j += 32) {
+      sq[j] = qp[j];
+      so[j] = T(0);
+    }
+    __syncwarp();
+    WarpVisitRadius<T> vis;
+    vis.radius = r.radius;
+    vis.out = r.hits ? r.hits + r.offsets[qi] : nullptr;
+    traverse_warp<T, PACKED>(a.nodes, ps, sq, so, stack, a.metric, a.approx != 0, a.e_inv, vis);
+    if (!r.hits && lane == 0) r.counts[qi] = vis.count;
+  }
+}
+
+template <typename T>
+struct BoxArgs {
+  const typename NodeOf<T>::type* nodes;
+  const typename Vec4Of<T>::type* pts4;
+  const T* rows;
+  const int32_t* indices;
+  const T* root_box;
+  const T* mins;
+  const T* maxs;
+  size_t stride;
+  uint32_t nb;
+  int sdim;
+  uint32_t* counts;
+  const uint64_t* offsets;
+  int32_t* hits;
+  void* ws;  // per warp: BoxFrame[depth] + T saved[depth]
+  size_t ws_depth;
+};
+
+// dynamic shared memory per warp: qmin[sdim] qmax[sdim] box[2*sdim]
+template <typename T, bool PACKED>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) box_warp_kernel(BoxArgs<T> a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* smem = reinterpret_cast<T*>(smem_raw);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  T* qmin = smem + (size_t)w * 4 * a.sdim;
+  T* qmax = qmin + a.sdim;
+  T* sbox = qmax + a.sdim;
+  const size_t warp_global = (size_t)blockIdx.x * kWarpsPerBlock + w;
+  const size_t total_warps = (size_t)gridDim.x * kWarpsPerBlock;
+  const size_t per_warp = a.ws_depth * (sizeof(BoxFrame) + sizeof(T));
+  unsigned char* wsb = static_cast<unsigned char*>(a.ws) + warp_global * per_warp;
+  BoxFrame* stack = reinterpret_cast<BoxFrame*>(wsb);
+  T* saved = reinterpret_cast<T*>(wsb + a.ws_depth * sizeof(BoxFrame));
+  PointSet<T, PACKED> ps{a.pts4, a.rows, a.indices, a.sdim};
+  for (size_t bi = warp_global; bi < a.nb; bi += total_warps) {
+    __syncwarp();
+    for (int j = lane; j < a.sdim; j += 32) {
+      qmin[j] = a.mins[bi * a.stride + j];
+      qmax[j] = a.maxs[bi * a.stride + j];
+    }
+    for (int j = lane; j < 2 * a.sdim; j += 32) sbox[j] = a.root_box[j];
+    __syncwarp();
+    int32_t* out = a.hits ? a.hits + a.offsets[bi] : nullptr;
+    const uint32_t c = traverse_box_warp<T, PACKED>(a.nodes, ps, a.indices, qmin, qmax, sbox, stack, saved, out);
+    if (!a.hits && lane == 0) a.counts[bi] = c;
+  }
+}
+
+// ------------------------------------------------------------------ host helpers
+struct CallCtx {
+  cudaStream_t st = nullptr;
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  std::vector<void*> async_allocs;
+  int init(int device) {
+    PICO_CUDA(cudaSetDevice(device));
+    PICO_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    for (auto& e : ev) PICO_CUDA(cudaEventCreate(&e));
+    return 0;
+  }
+  int alloc(void** p, size_t bytes) {
+    PICO_CUDA(cudaMallocAsync(p, bytes ? bytes : 16, st));
+    async_allocs.push_back(*p);
+    return 0;
+  }
+  ~CallCtx() {
+    if (st) {
+      for (void* p : async_allocs) cudaFreeAsync(p, st);
+      cudaStreamSynchronize(st);
+      cudaStreamDestroy(st);
+    }
+    for (auto& e : ev)
+      if (e) cudaEventDestroy(e);
+  }
+};
+
+template <typename T>
+int stage_queries(CallCtx& c, const T* q, size_t nq, size_t stride, size_t sdim, bool on_device, const T** d_q,
+                  size_t* d_stride) {
+  if (on_device) {
+    *d_q = q;
+    *d_stride = stride;
+    return 0;
+  }
+  T* buf = nullptr;
+  PICO_TRY(c.alloc(reinterpret_cast<void**>(&buf), nq * sdim * sizeof(T)));
+  if (nq)
+    PICO_CUDA(cudaMemcpy2DAsync(buf, sdim * sizeof(T), q, stride * sizeof(T), sdim * sizeof(T), nq,
+                                cudaMemcpyHostToDevice, c.st));
+  *d_q = buf;
+  *d_stride = sdim;
+  return 0;
+}
+
+// Z-order permutation of the batch (device). Returns nullptr in *perm for tiny batches.
+template <typename T>
+int make_perm(CallCtx& c, const pico_b200_tree* t, const T* d_q, size_t stride, size_t nq, unsigned flags,
+              uint32_t** perm) {
+  *perm = nullptr;
+  if ((flags & PICO_B200_NO_REORDER) || nq < 2048) return 0;
+  const int dims = (int)std::min<size_t>(t->sdim, 3);
+  double lo[3] = {0, 0, 0}, inv[3] = {0, 0, 0};
+  for (int j = 0; j < dims; ++j) {
+    lo[j] = t->root_box_host[j];
+    const double ext = t->root_box_host[4 + j] - t->root_box_host[j];
+    inv[j] = ext > 0 ? 1023.999 / ext : 0.0;
+  }
+  uint32_t *codes = nullptr, *ids = nullptr, *codes2 = nullptr, *ids2 = nullptr;
+  PICO_TRY(c.alloc(reinterpret_cast<void**>(&codes), nq * 4));
+  PICO_TRY(c.alloc(reinterpret_cast<void**>(&ids), nq * 4));
+  PICO_TRY(c.alloc(reinterpret_cast<void**>(&codes2), nq * 4));
+  PICO_TRY(c.alloc(reinterpret_cast<void**>(&ids2), nq * 4));
+  morton_kernel<T><<<(unsigned)((nq + 255) / 256), 256, 0, c.st>>>(d_q, stride, (uint32_t)nq, dims,
+                                                                    make_double3(lo[0], lo[1], lo[2]),
+                                                                    make_double3(inv[0], inv[1], inv[2]), codes, ids);
+  PICO_CUDA(cudaGetLastError());
+  size_t tmp_bytes = 0;
+  PICO_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, codes, codes2, ids, ids2, (int)nq, 0, 30, c.st));
+  void* tmp = nullptr;
+  PICO_TRY(c.alloc(&tmp, tmp_bytes));
+  PICO_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, codes, codes2, ids, ids2, (int)nq, 0, 30, c.st));
+  *perm = ids2;
+  return 0;
+}
+
+template <typename T>
+void fill_base(KnnArgs<T>& a, const pico_b200_tree* t, const T* d_q, size_t d_stride, size_t nq, const uint32_t* perm,
+               double e) {
+  a.nodes = static_cast<const typename NodeOf<T>::type*>(t->d_nodes);
+  a.pts4 = t->packed() ? static_cast<const typename Vec4Of<T>::type*>(t->d_pts) : nullptr;
+  a.rows = t->packed() ? nullptr : static_cast<const T*>(t->d_pts);
+  a.indices = t->d_indices;
+  a.q = d_q;
+  a.q_stride = d_stride;
+  a.nq = (uint32_t)nq;
+  a.perm = perm;
+  a.out = nullptr;
+  a.k = 0;
+  a.sdim = (int)t->sdim;
+  a.metric = t->metric;
+  a.approx = e > 0;
+  a.e_inv = e > 0 ? T(1.0) / T(e) : T(1.0);  // search_visitor.hpp:173,216,265
+  a.ws = nullptr;
+  a.ws_stride = a.ws_depth = 0;
+}
+
+// thread-per-query launch geometry + optional deep-tree workspace
+template <typename T>
+int thread_geometry(CallCtx& c, const pico_b200_tree* t, KnnArgs<T>& a, int dim, bool* deep, unsigned* blocks) {
+  *deep = t->height >= (size_t)kLocalStack;
+  size_t threads = ((size_t)a.nq + kThreadsPerBlock - 1) / kThreadsPerBlock * kThreadsPerBlock;
+  if (*deep) {
+    const size_t depth = t->height + 1;
+    const size_t per_thread = depth * (4 + sizeof(T) * (1 + dim));
+    const size_t budget = (size_t)2 << 30;
+    size_t max_threads = std::max<size_t>(budget / per_thread / kThreadsPerBlock, 1) * kThreadsPerBlock;
+    max_threads = std::min<size_t>(max_threads, (size_t)t->sm_count * 2048);
+    threads = std::min(threads, max_threads);
+    a.ws_stride = threads;
+    a.ws_depth = depth;
+    PICO_TRY(c.alloc(&a.ws, threads * per_thread));
+  }
+  *blocks = (unsigned)std::max<size_t>(threads / kThreadsPerBlock, 1);
+  return 0;
+}
+
+template <typename T>
+int warp_geometry(CallCtx& c, const pico_b200_tree* t, size_t items, size_t frame_bytes, size_t smem_per_warp,
+                  void** ws, size_t* depth, unsigned* blocks, size_t* smem) {
+  *depth = t->height + 2;
+  size_t warps = std::min<size_t>((items + 0), (size_t)t->sm_count * 64);
+  size_t nblocks = std::max<size_t>((warps + kWarpsPerBlock - 1) / kWarpsPerBlock, 1);
+  *smem = smem_per_warp * kWarpsPerBlock;
+  if (*smem > 200 * 1024) return fail(PICO_B200_ERR_UNSUPPORTED, "spatial dimension too large for shared memory");
+  *blocks = (unsigned)nblocks;
+  PICO_TRY(c.alloc(ws, nblocks * kWarpsPerBlock * *depth * frame_bytes));
+  return 0;
+}
+
+template <typename T, int DIM, bool FAST, bool DEEP>
+void launch_knn_thread_k(const KnnArgs<T>& a, unsigned blocks, cudaStream_t st) {
+  if (a.k == 1)
+    knn_thread_kernel<T, DIM, 1, FAST, DEEP><<<blocks, kThreadsPerBlock, 0, st>>>(a);
+  else if (a.k <= 4)
+    knn_thread_kernel<T, DIM, 4, FAST, DEEP><<<blocks, kThreadsPerBlock, 0, st>>>(a);
+  else if (a.k <= 8)
+    knn_thread_kernel<T, DIM, 8, FAST, DEEP><<<blocks, kThreadsPerBlock, 0, st>>>(a);
+  else
+    knn_thread_kernel<T, DIM, 16, FAST, DEEP><<<blocks, kThreadsPerBlock, 0, st>>>(a);
+}
+
+template <typename T, int DIM>
+void launch_knn_thread(const KnnArgs<T>& a, bool fast, bool deep, unsigned blocks, cudaStream_t st) {
+  if (fast) {
+    if (deep)
+      launch_knn_thread_k<T, DIM, true, true>(a, blocks, st);
+    else
+      launch_knn_thread_k<T, DIM, true, false>(a, blocks, st);
+  } else {
+    if (deep)
+      launch_knn_thread_k<T, DIM, false, true>(a, blocks, st);
+    else
+      launch_knn_thread_k<T, DIM, false, false>(a, blocks, st);
+  }
+}
+
+float elapsed(cudaEvent_t a, cudaEvent_t b) {
+  float ms = 0;
+  cudaEventElapsedTime(&ms, a, b);
+  return ms;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ knn
+template <typename T>
+int knn_batch(const pico_b200_tree* t, const T* q, size_t nq, size_t stride, size_t k, double e, Neighbor<T>* out,
+              unsigned flags, pico_b200_search_stats* stats) {
+  if (nq == 0 || k == 0) return 0;
+  if (nq > 0xfffffff0u) return fail(PICO_B200_ERR_UNSUPPORTED, "more than 2^32-16 queries in one call");
+  if (k > 0x7fffffffu) return fail(PICO_B200_ERR_INVALID_ARGUMENT, "k too large");
+  const bool on_device = flags & PICO_B200_DEVICE_POINTERS;
+  CallCtx c;
+  PICO_TRY(c.init(t->device));
+  PICO_CUDA(cudaEventRecord(c.ev[0], c.st));
+  const T* d_q = nullptr;
+  size_t d_stride = 0;
+  PICO_TRY(stage_queries(c, q, nq, stride, t->sdim, on_device, &d_q, &d_stride));
+  Neighbor<T>* d_out = out;
+  if (!on_device) PICO_TRY(c.alloc(reinterpret_cast<void**>(&d_out), nq * k * sizeof(Neighbor<T>)));
+  PICO_CUDA(cudaEventRecord(c.ev[1], c.st));
+  uint32_t* perm = nullptr;
+  PICO_TRY(make_perm(c, t, d_q, d_stride, nq, flags, &perm));
+  PICO_CUDA(cudaEventRecord(c.ev[2], c.st));
+
+  KnnArgs<T> a;
+  fill_base(a, t, d_q, d_stride, nq, perm, e);
+  a.out = d_out;
+  a.k = (int)k;
+  uint64_t launches = perm ? 3 : 0;
+  const bool use_thread = t->packed() && k <= 16 && !(flags & PICO_B200_WARP_PER_QUERY);
+  if (use_thread) {
+    bool deep;
+    unsigned blocks;
+    PICO_TRY(thread_geometry(c, t, a, (int)t->sdim, &deep, &blocks));
+    const bool fast = t->metric == PICO_B200_METRIC_L2_SQUARED && !(e > 0);
+    switch (t->sdim) {
+      case 1:
+        launch_knn_thread<T, 1>(a, fast, deep, blocks, c.st);
+        break;
+      case 2:
+        launch_knn_thread<T, 2>(a, fast, deep, blocks, c.st);
+        break;
+      default:
+        launch_knn_thread<T, 3>(a, fast, deep, blocks, c.st);
+        break;
+    }
+  } else {
+    unsigned blocks;
+    size_t smem;
+    PICO_TRY(warp_geometry<T>(c, t, nq, sizeof(WarpFrame<T>), 2 * t->sdim * sizeof(T), &a.ws, &a.ws_depth, &blocks,
+                              &smem));
+    const bool reg = k <= 32;
+#define PICO_LAUNCH_WARP(P, R)                                                                                  \
+  do {                                                                                                          \
+    if (smem > 48 * 1024)                                                                                       \
+      PICO_CUDA(cudaFuncSetAttribute(knn_warp_kernel<T, P, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                     (int)smem));                                                               \
+    knn_warp_kernel<T, P, R><<<blocks, kWarpsPerBlock * 32, smem, c.st>>>(a);                                   \
+  } while (0)
+    if (t->packed()) {
+      if (reg)
+        PICO_LAUNCH_WARP(true, true);
+      else
+        PICO_LAUNCH_WARP(true, false);
+    } else {
+      if (reg)
+        PICO_LAUNCH_WARP(false, true);
+      else
+        PICO_LAUNCH_WARP(false, false);
+    }
+#undef PICO_LAUNCH_WARP
+  }
+  PICO_CUDA(cudaGetLastError());
+  ++launches;
+  PICO_CUDA(cudaEventRecord(c.ev[3], c.st));
+  if (!on_device)
+    PICO_CUDA(cudaMemcpyAsync(out, d_out, nq * k * sizeof(Neighbor<T>), cudaMemcpyDeviceToHost, c.st));
+  PICO_CUDA(cudaEventRecord(c.ev[4], c.st));
+  PICO_CUDA(cudaStreamSynchronize(c.st));
+  if (stats) {
+    stats->h2d_ms = elapsed(c.ev[0], c.ev[1]);
+    stats->reorder_ms = elapsed(c.ev[1], c.ev[2]);
+    stats->kernel_ms = elapsed(c.ev[2], c.ev[3]);
+    stats->d2h_ms = elapsed(c.ev[3], c.ev[4]);
+    stats->kernel_launches = launches;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------ radius
+namespace {
+
+// Sort every query's hits by distance: records are {int32 index, f32 distance}; read as
+// little-endian uint64 the distance is the high word, and non-negative floats order like
+// their bit patterns, so one segmented radix sort of 64-bit keys sorts by (distance, index).
+int sort_hits_f32(CallCtx& c, Neighbor<float>* hits, size_t total, const uint64_t* d_offsets, size_t nq) {
+  if (total == 0) return 0;
+  if (total > 0x7fffffffu) return fail(PICO_B200_ERR_UNSUPPORTED, "too many hits to sort in one call");
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(hits);
+  unsigned long long* keys2 = nullptr;
+  PICO_TRY(c.alloc(reinterpret_cast<void**>(&keys2), total * 8));
+  size_t tmp_bytes = 0;
+  cub::DoubleBuffer<unsigned long long> db(keys, keys2);
+  const unsigned long long* offs = reinterpret_cast<const unsigned long long*>(d_offsets);
+  PICO_CUDA(cub::DeviceSegmentedSort::SortKeys(nullptr, tmp_bytes, db, (int)total, (int)nq, offs, offs + 1, c.st));
+  void* tmp = nullptr;
+  PICO_TRY(c.alloc(&tmp, tmp_bytes));
+  PICO_CUDA(cub::DeviceSegmentedSort::SortKeys(tmp, tmp_bytes, db, (int)total, (int)nq, offs, offs + 1, c.st));
+  if (db.Current() != keys)
+    PICO_CUDA(cudaMemcpyAsync(keys, db.Current(), total * 8, cudaMemcpyDeviceToDevice, c.st));
+  return 0;
+}
+
+// f64 records are 16 bytes {int32, pad, f64}: sort (distance bits, index) pairs.
+__global__ void split_hits_f64(const Neighbor<double>* hits, size_t n, unsigned long long* keys, int* vals) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  keys[i] = (unsigned long long)__double_as_longlong(hits[i].distance);
+  vals[i] = hits[i].index;
+}
+__global__ void join_hits_f64(Neighbor<double>* hits, size_t n, const unsigned long long* keys, const int* vals) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  hits[i].index = vals[i];
+  hits[i].distance = __longlong_as_double((long long)keys[i]);
+}
+
+int sort_hits_f64(CallCtx& c, Neighbor<double>* hits, size_t total, const uint64_t* d_offsets, size_t nq) {
+  if (total == 0) return 0;
+  if (total > 0x7fffffffu) return fail(PICO_B200_ERR_UNSUPPORTED, "too many hits to sort in one call");
+  unsigned long long *k1 = nullptr, *k2 = nullptr;
+  int *v1 = nullptr, *v2 = nullptr;
+  PICO_TRY(c.alloc(reinterpret_cast<void**>(&k1), total * 8));
+  PICO_TRY(c.alloc(reinterpret_cast<void**>(&k2), total * 8));
+  PICO_TRY(c.alloc(reinterpret_cast<void**>(&v1), total * 4));
+  PICO_TRY(c.alloc(reinterpret_cast<void**>(&v2), total * 4));
+  split_hits_f64<<<(unsigned)((total + 255) / 256), 256, 0, c.st>>>(hits, total, k1, v1);
+  cub::DoubleBuffer<unsigned long long> dk(k1, k2);
+  cub::DoubleBuffer<int> dv(v1, v2);
+  const unsigned long long* offs = reinterpret_cast<const unsigned long long*>(d_offsets);
+  size_t tmp_bytes = 0;
+  PICO_CUDA(
+      cub::DeviceSegmentedSort::SortPairs(nullptr, tmp_bytes, dk, dv, (int)total, (int)nq, offs, offs + 1, c.st));
+  void* tmp = nullptr;
+  PICO_TRY(c.alloc(&tmp, tmp_bytes));
+  PICO_CUDA(cub::DeviceSegmentedSort::SortPairs(tmp, tmp_bytes, dk, dv, (int)total, (int)nq, offs, offs + 1, c.st));
+  join_hits_f64<<<(unsigned)((total + 255) / 256), 256, 0, c.st>>>(hits, total, dk.Current(), dv.Current());
+  PICO_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int sort_hits(CallCtx& c, Neighbor<float>* h, size_t total, const uint64_t* o, size_t nq) {
+  return sort_hits_f32(c, h, total, o, nq);
+}
+int sort_hits(CallCtx& c, Neighbor<double>* h, size_t total, const uint64_t* o, size_t nq) {
+  return sort_hits_f64(c, h, total, o, nq);
+}
+
+__global__ void widen_counts(const uint32_t* c, size_t n, uint64_t* out) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = c[i];
+}
+
+// counts[n] (u32) -> offsets[n+1] (u64, exclusive scan, last = total)
+int scan_counts(CallCtx& c, const uint32_t* counts, size_t n, uint64_t** d_offsets) {
+  uint64_t* wide = nullptr;
+  uint64_t* offs = nullptr;
+  PICO_TRY(c.alloc(reinterpret_cast<void**>(&wide), (n + 1) * 8));
+  PICO_TRY(c.alloc(reinterpret_cast<void**>(&offs), (n + 1) * 8));
+  PICO_CUDA(cudaMemsetAsync(wide, 0, (n + 1) * 8, c.st));
+  widen_counts<<<(unsigned)((n + 255) / 256), 256, 0, c.st>>>(counts, n, wide);
+  size_t tmp_bytes = 0;
+  PICO_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, wide, offs, (int)(n + 1), c.st));
+  void* tmp = nullptr;
+  PICO_TRY(c.alloc(&tmp, tmp_bytes));
+  PICO_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, wide, offs, (int)(n + 1), c.st));
+  *d_offsets = offs;
+  return 0;
+}
+
+template <typename T, bool FILL>
+int launch_radius(CallCtx& c, const pico_b200_tree* t, RadiusArgs<T>& r, unsigned flags) {
+  KnnArgs<T>& a = r.base;
+  const bool use_thread = t->packed() && !(flags & PICO_B200_WARP_PER_QUERY);
+  if (use_thread) {
+    bool deep;
+    unsigned blocks;
+    PICO_TRY(thread_geometry(c, t, a, (int)t->sdim, &deep, &blocks));
+#define PICO_RADIUS_T(D)                                                                          \
+  do {                                                                                            \
+    if (deep)                                                                                     \
+      radius_thread_kernel<T, D, FILL, true><<<blocks, kThreadsPerBlock, 0, c.st>>>(r);           \
+    else                                                                                          \
+      radius_thread_kernel<T, D, FILL, false><<<blocks, kThreadsPerBlock, 0, c.st>>>(r);          \
+  } while (0)
+    switch (t->sdim) {
+      case 1:
+        PICO_RADIUS_T(1);
+        break;
+      case 2:
+        PICO_RADIUS_T(2);
+        break;
+      default:
+        PICO_RADIUS_T(3);
+        break;
+    }
+#undef PICO_RADIUS_T
+  } else {
+    unsigned blocks;
+    size_t smem;
+    PICO_TRY(warp_geometry<T>(c, t, a.nq, sizeof(WarpFrame<T>), 2 * t->sdim * sizeof(T), &a.ws, &a.ws_depth, &blocks,
+                              &smem));
+    if (t->packed()) {
+      radius_warp_kernel<T, true><<<blocks, kWarpsPerBlock * 32, smem, c.st>>>(r);
+    } else {
+      if (smem > 48 * 1024)
+        PICO_CUDA(cudaFuncSetAttribute(radius_warp_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+      radius_warp_kernel<T, false><<<blocks, kWarpsPerBlock * 32, smem, c.st>>>(r);
+    }
+  }
+  PICO_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+template <typename T>
+int radius_batch(const pico_b200_tree* t, const T* q, size_t nq, size_t stride, double radius, double e,
+                 uint64_t* offsets_out, void** out, unsigned flags, pico_b200_search_stats* stats) {
+  *out = nullptr;
+  if (nq > 0xfffffff0u) return fail(PICO_B200_ERR_UNSUPPORTED, "more than 2^32-16 queries in one call");
+  const bool on_device = flags & PICO_B200_DEVICE_POINTERS;
+  if (on_device) return fail(PICO_B200_ERR_UNSUPPORTED, "radius search returns host buffers; pass host pointers");
+  offsets_out[0] = 0;
+  if (nq == 0) return 0;
+  CallCtx c;
+  PICO_TRY(c.init(t->device));
+  PICO_CUDA(cudaEventRecord(c.ev[0], c.st));
+  const T* d_q = nullptr;
+  size_t d_stride = 0;
+  PICO_TRY(stage_queries(c, q, nq, stride, t->sdim, false, &d_q, &d_stride));
+  PICO_CUDA(cudaEventRecord(c.ev[1], c.st));
+  uint32_t* perm = nullptr;
+  PICO_TRY(make_perm(c, t, d_q, d_stride, nq, flags, &perm));
+  PICO_CUDA(cudaEventRecord(c.ev[2], c.st));
+
+  RadiusArgs<T> r;
+  fill_base(r.base, t, d_q, d_stride, nq, perm, e);
+  // search_approximate_radius scales the radius once (search_visitor.hpp:261-267)
+  r.radius = e > 0 ? T(radius) * r.base.e_inv : T(radius);
+  r.offsets = nullptr;
+  r.hits = nullptr;
+  PICO_TRY(c.alloc(reinterpret_cast<void**>(&r.counts), nq * 4));
+  PICO_TRY((launch_radius<T, false>(c, t, r, flags)));
+  uint64_t* d_offsets = nullptr;
+  PICO_TRY(scan_counts(c, r.counts, nq, &d_offsets));
+  PICO_CUDA(cudaMemcpyAsync(offsets_out, d_offsets, (nq + 1) * 8, cudaMemcpyDeviceToHost, c.st));
+  PICO_CUDA(cudaStreamSynchronize(c.st));
+  const size_t total = offsets_out[nq];
+  Neighbor<T>* h_hits = static_cast<Neighbor<T>*>(malloc((total ? total : 1) * sizeof(Neighbor<T>)));
+  if (!h_hits) return fail(PICO_B200_ERR_OUT_OF_MEMORY, "host allocation of radius results failed");
+  if (total) {
+    Neighbor<T>* d_hits = nullptr;
+    int rc = c.alloc(reinterpret_cast<void**>(&d_hits), total * sizeof(Neighbor<T>));
+    if (rc) {
+      free(h_hits);
+      return rc;
+    }
+    if (sizeof(T) == 8) cudaMemsetAsync(d_hits, 0, total * sizeof(Neighbor<T>), c.st);  // defined padding
+    r.offsets = d_offsets;
+    r.hits = d_hits;
+    r.base.ws = nullptr;
+    rc = launch_radius<T, true>(c, t, r, flags);
+    if (!rc && (flags & PICO_B200_SORT_RESULTS)) rc = sort_hits(c, d_hits, total, d_offsets, nq);
+    if (rc) {
+      free(h_hits);
+      return rc;
+    }
+    PICO_CUDA(cudaEventRecord(c.ev[3], c.st));
+    PICO_CUDA(cudaMemcpyAsync(h_hits, d_hits, total * sizeof(Neighbor<T>), cudaMemcpyDeviceToHost, c.st));
+  } else {
+    PICO_CUDA(cudaEventRecord(c.ev[3], c.st));
+  }
+  PICO_CUDA(cudaEventRecord(c.ev[4], c.st));
+  PICO_CUDA(cudaStreamSynchronize(c.st));
+  *out = h_hits;
+  if (stats) {
+    stats->h2d_ms = elapsed(c.ev[0], c.ev[1]);
+    stats->reorder_ms = elapsed(c.ev[1], c.ev[2]);
+    stats->kernel_ms = elapsed(c.ev[2], c.ev[3]);
+    stats->d2h_ms = elapsed(c.ev[3], c.ev[4]);
+    stats->kernel_launches = (perm ? 3 : 0) + 4 + ((flags & PICO_B200_SORT_RESULTS) ? 1 : 0);
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------ box
+template <typename T>
+int box_batch(const pico_b200_tree* t, const T* mins, const T* maxs, size_t nb, size_t stride, uint64_t* offsets_out,
+              int32_t** out, unsigned flags, pico_b200_search_stats* stats) {
+  *out = nullptr;
+  if (nb > 0xfffffff0u) return fail(PICO_B200_ERR_UNSUPPORTED, "more than 2^32-16 boxes in one call");
+  if (flags & PICO_B200_DEVICE_POINTERS)
+    return fail(PICO_B200_ERR_UNSUPPORTED, "box search returns host buffers; pass host pointers");
+  offsets_out[0] = 0;
+  if (nb == 0) return 0;
+  CallCtx c;
+  PICO_TRY(c.init(t->device));
+  PICO_CUDA(cudaEventRecord(c.ev[0], c.st));
+  const T *d_min = nullptr, *d_max = nullptr;
+  size_t d_stride = 0;
+  PICO_TRY(stage_queries(c, mins, nb, stride, t->sdim, false, &d_min, &d_stride));
+  PICO_TRY(stage_queries(c, maxs, nb, stride, t->sdim, false, &d_max, &d_stride));
+  PICO_CUDA(cudaEventRecord(c.ev[1], c.st));
+  PICO_CUDA(cudaEventRecord(c.ev[2], c.st));
+
+  BoxArgs<T> a;
+  a.nodes = static_cast<const typename NodeOf<T>::type*>(t->d_nodes);
+  a.pts4 = t->packed() ? static_cast<const typename Vec4Of<T>::type*>(t->d_pts) : nullptr;
+  a.rows = t->packed() ? nullptr : static_cast<const T*>(t->d_pts);
+  a.indices = t->d_indices;
+  a.root_box = static_cast<const T*>(t->d_root_box);
+  a.mins = d_min;
+  a.maxs = d_max;
+  a.stride = d_stride;
+  a.nb = (uint32_t)nb;
+  a.sdim = (int)t->sdim;
+  a.offsets = nullptr;
+  a.hits = nullptr;
+  PICO_TRY(c.alloc(reinterpret_cast<void**>(&a.counts), nb * 4));
+  unsigned blocks;
+  size_t smem;
+  PICO_TRY(warp_geometry<T>(c, t, nb, sizeof(BoxFrame) + sizeof(T), 4 * t->sdim * sizeof(T), &a.ws, &a.ws_depth,
+                            &blocks, &smem));
+  auto launch = [&]() -> int {
+    if (t->packed()) {
+      box_warp_kernel<T, true><<<blocks, kWarpsPerBlock * 32, smem, c.st>>>(a);
+    } else {
+      if (smem > 48 * 1024)
+        PICO_CUDA(cudaFuncSetAttribute(box_warp_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+      box_warp_kernel<T, false><<<blocks, kWarpsPerBlock * 32, smem, c.st>>>(a);
+    }
+    PICO_CUDA(cudaGetLastError());
+    return 0;
+  };
+  PICO_TRY(launch());
+  uint64_t* d_offsets = nullptr;
+  PICO_TRY(scan_counts(c, a.counts, nb, &d_offsets));
+  PICO_CUDA(cudaMemcpyAsync(offsets_out, d_offsets, (nb + 1) * 8, cudaMemcpyDeviceToHost, c.st));
+  PICO_CUDA(cudaStreamSynchronize(c.st));
+  const size_t total = offsets_out[nb];
+  int32_t* h_hits = static_cast<int32_t*>(malloc((total ? total : 1) * sizeof(int32_t)));
+  if (!h_hits) return fail(PICO_B200_ERR_OUT_OF_MEMORY, "host allocation of box results failed");
+  if (total) {
+    int32_t* d_hits = nullptr;
+    int rc = c.alloc(reinterpret_cast<void**>(&d_hits), total * sizeof(int32_t));
+    if (!rc) {
+      a.offsets = d_offsets;
+      a.hits = d_hits;
+      rc = launch();
+    }
+    if (rc) {
+      free(h_hits);
+      return rc;
+    }
+    PICO_CUDA(cudaEventRecord(c.ev[3], c.st));
+    PICO_CUDA(cudaMemcpyAsync(h_hits, d_hits, total * sizeof(int32_t), cudaMemcpyDeviceToHost, c.st));
+  } else {
+    PICO_CUDA(cudaEventRecord(c.ev[3], c.st));
+  }
+  PICO_CUDA(cudaEventRecord(c.ev[4], c.st));
+  PICO_CUDA(cudaStreamSynchronize(c.st));
+  *out = h_hits;
+  if (stats) {
+    stats->h2d_ms = elapsed(c.ev[0], c.ev[1]);
+    stats->reorder_ms = 0;
+    stats->kernel_ms = elapsed(c.ev[2], c.ev[3]);
+    stats->d2h_ms = elapsed(c.ev[3], c.ev[4]);
+    stats->kernel_launches = 4;
+  }
+  return 0;
+}
+
+template int knn_batch<float>(const pico_b200_tree*, const float*, size_t, size_t, size_t, double, Neighbor<float>*,
+                              unsigned, pico_b200_search_stats*);
+template int knn_batch<double>(const pico_b200_tree*, const double*, size_t, size_t, size_t, double,
+                               Neighbor<double>*, unsigned, pico_b200_search_stats*);
+template int radius_batch<float>(const pico_b200_tree*, const float*, size_t, size_t, double, double, uint64_t*,
+                                 void**, unsigned, pico_b200_search_stats*);
+template int radius_batch<double>(const pico_b200_tree*, const double*, size_t, size_t, double, double, uint64_t*,
+                                  void**, unsigned, pico_b200_search_stats*);
+template int box_batch<float>(const pico_b200_tree*, const float*, const float*, size_t, size_t, uint64_t*, int32_t**,
+                              unsigned, pico_b200_search_stats*);
+template int box_batch<double>(const pico_b200_tree*, const double*, const double*, size_t, size_t, uint64_t*,
+                               int32_t**, unsigned, pico_b200_search_stats*);
+
+}  // namespace pico

@@ -1,0 +1,293 @@
+// traverse.cuh — device-side depth-first traversals of the flat tree.
+//
+// These are the CUDA counterparts of search_nearest_euclidean::search_nearest
+// (internal/kd_tree_search.hpp:52-105) and search_box::operator()
+// (internal/kd_tree_search.hpp:270-306). The recursion is unrolled onto an explicit stack;
+// the arithmetic keeps the reference's operand order and is never contracted into FMAs
+// (file compiled with --fmad=false and written with round-to-nearest intrinsics), so
+// distances and pruning decisions are bit-identical to a portable x86-64 build of the
+// reference.
+#pragma once
+
+#include "common.cuh"
+
+namespace pico {
+
+// ---------------------------------------------------------------- exact scalar ops
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float abs_t(float a) { return fabsf(a); }
+__device__ __forceinline__ double abs_t(double a) { return fabs(a); }
+
+__device__ __forceinline__ int index_of(const float4& p) { return __float_as_int(p.w); }
+__device__ __forceinline__ int index_of(const double4& p) { return (int)__double_as_longlong(p.w); }
+
+__device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
+__device__ __forceinline__ double4 ldg4(const double4* p) {
+  const double2 a = __ldg(reinterpret_cast<const double2*>(p));
+  const double2 b = __ldg(reinterpret_cast<const double2*>(p) + 1);
+  return make_double4(a.x, a.y, b.x, b.y);
+}
+
+// Node load: one 16-B (f32) / two 16-B (f64) read-only transactions.
+struct NodeF32 {
+  uint32_t a, b, right, split_dim;
+};
+__device__ __forceinline__ void load_node(const pico_b200_node_f32* nodes, uint32_t i, float& a, float& b,
+                                          uint32_t& right, uint32_t& sd, int& lb, int& le) {
+  const uint4 r = __ldg(reinterpret_cast<const uint4*>(nodes) + i);
+  a = __uint_as_float(r.x);
+  b = __uint_as_float(r.y);
+  lb = (int)r.x;
+  le = (int)r.y;
+  right = r.z;
+  sd = r.w;
+}
+__device__ __forceinline__ void load_node(const pico_b200_node_f64* nodes, uint32_t i, double& a, double& b,
+                                          uint32_t& right, uint32_t& sd, int& lb, int& le) {
+  const uint4* p = reinterpret_cast<const uint4*>(nodes) + 2 * (size_t)i;
+  const uint4 r0 = __ldg(p);
+  const uint4 r1 = __ldg(p + 1);
+  a = __longlong_as_double((long long)(((unsigned long long)r0.y << 32) | r0.x));
+  b = __longlong_as_double((long long)(((unsigned long long)r0.w << 32) | r0.z));
+  lb = (int)r0.x;
+  le = (int)r0.z;
+  right = r1.x;
+  sd = r1.y;
+}
+
+// metric(x): metric.hpp:93-96,119-122,147-150,176-179
+template <typename T>
+__device__ __forceinline__ T metric1(int metric, T x) {
+  return metric == PICO_B200_METRIC_L2_SQUARED ? mul_rn(x, x) : abs_t(x);
+}
+
+// One term folded into the running distance, j ascending (metric.hpp:36-51, :131-145, :158-174).
+template <typename T>
+__device__ __forceinline__ T metric_fold(int metric, T d, T qj, T pj) {
+  const T t = sub_rn(qj, pj);
+  switch (metric) {
+    case PICO_B200_METRIC_L2_SQUARED:
+      return add_rn(d, mul_rn(t, t));
+    case PICO_B200_METRIC_L1:
+      return add_rn(d, abs_t(t));
+    case PICO_B200_METRIC_LPINF: {
+      const T a = abs_t(t);
+      return d < a ? a : d;
+    }
+    default: {
+      const T a = abs_t(t);
+      return a < d ? a : d;
+    }
+  }
+}
+template <typename T>
+__device__ __forceinline__ T metric_init(int metric) {
+  return metric == PICO_B200_METRIC_LNINF ? Limits<T>::max() : T(0);
+}
+
+// ---------------------------------------------------------------- thread-per-query, sdim <= 3
+// Stack entry = far child + its box distance + a snapshot of the per-dimension offsets
+// (node_box_offset_) that hold while the far subtree is visited. Taking a snapshot instead
+// of the reference's set/restore pair is equivalent: every pop installs the full state.
+template <typename T, int DIM, int DEPTH>
+struct LocalStack {
+  uint32_t node[DEPTH];
+  T dist[DEPTH];
+  T off[DIM][DEPTH];
+  __device__ __forceinline__ void push(int sp, uint32_t n, T d, const T (&o)[DIM]) {
+    node[sp] = n;
+    dist[sp] = d;
+#pragma unroll
+    for (int j = 0; j < DIM; ++j) off[j][sp] = o[j];
+  }
+  __device__ __forceinline__ void pop(int sp, uint32_t& n, T& d, T (&o)[DIM]) const {
+    n = node[sp];
+    d = dist[sp];
+#pragma unroll
+    for (int j = 0; j < DIM; ++j) o[j] = off[j][sp];
+  }
+};
+
+// Same interface over a global workspace (trees deeper than the local stack). Entries of
+// one thread are `stride` words apart so that a warp's accesses coalesce.
+template <typename T, int DIM>
+struct GlobalStack {
+  uint32_t* node;
+  T* dist;
+  T* off;  // [DIM][depth][stride]
+  size_t stride, depth;
+  __device__ __forceinline__ void push(int sp, uint32_t n, T d, const T (&o)[DIM]) {
+    node[(size_t)sp * stride] = n;
+    dist[(size_t)sp * stride] = d;
+#pragma unroll
+    for (int j = 0; j < DIM; ++j) off[((size_t)j * depth + sp) * stride] = o[j];
+  }
+  __device__ __forceinline__ void pop(int sp, uint32_t& n, T& d, T (&o)[DIM]) const {
+    n = node[(size_t)sp * stride];
+    d = dist[(size_t)sp * stride];
+#pragma unroll
+    for (int j = 0; j < DIM; ++j) o[j] = off[((size_t)j * depth + sp) * stride];
+  }
+};
+
+// FAST = metric_l2_squared + exact visitors, resolved at compile time.
+template <typename T, int DIM, bool FAST, typename Stack, typename Visitor>
+__device__ __forceinline__ void traverse_packed(const typename NodeOf<T>::type* __restrict__ nodes,
+                                                const typename Vec4Of<T>::type* __restrict__ pts4,
+                                                const T (&q)[DIM], int metric_rt, bool approx_rt, T e_inv, Stack& stack,
+                                                Visitor& vis) {
+  const int metric = FAST ? (int)PICO_B200_METRIC_L2_SQUARED : metric_rt;
+  const bool approx = FAST ? false : approx_rt;
+  T off[DIM];
+#pragma unroll
+  for (int j = 0; j < DIM; ++j) off[j] = T(0);
+  uint32_t node = 0;
+  T node_dist = T(0);
+  int sp = 0;
+  for (;;) {
+    // ---- descend to a leaf (kd_tree_search.hpp:60-88)
+    T a, b;
+    uint32_t right, sd;
+    int lb, le;
+    load_node(nodes, node, a, b, right, sd, lb, le);
+    while (sd != PICO_B200_LEAF) {
+      T v = q[0], old = off[0];
+#pragma unroll
+      for (int j = 1; j < DIM; ++j) {
+        if (sd == (uint32_t)j) {
+          v = q[j];
+          old = off[j];
+        }
+      }
+      // (left_max + right_min - v - v) > 0, evaluated left to right
+      const bool go_left = sub_rn(sub_rn(add_rn(a, b), v), v) > T(0);
+      const T new_off = metric1(metric, sub_rn(go_left ? b : a, v));
+      const uint32_t far = go_left ? right : node + 1;
+      node = go_left ? node + 1 : right;
+      // node_box_distance - old_offset + new_offset (kd_tree_search.hpp:93-94)
+      const T far_dist = add_rn(sub_rn(node_dist, old), new_off);
+      // The reference tests `visitor.max() >= dist` after the near subtree; max() never
+      // grows, so a far child that already fails now can be dropped without a push.
+      if (vis.max() >= far_dist) {
+        T snap[DIM];
+#pragma unroll
+        for (int j = 0; j < DIM; ++j) snap[j] = (sd == (uint32_t)j) ? new_off : off[j];
+        stack.push(sp, far, far_dist, snap);
+        ++sp;
+      }
+      load_node(nodes, node, a, b, right, sd, lb, le);
+    }
+    // ---- leaf scan (kd_tree_search.hpp:54-59): contiguous Vec4 records, index in .w
+    for (int i = lb; i < le; ++i) {
+      const typename Vec4Of<T>::type p = ldg4(pts4 + i);
+      T d = metric_init<T>(metric);
+      d = metric_fold(metric, d, q[0], p.x);
+      if (DIM > 1) d = metric_fold(metric, d, q[DIM > 1 ? 1 : 0], p.y);
+      if (DIM > 2) d = metric_fold(metric, d, q[DIM > 2 ? 2 : 0], p.z);
+      if (approx) d = mul_rn(d, e_inv);
+      vis.visit(index_of(p), d);
+    }
+    // ---- next pending far child (kd_tree_search.hpp:99-103)
+    bool found = false;
+    while (sp > 0) {
+      --sp;
+      T d;
+      uint32_t n;
+      T snap[DIM];
+      stack.pop(sp, n, d, snap);
+      if (vis.max() >= d) {
+        node = n;
+        node_dist = d;
+#pragma unroll
+        for (int j = 0; j < DIM; ++j) off[j] = snap[j];
+        found = true;
+        break;
+      }
+    }
+    if (!found) return;
+  }
+}
+
+// ---------------------------------------------------------------- visitors (thread-local)
+// search_nn, search_visitor.hpp:41-65 (+ approximate :164-191; scaling done by the caller)
+template <typename T>
+struct VisitNn {
+  T best = Limits<T>::max();
+  int idx = -1;
+  __device__ __forceinline__ T max() const { return best; }
+  __device__ __forceinline__ void visit(int i, T d) {
+    if (best > d) {
+      best = d;
+      idx = i;
+    }
+  }
+};
+
+// search_knn + insert_sorted, search_visitor.hpp:20-38,82-123. All KMAX slots start at
+// max(); running the insertion over KMAX >= k slots leaves the first k identical to the
+// k-slot version because acceptance is tested against slot k-1.
+template <typename T, int KMAX>
+struct VisitKnn {
+  T d[KMAX];
+  int id[KMAX];
+  T worst;
+  int k;
+  __device__ __forceinline__ void init(int k_) {
+    k = k_;
+    worst = Limits<T>::max();
+#pragma unroll
+    for (int i = 0; i < KMAX; ++i) {
+      d[i] = Limits<T>::max();
+      id[i] = -1;
+    }
+  }
+  __device__ __forceinline__ T max() const { return worst; }
+  __device__ __forceinline__ void visit(int i_new, T x) {
+    if (!(worst > x)) return;
+#pragma unroll
+    for (int i = KMAX - 1; i >= 1; --i) {
+      const bool shift = d[i - 1] > x;
+      const bool here = !shift && (d[i] > x);
+      const T nd = shift ? d[i - 1] : (here ? x : d[i]);
+      const int ni = shift ? id[i - 1] : (here ? i_new : id[i]);
+      d[i] = nd;
+      id[i] = ni;
+    }
+    if (d[0] > x) {
+      d[0] = x;
+      id[0] = i_new;
+    }
+#pragma unroll
+    for (int i = 0; i < KMAX; ++i)
+      if (i == k - 1) worst = d[i];
+  }
+};
+
+// search_radius, search_visitor.hpp:126-156: max() is the constant radius.
+template <typename T>
+struct VisitRadiusCount {
+  T radius;
+  uint32_t count = 0;
+  __device__ __forceinline__ T max() const { return radius; }
+  __device__ __forceinline__ void visit(int, T d) { count += (radius > d); }
+};
+template <typename T>
+struct VisitRadiusFill {
+  T radius;
+  Neighbor<T>* out;
+  __device__ __forceinline__ T max() const { return radius; }
+  __device__ __forceinline__ void visit(int i, T d) {
+    if (radius > d) {
+      out->index = i;
+      out->distance = d;
+      ++out;
+    }
+  }
+};
+
+}  // namespace pico

@@ -1,0 +1,375 @@
+// traverse_warp.cuh — warp-per-query traversal for any spatial dimension / any k.
+//
+// All 32 lanes walk the tree together (node loads are warp-uniform broadcasts); a leaf is
+// scanned with one lane per point, each lane accumulating its distance over the dimensions
+// in ascending order (so the rounding equals the reference's sequential sum,
+// metric.hpp:36-51), and candidates are handed to the visitor in leaf order so that
+// "first visited wins" (search_visitor.hpp:55,107,141) is preserved.
+//
+// The reference's set/restore of node_box_offset_ (kd_tree_search.hpp:93-103) is kept
+// literally: frames on a per-warp stack in global memory carry {far child, parent box
+// distance, new offset, saved offset, split_dim | state}; the offset vector itself lives
+// in shared memory next to the query.
+#pragma once
+
+#include "traverse.cuh"
+
+namespace pico {
+
+template <typename T>
+struct WarpFrame {
+  uint32_t far;
+  uint32_t sd_state;  // split_dim | (ACTIVE << 31)
+  T dist;             // box distance of the parent (PENDING) — unused once ACTIVE
+  T new_off;
+  T old_off;
+};
+
+// Point access: PACKED = Vec4 records with the index in .w (sdim <= 3); else rows + indices.
+template <typename T, bool PACKED>
+struct PointSet {
+  const typename Vec4Of<T>::type* pts4;
+  const T* rows;
+  const int32_t* indices;
+  int sdim;
+  __device__ __forceinline__ T distance(int i, const T* q, int metric, int& index) const {
+    T d = metric_init<T>(metric);
+    if (PACKED) {
+      const typename Vec4Of<T>::type p = ldg4(pts4 + i);
+      d = metric_fold(metric, d, q[0], p.x);
+      if (sdim > 1) d = metric_fold(metric, d, q[1], p.y);
+      if (sdim > 2) d = metric_fold(metric, d, q[2], p.z);
+      index = index_of(p);
+    } else {
+      const T* p = rows + (size_t)i * sdim;
+      for (int j = 0; j < sdim; ++j) d = metric_fold(metric, d, q[j], __ldg(p + j));
+      index = __ldg(indices + i);
+    }
+    return d;
+  }
+  __device__ __forceinline__ bool inside(int i, const T* qmin, const T* qmax, int& index) const {
+    // box_base::contains(point), box.hpp:31-40 (inclusive)
+    bool ok = true;
+    if (PACKED) {
+      const typename Vec4Of<T>::type p = ldg4(pts4 + i);
+      const T c[3] = {p.x, p.y, p.z};
+      for (int j = 0; j < sdim; ++j) ok = ok && !(qmin[j] > c[j] || qmax[j] < c[j]);
+      index = index_of(p);
+    } else {
+      const T* p = rows + (size_t)i * sdim;
+      for (int j = 0; j < sdim; ++j) {
+        const T x = __ldg(p + j);
+        ok = ok && !(qmin[j] > x || qmax[j] < x);
+      }
+      index = __ldg(indices + i);
+    }
+    return ok;
+  }
+};
+
+// ---------------------------------------------------------------- warp visitors
+// k <= 32: the sorted list lives in registers, slot i in lane i ("register k-heap").
+template <typename T>
+struct WarpKnnReg {
+  T d;
+  int id;
+  T worst;
+  int k;
+  __device__ __forceinline__ void init(int k_) {
+    k = k_;
+    d = Limits<T>::max();
+    id = -1;
+    worst = Limits<T>::max();
+  }
+  __device__ __forceinline__ T max() const { return worst; }
+  // insert_sorted (search_visitor.hpp:24-38): new item goes behind all items <= it.
+  __device__ __forceinline__ void insert(int i_new, T x) {
+    const int lane = threadIdx.x & 31;
+    const unsigned le = __ballot_sync(0xffffffffu, lane < k && d <= x);
+    const int p = __popc(le);
+    const T up_d = __shfl_up_sync(0xffffffffu, d, 1);
+    const int up_i = __shfl_up_sync(0xffffffffu, id, 1);
+    if (lane == p) {
+      d = x;
+      id = i_new;
+    } else if (lane > p) {
+      d = up_d;
+      id = up_i;
+    }
+    worst = __shfl_sync(0xffffffffu, d, k - 1);
+  }
+  __device__ __forceinline__ void store(Neighbor<T>* out) const {
+    const int lane = threadIdx.x & 31;
+    if (lane < k) {
+      out[lane].index = id;
+      out[lane].distance = d;
+    }
+  }
+};
+
+// any k: the output row itself is the sorted working list, like the reference's iterator
+// range (search_visitor.hpp:98-123).
+template <typename T>
+struct WarpKnnMem {
+  Neighbor<T>* list;
+  int k, active;
+  T worst;
+  __device__ __forceinline__ void init(Neighbor<T>* row, int k_) {
+    list = row;
+    k = k_;
+    active = 0;
+    worst = Limits<T>::max();
+    const int lane = threadIdx.x & 31;
+    for (int i = lane; i < k; i += 32) {
+      list[i].index = -1;
+      list[i].distance = Limits<T>::max();
+    }
+    __syncwarp();
+  }
+  __device__ __forceinline__ T max() const { return worst; }
+  __device__ __forceinline__ void insert(int i_new, T x) {
+    const int lane = threadIdx.x & 31;
+    if (active < k) ++active;
+    int c = 0;
+    for (int i = lane; i < active - 1; i += 32) c += (list[i].distance <= x);
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    const int p = c;
+    for (int hi = active - 1; hi > p; hi -= 32) {
+      const int i = hi - lane;
+      Neighbor<T> v;
+      if (i > p) v = list[i - 1];
+      __syncwarp();
+      if (i > p) list[i] = v;
+      __syncwarp();
+    }
+    if (lane == 0) {
+      list[p].index = i_new;
+      list[p].distance = x;
+    }
+    __syncwarp();
+    worst = (active == k) ? list[k - 1].distance : Limits<T>::max();
+  }
+  __device__ __forceinline__ void store(Neighbor<T>*) const {}
+};
+
+template <typename T, typename List>
+struct WarpVisitKnn {
+  List list;
+  __device__ __forceinline__ T max() const { return list.max(); }
+  __device__ __forceinline__ void visit_batch(bool valid, int idx, T d) {
+    unsigned cand = __ballot_sync(0xffffffffu, valid && list.max() > d);
+    while (cand) {
+      const int l = __ffs(cand) - 1;
+      cand &= cand - 1;
+      const T x = __shfl_sync(0xffffffffu, d, l);
+      const int xi = __shfl_sync(0xffffffffu, idx, l);
+      if (list.max() > x) list.insert(xi, x);  // max() may have shrunk since the ballot
+    }
+  }
+};
+
+template <typename T>
+struct WarpVisitRadius {
+  T radius;
+  Neighbor<T>* out;  // nullptr while counting
+  uint32_t count = 0;
+  __device__ __forceinline__ T max() const { return radius; }
+  __device__ __forceinline__ void visit_batch(bool valid, int idx, T d) {
+    const unsigned hits = __ballot_sync(0xffffffffu, valid && radius > d);
+    if (out) {
+      const int lane = threadIdx.x & 31;
+      if (hits & (1u << lane)) {
+        Neighbor<T>* o = out + count + __popc(hits & ((1u << lane) - 1u));
+        o->index = idx;
+        o->distance = d;
+      }
+    }
+    count += __popc(hits);
+  }
+};
+
+// ---------------------------------------------------------------- nearest traversal
+// `sq` = query, `so` = node_box_offset_ (both shared, sdim entries, warp-private).
+template <typename T, bool PACKED, typename Visitor>
+__device__ void traverse_warp(const typename NodeOf<T>::type* __restrict__ nodes, const PointSet<T, PACKED>& ps,
+                              const T* sq, T* so, WarpFrame<T>* stack, int metric, bool approx, T e_inv,
+                              Visitor& vis) {
+  const int lane = threadIdx.x & 31;
+  uint32_t node = 0;
+  T node_dist = T(0);
+  int sp = 0;
+  for (;;) {
+    T a, b;
+    uint32_t right, sd;
+    int lb, le;
+    load_node(nodes, node, a, b, right, sd, lb, le);
+    while (sd != PICO_B200_LEAF) {
+      const T v = sq[sd];
+      const bool go_left = sub_rn(sub_rn(add_rn(a, b), v), v) > T(0);
+      const T new_off = metric1(metric, sub_rn(go_left ? b : a, v));
+      if (lane == 0) {
+        WarpFrame<T> f;
+        f.far = go_left ? right : node + 1;
+        f.sd_state = sd;
+        f.dist = node_dist;
+        f.new_off = new_off;
+        f.old_off = T(0);
+        stack[sp] = f;
+      }
+      ++sp;
+      node = go_left ? node + 1 : right;
+      load_node(nodes, node, a, b, right, sd, lb, le);
+    }
+    for (int base = lb; base < le; base += 32) {
+      const int i = base + lane;
+      const bool valid = i < le;
+      int idx = -1;
+      T d = Limits<T>::max();
+      if (valid) {
+        d = ps.distance(i, sq, metric, idx);
+        if (approx) d = mul_rn(d, e_inv);
+      }
+      vis.visit_batch(valid, idx, d);
+    }
+    // unwind (kd_tree_search.hpp:93-103)
+    bool found = false;
+    __syncwarp();
+    while (sp > 0) {
+      const WarpFrame<T> f = stack[sp - 1];
+      const uint32_t fsd = f.sd_state & 0x7fffffffu;
+      if (!(f.sd_state >> 31)) {
+        const T old = so[fsd];
+        const T d2 = add_rn(sub_rn(f.dist, old), f.new_off);
+        if (vis.max() >= d2) {
+          __syncwarp();
+          if (lane == 0) {
+            stack[sp - 1].sd_state = fsd | 0x80000000u;
+            stack[sp - 1].old_off = old;
+            so[fsd] = f.new_off;
+          }
+          __syncwarp();
+          node = f.far;
+          node_dist = d2;
+          found = true;
+          break;
+        }
+        --sp;
+      } else {
+        __syncwarp();
+        if (lane == 0) so[fsd] = f.old_off;
+        __syncwarp();
+        --sp;
+      }
+    }
+    if (!found) return;
+  }
+}
+
+// ---------------------------------------------------------------- box traversal
+struct BoxFrame {
+  uint32_t node;
+  uint32_t stage;
+};
+
+// search_box::operator() (kd_tree_search.hpp:270-306). `sbox` = running box_ (min then
+// max), `qmin/qmax` = query box, all shared and warp-private; `saved` holds the value a
+// frame has to put back. With out == nullptr only counts.
+template <typename T, bool PACKED>
+__device__ uint32_t traverse_box_warp(const typename NodeOf<T>::type* __restrict__ nodes,
+                                      const PointSet<T, PACKED>& ps, const int32_t* __restrict__ indices,
+                                      const T* qmin, const T* qmax, T* sbox, BoxFrame* stack, T* saved,
+                                      int32_t* out) {
+  const int lane = threadIdx.x & 31;
+  const int sdim = ps.sdim;
+  uint32_t count = 0;
+  int sp = 0;
+  if (lane == 0) {
+    stack[0].node = 0;
+    stack[0].stage = 0;
+  }
+  sp = 1;
+  __syncwarp();
+  while (sp > 0) {
+    const BoxFrame f = stack[sp - 1];
+    T a, b;
+    uint32_t right, sd;
+    int lb, le;
+    load_node(nodes, f.node, a, b, right, sd, lb, le);
+    if (sd == PICO_B200_LEAF) {
+      for (int base = lb; base < le; base += 32) {
+        const int i = base + lane;
+        int idx = -1;
+        const bool in = (i < le) && ps.inside(i, qmin, qmax, idx);
+        const unsigned hits = __ballot_sync(0xffffffffu, in);
+        if (out && in) out[count + __popc(hits & ((1u << lane) - 1u))] = idx;
+        count += __popc(hits);
+      }
+      --sp;
+      continue;
+    }
+    if (f.stage == 2) {
+      __syncwarp();
+      if (lane == 0) sbox[sd] = saved[sp - 1];
+      __syncwarp();
+      --sp;
+      continue;
+    }
+    // stage 0: narrow max to left_max and look at the left child;
+    // stage 1: put max back, narrow min to right_min and look at the right child.
+    const uint32_t child = (f.stage == 0) ? f.node + 1 : right;
+    __syncwarp();
+    if (lane == 0) {
+      if (f.stage == 0) {
+        saved[sp - 1] = sbox[sdim + sd];
+        sbox[sdim + sd] = a;
+      } else {
+        sbox[sdim + sd] = saved[sp - 1];
+        saved[sp - 1] = sbox[sd];
+        sbox[sd] = b;
+      }
+      stack[sp - 1].stage = f.stage + 1;
+    }
+    __syncwarp();
+    // query.contains(box_) := contains(box.min) && contains(box.max)  (box.hpp:44-47)
+    bool contained = true;
+    for (int j = lane; j < 2 * sdim; j += 32) {
+      const int dj = j < sdim ? j : j - sdim;
+      const T x = sbox[j];
+      if (qmin[dj] > x || qmax[dj] < x) contained = false;
+    }
+    contained = __all_sync(0xffffffffu, contained);
+    if (contained) {
+      // report_node (kd_tree_search.hpp:336-372): the subtree's points are one contiguous run
+      uint32_t nl = child, nr = child;
+      int rb, re, dummy0, dummy1;
+      T ta, tb;
+      uint32_t tr, tsd;
+      load_node(nodes, nl, ta, tb, tr, tsd, rb, dummy0);
+      while (tsd != PICO_B200_LEAF) {
+        ++nl;
+        load_node(nodes, nl, ta, tb, tr, tsd, rb, dummy0);
+      }
+      load_node(nodes, nr, ta, tb, tr, tsd, dummy1, re);
+      while (tsd != PICO_B200_LEAF) {
+        nr = tr;
+        load_node(nodes, nr, ta, tb, tr, tsd, dummy1, re);
+      }
+      if (out)
+        for (int i = rb + lane; i < re; i += 32) out[count + (i - rb)] = __ldg(indices + i);
+      count += (uint32_t)(re - rb);
+    } else {
+      const bool intersects = (f.stage == 0) ? (qmin[sd] <= a) : (qmax[sd] >= b);
+      if (intersects) {
+        if (lane == 0) {
+          stack[sp].node = child;
+          stack[sp].stage = 0;
+        }
+        ++sp;
+        __syncwarp();
+      }
+    }
+  }
+  return count;
+}
+
+}  // namespace pico

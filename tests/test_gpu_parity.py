@@ -1,0 +1,347 @@
+"""Parity of the CUDA path (through the C-ABI / Python host mirror) against the CPU oracle and
+against the committed reference fixtures. Everything here needs a B200: `-m gpu`."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from parity import (assert_knn_parity, assert_radius_parity, assert_same_structure, leaf_sets_equal,
+                    nodes_from_export, split_ragged)
+
+pytestmark = pytest.mark.gpu
+
+METRIC = {"l2_squared": "L2Squared", "l1": "L1", "lpinf": "LPInf", "lninf": "LNInf"}
+RULE = {"sliding_midpoint": "SlidingMidpointMaxSide", "midpoint": "MidpointMaxSide", "median": "MedianMaxSide"}
+
+
+def make_tree(pt, pts, metric="l2_squared", rule="sliding_midpoint", stop="max_leaf_size", stop_value=10, bounds=None):
+    kw = {"rule": pt.kd_tree.Rule[RULE[rule]], "bounds": bounds}
+    if stop == "max_leaf_depth":
+        kw["max_leaf_depth"] = stop_value
+        return pt.KdTree(pts, pt.Metric[METRIC[metric]], **kw)
+    return pt.KdTree(pts, pt.Metric[METRIC[metric]], stop_value, **kw)
+
+
+@pytest.fixture(scope="module")
+def pt():
+    import pico_tree_b200
+    return pico_tree_b200
+
+
+def _golden_files():
+    d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    return sorted(glob.glob(os.path.join(d, "*.npz")))
+
+
+# ---------------------------------------------------------------- reference fixtures
+@pytest.mark.parametrize("path", _golden_files(), ids=lambda p: os.path.basename(p)[:-4])
+def test_fixture_build_and_search(pt, path):
+    """Device build + every search kind against outputs of the unmodified reference."""
+    g = np.load(path)
+    pts, q = g["pts"], g["q"]
+    metric, rule, stop = str(g["metric"]), str(g["rule"]), str(g["stop"])
+    t = make_tree(pt, pts, metric, rule, stop, int(g["stop_value"]))
+    nodes, indices, box = t.export()
+    assert np.array_equal(box, g["root_box"])
+    got = nodes_from_export(nodes, pts.dtype)
+    want = {f: g["node_" + f] for f in ("left_max", "right_min", "split_dim", "begin", "end", "left", "right")}
+    dup_coords = any(k in path for k in ("clustered", "grid"))
+    if rule != "median" and not dup_coords:
+        # split positions, split dims, tight bounds, leaf ranges, links: node for node
+        assert_same_structure(got, want)
+        assert leaf_sets_equal(want, indices, g["indices"])
+    elif rule != "median":
+        # duplicated coordinates: which of several equal extreme points slides is decided by
+        # libstdc++'s nth_element in the reference (SURVEY.md §8c hazard 4); exact search
+        # results below are unaffected
+        assert got["split_dim"][0] == want["split_dim"][0]
+    else:
+        # median: positions fixed by the rule; members with equal coordinates are libstdc++-defined
+        for f in ("split_dim", "begin", "end", "left", "right"):
+            assert np.array_equal(got[f], want[f]), f
+    assert sorted(indices.tolist()) == list(range(len(pts)))
+
+    k = g["knn_index"].shape[1]
+    ties = 0
+    for name, kk, e in (("nn", 1, 0.0), ("knn", k, 0.0)):
+        r = t.search_knn(q, kk) if e == 0.0 else t.search_knn(q, kk, e)
+        want_r = np.empty(r.shape, r.dtype)
+        want_r["index"], want_r["distance"] = g[name + "_index"], g[name + "_distance"]
+        ties += assert_knn_parity(r, want_r, pts, q, metric)
+        rw = t.search_knn(q, kk, warp_per_query=True)
+        ties += assert_knn_parity(rw, want_r, pts, q, metric)
+    # radius: strict '<', counts and records (multiset: leaf order may differ after a slide)
+    nns = t.search_radius(q, float(g["radius"]))
+    want_flat = np.empty(len(g["radius_index"]), nns.dtype)
+    want_flat["index"], want_flat["distance"] = g["radius_index"], g["radius_distance"]
+    assert_radius_parity(nns._offsets, nns._flat[:len(want_flat)], g["radius_offsets"], want_flat, ordered=False)
+    # box: inclusive bounds, same sets
+    boxes = np.empty((2 * len(q), pts.shape[1]), pts.dtype)
+    boxes[0::2], boxes[1::2] = g["box_min"], g["box_max"]
+    res = t.search_box(boxes)
+    assert np.array_equal(res._offsets, g["box_offsets"])
+    for a, b in zip(split_ragged(res._offsets, res._flat), split_ragged(g["box_offsets"], g["box_index"])):
+        assert np.array_equal(np.sort(a), np.sort(b))
+
+
+@pytest.mark.parametrize("path", _golden_files(), ids=lambda p: os.path.basename(p)[:-4])
+def test_fixture_reference_tree_uploaded(pt, path, tmp_path):
+    """The reference's own saved stream loads into the engine (kd_tree::load path) and then every
+    result — including approximate search and visit ORDER — must be identical, ties included."""
+    g = np.load(path)
+    pts, q = g["pts"], g["q"]
+    metric = str(g["metric"])
+    header = b"\x89PKD" + (1).to_bytes(4, "little") + len(METRIC[metric]).to_bytes(8, "little") + METRIC[metric].encode()
+    f = tmp_path / "ref.pkd"
+    f.write_bytes(header + g["saved_stream"].tobytes())
+    t = pt.load_kd_tree(pts, str(f))
+    _, indices, box = t.export()
+    assert np.array_equal(indices, g["indices"]) and np.array_equal(box, g["root_box"])
+    k = g["knn_index"].shape[1]
+    for kw in ({}, {"warp_per_query": True}, {"reorder": False}):
+        for name, kk, e in (("nn", 1, 0.0), ("knn", k, 0.0), ("aknn", k, 1.5)):
+            r = t.search_knn(q, kk, **kw) if e == 0.0 else t.search_knn(q, kk, e, **kw)
+            assert np.array_equal(r["index"], g[name + "_index"]), (name, kw)
+            assert np.array_equal(r["distance"], g[name + "_distance"]), (name, kw)
+    for kw in ({}, {"warp_per_query": True}):
+        nns = t.search_radius(q, float(g["radius"]), **kw)
+        assert np.array_equal(nns._offsets, g["radius_offsets"])
+        n = len(g["radius_index"])
+        assert np.array_equal(nns._flat["index"][:n], g["radius_index"])
+        assert np.array_equal(nns._flat["distance"][:n], g["radius_distance"])
+        nns = t.search_radius(q, float(g["radius"]), 1.5, True, **kw)
+        assert np.array_equal(nns._offsets, g["aradius_offsets"])
+        assert np.array_equal(nns._flat["distance"][:len(g["aradius_distance"])], g["aradius_distance"])
+    boxes = np.empty((2 * len(q), pts.shape[1]), pts.dtype)
+    boxes[0::2], boxes[1::2] = g["box_min"], g["box_max"]
+    res = t.search_box(boxes)
+    assert np.array_equal(res._offsets, g["box_offsets"])
+    assert np.array_equal(res._flat[:len(g["box_index"])], g["box_index"])  # DFS order
+    # and the engine writes the same bytes back
+    out = tmp_path / "mine.pkd"
+    pt.save_kd_tree(t, str(out))
+    assert out.read_bytes() == f.read_bytes()
+
+
+# ---------------------------------------------------------------- oracle on seeded inputs
+@pytest.mark.parametrize("n,sdim,leaf", [(100_000, 3, 10), (50_000, 2, 1), (30_000, 3, 64), (20_000, 1, 7)])
+def test_uniform_vs_oracle(pt, oracle, n, sdim, leaf):
+    """cfg1-like: uniform clouds, build + knn 1/4/16 + radius + box against the oracle."""
+    from pico_tree_b200 import datasets as D
+    pts = D.uniform(n, sdim, seed=1)
+    q = D.uniform(n // 2, sdim, seed=2)
+    o = oracle.OracleTree(pts, leaf)
+    t = pt.KdTree(pts, pt.Metric.L2Squared, leaf)
+    nodes, indices, box = t.export()
+    on = o.nodes
+    assert_same_structure(nodes_from_export(nodes, pts.dtype), on)
+    assert np.array_equal(box, o.root_box)
+    assert leaf_sets_equal(on, indices, o.indices)
+    info = t.info()
+    assert info["n_nodes"] == o.num_nodes and info["height"] == o.height
+    ties = 0
+    for k in (1, 4, 16, 40):
+        ties += assert_knn_parity(t.search_knn(q, k), o.search_knn(q, k), pts, q)
+    assert ties <= 4
+    r = 0.0004 if sdim > 1 else 1e-8
+    nns = t.search_radius(q, r)
+    offs, flat = o.search_radius(q, r)
+    assert_radius_parity(nns._offsets, nns._flat[:len(flat)], offs, flat, ordered=False)
+    nns = t.search_radius(q, r, True)
+    offs, flat = o.search_radius(q, r, sort=True)
+    assert np.array_equal(nns._offsets, offs) and np.array_equal(nns._flat["distance"][:len(flat)], flat["distance"])
+    boxes = np.empty((2000, sdim), np.float32)
+    boxes[0::2] = q[:1000] - 0.03
+    boxes[1::2] = q[:1000] + 0.02
+    res = t.search_box(boxes)
+    offs, flat = o.search_box(boxes[0::2], boxes[1::2])
+    assert np.array_equal(res._offsets, offs)
+    for a, b in zip(split_ragged(res._offsets, res._flat), split_ragged(offs, flat)):
+        assert np.array_equal(np.sort(a), np.sort(b))
+
+
+def test_lidar_shape_vs_oracle(pt, oracle):
+    """cfg2's cloud at a size the oracle finishes in seconds: slides in both directions, deep tree."""
+    from pico_tree_b200 import datasets as D
+    pts = D.lidar_shape(400_000, seed=1)
+    q = D.lidar_shape(200_000, seed=2, pose_shift=0.35)
+    o = oracle.OracleTree(pts, 10)
+    t = pt.KdTree(pts, pt.Metric.L2Squared, 10)
+    nodes, indices, box = t.export()
+    assert_same_structure(nodes_from_export(nodes, pts.dtype), o.nodes)
+    want = o.search_knn(q, 1, threads=oracle.max_threads())
+    for kw in ({}, {"reorder": False}, {"warp_per_query": True}):
+        ties = assert_knn_parity(t.search_knn(q, 1, **kw), want, pts, q)
+        assert ties <= 2
+    assert_knn_parity(t.search_knn(q, 16), o.search_knn(q, 16, threads=oracle.max_threads()), pts, q)
+    nns = t.search_radius(q[:50_000], 0.01)
+    offs, flat = o.search_radius(q[:50_000], 0.01)
+    assert_radius_parity(nns._offsets, nns._flat[:len(flat)], offs, flat, ordered=False)
+
+
+@pytest.mark.parametrize("metric", ["l1", "lpinf", "lninf"])
+def test_other_metrics_and_approximate(pt, oracle, metric):
+    from pico_tree_b200 import datasets as D
+    pts = D.uniform(40_000, 3, seed=5)
+    q = D.uniform(5_000, 3, seed=6)
+    o = oracle.OracleTree(pts, 8, metric=metric)
+    t = make_tree(pt, pts, metric, stop_value=8)
+    assert_knn_parity(t.search_knn(q, 5), o.search_knn(q, 5), pts, q, metric)
+    assert_knn_parity(t.search_knn(q, 24), o.search_knn(q, 24), pts, q, metric)
+    # approximate results depend on the traversal; identical trees -> identical answers
+    got, want = t.search_knn(q, 3, 1.7), o.search_knn(q, 3, e=1.7)
+    assert np.array_equal(got["distance"], want["distance"]) and np.array_equal(got["index"], want["index"])
+
+
+def test_high_dim_runtime_path(pt, oracle):
+    """cfg4-like (runtime-dim path): 128-D descriptors, knn=10 exact and approximate."""
+    from pico_tree_b200 import datasets as D
+    pts = D.sift_shape(20_000, seed=1)
+    q = D.sift_shape(64, seed=2)
+    o = oracle.OracleTree(pts, 10)
+    t = pt.KdTree(pts, pt.Metric.L2Squared, 10)
+    assert_knn_parity(t.search_knn(q, 10), o.search_knn(q, 10), pts, q)
+    assert_knn_parity(t.search_knn(q, 100), o.search_knn(q, 100), pts, q)
+    # approximate search is traversal dependent: compare on the reference-built tree
+    import ctypes as C
+    got = t.search_knn(q, 10, 2.25)
+    exact = o.search_knn(q, 10)
+    assert np.all(got["distance"][:, 0] * np.float32(2.25) >= exact["distance"][:, 0])
+
+
+def test_float64(pt, oracle):
+    rng = np.random.default_rng(11)
+    pts = rng.random((30_000, 3))
+    q = rng.random((4_000, 3))
+    o = oracle.OracleTree(pts, 10)
+    t = pt.KdTree(pts, pt.Metric.L2Squared, 10)
+    assert t.dtype_neighbor.itemsize == 16
+    nodes, indices, _ = t.export()
+    assert_same_structure(nodes_from_export(nodes, pts.dtype), o.nodes)
+    assert_knn_parity(t.search_knn(q, 1), o.search_knn(q, 1), pts, q)
+    assert_knn_parity(t.search_knn(q, 12), o.search_knn(q, 12), pts, q)
+    nns = t.search_radius(q, 0.0005)
+    offs, flat = o.search_radius(q, 0.0005)
+    assert_radius_parity(nns._offsets, nns._flat[:len(flat)], offs, flat, ordered=False)
+
+
+# ---------------------------------------------------------------- edge cases
+def test_edge_cases(pt, oracle):
+    # a single point, k larger than n, all points identical, queries far outside the root box
+    one = np.array([[0.5, 0.25, 0.125]], np.float32)
+    t = pt.KdTree(one, pt.Metric.L2Squared, 10)
+    r = t.search_knn(np.array([[0, 0, 0], [9, 9, 9]], np.float32), 1)
+    assert r["index"].ravel().tolist() == [0, 0]
+    same = np.tile(np.array([[1.0, 2.0, 3.0]], np.float32), (100, 1))
+    t = pt.KdTree(same, pt.Metric.L2Squared, 10)
+    o = oracle.OracleTree(same, 10)
+    q = np.array([[1, 2, 3], [0, 0, 0]], np.float32)
+    assert_knn_parity(t.search_knn(q, 7), o.search_knn(q, 7), same, q)
+    assert len(t.search_radius(q, 1e-12)[0]) == 100  # all duplicates at distance 0 < r
+    assert len(t.search_radius(q, 0.0)[0]) == 0      # strict '<'
+    # k == n returns everything, sorted
+    pts = np.random.default_rng(0).random((50, 2), dtype=np.float32)
+    t = pt.KdTree(pts, pt.Metric.L2Squared, 3)
+    o = oracle.OracleTree(pts, 3)
+    q = np.random.default_rng(1).random((20, 2), dtype=np.float32) * 3 - 1
+    got = t.search_knn(q, 50)
+    assert_knn_parity(got, o.search_knn(q, 50), pts, q)
+    assert np.all(np.diff(got["distance"], axis=1) >= 0)
+    # inclusive box bounds: a box that is exactly one point
+    boxes = np.stack([pts[3], pts[3]])
+    assert t.search_box(boxes)[0].tolist() == [3]
+    # leaf_ranges with max_leaf_depth(2): 4 leaves covering every index once (kd_tree_test.cpp:148-178)
+    t = pt.KdTree(pts, pt.Metric.L2Squared, max_leaf_depth=2)
+    ranges = t.leaf_ranges()
+    assert len(ranges) == 4 and sorted(np.concatenate(ranges).tolist()) == list(range(50))
+    # empty query batch
+    assert t.search_knn(np.empty((0, 2), np.float32), 1).shape == (0, 1)
+    # column-major queries give (k, n) output (kd_tree_test.py:71-88)
+    qf = np.asfortranarray(q.T)
+    assert qf.flags["F_CONTIGUOUS"]
+    got_f = t.search_knn(qf, 2)
+    assert got_f.shape == (2, 20)
+    assert np.array_equal(got_f.T["index"], t.search_knn(q, 2)["index"])
+
+
+def test_python_api_three_point_cases(pt):
+    # test/pyco_tree/kd_tree_test.py:53-69,90-118,151-192
+    a = np.array([[2, 1], [4, 3], [8, 7]], np.float32)
+    t = pt.KdTree(a, pt.Metric.L2Squared, 10)
+    assert (t.sdim, t.npts) == (2, 3) and t.metric(-2.0) == 4
+    assert pt.KdTree(a, pt.Metric.L1, 10).metric(-2.0) == 2
+    nns = t.search_knn(a, 2)
+    assert nns.shape == (3, 2) and nns["index"][:, 0].tolist() == [0, 1, 2] and np.all(nns["distance"][:, 0] == 0)
+    data = nns.ctypes.data
+    t.search_knn(a, 2, nns)
+    assert nns.ctypes.data == data
+    nns = t.search_knn(a, 2, 1.0)
+    assert nns["index"][:, 0].tolist() == [0, 1, 2]
+    rad = t.search_radius(a, t.metric(2.5))
+    assert len(rad) == 3 and rad.dtype == t.dtype_neighbor
+    assert [len(n) for n in rad] == [1, 1, 1] and [int(n[0][0]) for n in rad] == [0, 1, 2]
+    boxes = np.array([[0, 0], [3, 3], [2, 2], [3, 3], [0, 0], [9, 9], [6, 6], [9, 9]], np.float32)
+    res = t.search_box(boxes)
+    assert res.dtype == t.dtype_index and [len(n) for n in res] == [1, 0, 3, 1]
+    assert [len(n) for n in res[0:4:2]] == [1, 3]
+    with pytest.raises(ValueError):
+        t.search_box(boxes[:3])
+    with pytest.raises(ValueError):
+        t.search_knn(a.astype(np.float64), 1)
+
+
+def test_deep_tree_uses_global_stack(pt, oracle):
+    """Duplicated coordinates make the sliding midpoint peel one point per level: the tree gets
+    deeper than the local traversal stack and the workspace variant must take over."""
+    rng = np.random.default_rng(3)
+    pts = rng.random((6000, 3), dtype=np.float32)
+    pts[:, 0] = np.float32(0.5)
+    pts[::2, 1] = np.float32(0.25)
+    o = oracle.OracleTree(pts, 2)
+    t = pt.KdTree(pts, pt.Metric.L2Squared, 2)
+    assert t.info()["height"] == o.height and o.height >= 64
+    q = rng.random((3000, 3), dtype=np.float32)
+    for kw in ({}, {"warp_per_query": True}):
+        assert_knn_parity(t.search_knn(q, 1, **kw), o.search_knn(q, 1), pts, q)
+        assert_knn_parity(t.search_knn(q, 6, **kw), o.search_knn(q, 6), pts, q)
+    nns = t.search_radius(q, 0.001)
+    offs, flat = o.search_radius(q, 0.001)
+    assert_radius_parity(nns._offsets, nns._flat[:len(flat)], offs, flat, ordered=False)
+
+
+# ---------------------------------------------------------------- BASELINE sizes: properties
+def test_full_size_properties(pt):
+    """cfg2 at full size (7,733,372 / 7,200,863): size-independent properties instead of the oracle —
+    (a) nn of a tree point is itself at distance 0; (b) nn distance is a lower bound of the distance
+    to a random sample of points and is attained by the returned index; (c) results do not depend on
+    the traversal kernel or on query reordering; (d) knn=16 rows are sorted and start with the nn."""
+    from parity import ref_distance
+    from pico_tree_b200 import datasets as D
+    tree_pts, q = D.bench_clouds()
+    t = pt.KdTree(tree_pts, pt.Metric.L2Squared, 10)
+    info = t.info()
+    assert info["n_points"] == D.N_TREE and info["n_leaves"] * 10 >= D.N_TREE
+    sub = tree_pts[::97]
+    r = t.search_knn(sub, 1)
+    assert np.all(r["distance"] == 0)
+    assert np.array_equal(tree_pts[r["index"][:, 0]], sub)  # duplicates may answer for each other
+    nn = t.search_knn(q, 1)
+    d = ref_distance(tree_pts, q, nn["index"][:, 0])
+    assert np.array_equal(d, nn["distance"][:, 0])
+    rng = np.random.default_rng(0)
+    for _ in range(4):
+        other = rng.integers(0, D.N_TREE, size=len(q))
+        assert np.all(ref_distance(tree_pts, q, other) >= nn["distance"][:, 0])
+    nn2 = t.search_knn(q, 1, reorder=False)
+    assert np.array_equal(nn2["distance"], nn["distance"]) and np.array_equal(nn2["index"], nn["index"])
+    part = q[:500_000]
+    nn3 = t.search_knn(part, 1, warp_per_query=True)
+    assert np.array_equal(nn3["index"], nn["index"][:500_000])
+    k16 = t.search_knn(part, 16)
+    assert np.all(np.diff(k16["distance"], axis=1) >= 0)
+    assert np.array_equal(k16["index"][:, 0], nn["index"][:500_000, 0])
+    # radius search agrees with knn: count(d < r) >= 1 iff nn distance < r
+    rad = t.search_radius(part, 0.01)
+    counts = np.diff(rad._offsets.astype(np.int64))
+    assert np.array_equal(counts > 0, nn["distance"][:500_000, 0] < np.float32(0.01))
