@@ -70,7 +70,9 @@ enum {
   PICO_B200_DEVICE_POINTERS = 1u << 0, /* query/result pointers are device pointers on the tree's device */
   PICO_B200_NO_REORDER = 1u << 1,      /* do not Z-order the query batch before traversal            */
   PICO_B200_SORT_RESULTS = 1u << 2,    /* search_radius(..., sort = true) kd_tree.hpp:265-267        */
-  PICO_B200_WARP_PER_QUERY = 1u << 3   /* force the warp-per-query traversal kernel                  */
+  PICO_B200_WARP_PER_QUERY = 1u << 3,  /* force the warp-per-query traversal kernel                  */
+  PICO_B200_ASYNC = 1u << 4            /* with DEVICE_POINTERS + pico_b200_set_stream: enqueue only,  */
+                                       /* do not synchronise (stats are not filled)                   */
 };
 
 typedef struct pico_b200_tree pico_b200_tree;
@@ -222,6 +224,21 @@ int pico_b200_tree_save(const pico_b200_tree* tree, void* dst);
 int pico_b200_tree_load(const void* pts, size_t n, size_t sdim, size_t stride, int scalar, int metric,
                         const void* stream, uint64_t stream_bytes, int device, pico_b200_tree** out,
                         uint64_t* consumed);
+
+/*
+ * Caller-provided CUDA stream (cudaStream_t) for the calling host thread; NULL restores the
+ * default (a private stream per call). With a caller stream the searches are ordered on that
+ * stream, so they compose with the caller's own kernels, events and CUDA graphs.
+ */
+int pico_b200_set_stream(void* cuda_stream);
+
+/*
+ * Device-side profiling of the traversal kernels launched by the calling thread: between
+ * begin and end every knn / radius traversal launch is bracketed by CUDA events on its
+ * stream; end synchronises and returns their summed duration and their number.
+ */
+int pico_b200_profile_begin(void);
+int pico_b200_profile_end(double* traversal_ms, uint64_t* traversal_launches);
 
 void pico_b200_free(void* p);
 

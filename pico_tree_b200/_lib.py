@@ -16,13 +16,15 @@ FLAG_DEVICE_POINTERS = 1 << 0
 FLAG_NO_REORDER = 1 << 1
 FLAG_SORT_RESULTS = 1 << 2
 FLAG_WARP_PER_QUERY = 1 << 3
+FLAG_ASYNC = 1 << 4
 
 EXPORTS = [
     "pico_b200_last_error", "pico_b200_abi_version", "pico_b200_device_count", "pico_b200_tree_create",
     "pico_b200_tree_create_from_nodes", "pico_b200_tree_destroy", "pico_b200_tree_info_get", "pico_b200_tree_export",
     "pico_b200_knn", "pico_b200_radius", "pico_b200_box", "pico_b200_tree_broadcast",
     "pico_b200_tree_serialize_size", "pico_b200_tree_serialize", "pico_b200_tree_deserialize", "pico_b200_free",
-    "pico_b200_tree_save_size", "pico_b200_tree_save", "pico_b200_tree_load",
+    "pico_b200_tree_save_size", "pico_b200_tree_save", "pico_b200_tree_load", "pico_b200_set_stream",
+    "pico_b200_profile_begin", "pico_b200_profile_end",
 ]
 
 
@@ -81,6 +83,9 @@ def lib():
     L.pico_b200_tree_save.argtypes = [vp, vp]
     L.pico_b200_tree_load.argtypes = [vp, sz, sz, sz, i32, i32, vp, C.c_uint64, i32, C.POINTER(vp),
                                       C.POINTER(C.c_uint64)]
+    L.pico_b200_set_stream.argtypes = [vp]
+    L.pico_b200_profile_begin.argtypes = []
+    L.pico_b200_profile_end.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
     _lib = L
     return L
 

@@ -242,6 +242,12 @@ int pico_b200_box(const pico_b200_tree* t, const void* mins, const void* maxs, s
 
 void pico_b200_free(void* p) { free(p); }
 
+int pico_b200_set_stream(void* cuda_stream) { return set_thread_stream(cuda_stream, cuda_stream != nullptr); }
+int pico_b200_profile_begin(void) { return profile_begin(); }
+int pico_b200_profile_end(double* traversal_ms, uint64_t* traversal_launches) {
+  return profile_end(traversal_ms, traversal_launches);
+}
+
 // ---------------------------------------------------------------- (de)serialisation
 int pico_b200_tree_serialize_size(const pico_b200_tree* t, uint64_t* bytes) {
   if (!t || !bytes) return fail(PICO_B200_ERR_INVALID_ARGUMENT, "null argument");

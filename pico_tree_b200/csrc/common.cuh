@@ -115,6 +115,9 @@ int upload_tree(pico_b200_tree* t, const T* h_pts, size_t stride, const void* no
                 const int32_t* indices, const T* root_box);
 
 // search.cu
+int set_thread_stream(void* stream, bool has);
+int profile_begin();
+int profile_end(double* ms, uint64_t* launches);
 template <typename T>
 int knn_batch(const pico_b200_tree* t, const T* q, size_t nq, size_t stride, size_t k, double e, Neighbor<T>* out,
               unsigned flags, pico_b200_search_stats* stats);

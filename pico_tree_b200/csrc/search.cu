@@ -286,14 +286,51 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) box_warp_kernel(BoxArgs<T
 }
 
 // ------------------------------------------------------------------ host helpers
+// per-thread call configuration (pico_b200_set_stream / pico_b200_profile_*)
+struct ThreadCfg {
+  cudaStream_t user_stream = nullptr;
+  bool has_user_stream = false;
+  bool profiling = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> spans;
+};
+thread_local ThreadCfg g_cfg;
+
 struct CallCtx {
   cudaStream_t st = nullptr;
+  bool owns_stream = true;
+  bool async = false;
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   std::vector<void*> async_allocs;
-  int init(int device) {
+  int init(int device, bool want_async = false) {
     PICO_CUDA(cudaSetDevice(device));
-    PICO_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    for (auto& e : ev) PICO_CUDA(cudaEventCreate(&e));
+    if (g_cfg.has_user_stream) {
+      st = g_cfg.user_stream;
+      owns_stream = false;
+      async = want_async;
+    } else {
+      PICO_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    }
+    if (!async)
+      for (auto& e : ev) PICO_CUDA(cudaEventCreate(&e));
+    return 0;
+  }
+  int mark(int i) {
+    if (!async) PICO_CUDA(cudaEventRecord(ev[i], st));
+    return 0;
+  }
+  // brackets a traversal kernel when the thread is profiling
+  int span_begin() {
+    if (!g_cfg.profiling) return 0;
+    cudaEvent_t a, b;
+    PICO_CUDA(cudaEventCreate(&a));
+    PICO_CUDA(cudaEventCreate(&b));
+    PICO_CUDA(cudaEventRecord(a, st));
+    g_cfg.spans.emplace_back(a, b);
+    return 0;
+  }
+  int span_end() {
+    if (!g_cfg.profiling) return 0;
+    PICO_CUDA(cudaEventRecord(g_cfg.spans.back().second, st));
     return 0;
   }
   int alloc(void** p, size_t bytes) {
@@ -302,11 +339,9 @@ struct CallCtx {
     return 0;
   }
   ~CallCtx() {
-    if (st) {
-      for (void* p : async_allocs) cudaFreeAsync(p, st);
-      cudaStreamSynchronize(st);
-      cudaStreamDestroy(st);
-    }
+    for (void* p : async_allocs) cudaFreeAsync(p, st);
+    if (!async && (st || !owns_stream)) cudaStreamSynchronize(st);
+    if (owns_stream && st) cudaStreamDestroy(st);
     for (auto& e : ev)
       if (e) cudaEventDestroy(e);
   }
@@ -458,18 +493,20 @@ int knn_batch(const pico_b200_tree* t, const T* q, size_t nq, size_t stride, siz
   if (nq > 0xfffffff0u) return fail(PICO_B200_ERR_UNSUPPORTED, "more than 2^32-16 queries in one call");
   if (k > 0x7fffffffu) return fail(PICO_B200_ERR_INVALID_ARGUMENT, "k too large");
   const bool on_device = flags & PICO_B200_DEVICE_POINTERS;
+  const bool want_async = (flags & PICO_B200_ASYNC) && on_device;
   CallCtx c;
-  PICO_TRY(c.init(t->device));
-  PICO_CUDA(cudaEventRecord(c.ev[0], c.st));
+  PICO_TRY(c.init(t->device, want_async));
+  PICO_TRY(c.mark(0));
   const T* d_q = nullptr;
   size_t d_stride = 0;
   PICO_TRY(stage_queries(c, q, nq, stride, t->sdim, on_device, &d_q, &d_stride));
   Neighbor<T>* d_out = out;
   if (!on_device) PICO_TRY(c.alloc(reinterpret_cast<void**>(&d_out), nq * k * sizeof(Neighbor<T>)));
-  PICO_CUDA(cudaEventRecord(c.ev[1], c.st));
+  PICO_TRY(c.mark(1));
   uint32_t* perm = nullptr;
   PICO_TRY(make_perm(c, t, d_q, d_stride, nq, flags, &perm));
-  PICO_CUDA(cudaEventRecord(c.ev[2], c.st));
+  PICO_TRY(c.mark(2));
+  PICO_TRY(c.span_begin());
 
   KnnArgs<T> a;
   fill_base(a, t, d_q, d_stride, nq, perm, e);
@@ -520,11 +557,13 @@ int knn_batch(const pico_b200_tree* t, const T* q, size_t nq, size_t stride, siz
 #undef PICO_LAUNCH_WARP
   }
   PICO_CUDA(cudaGetLastError());
+  PICO_TRY(c.span_end());
   ++launches;
-  PICO_CUDA(cudaEventRecord(c.ev[3], c.st));
+  PICO_TRY(c.mark(3));
   if (!on_device)
     PICO_CUDA(cudaMemcpyAsync(out, d_out, nq * k * sizeof(Neighbor<T>), cudaMemcpyDeviceToHost, c.st));
-  PICO_CUDA(cudaEventRecord(c.ev[4], c.st));
+  PICO_TRY(c.mark(4));
+  if (c.async) return 0;
   PICO_CUDA(cudaStreamSynchronize(c.st));
   if (stats) {
     stats->h2d_ms = elapsed(c.ev[0], c.ev[1]);
@@ -701,7 +740,9 @@ int radius_batch(const pico_b200_tree* t, const T* q, size_t nq, size_t stride, 
   r.offsets = nullptr;
   r.hits = nullptr;
   PICO_TRY(c.alloc(reinterpret_cast<void**>(&r.counts), nq * 4));
+  PICO_TRY(c.span_begin());
   PICO_TRY((launch_radius<T, false>(c, t, r, flags)));
+  PICO_TRY(c.span_end());
   uint64_t* d_offsets = nullptr;
   PICO_TRY(scan_counts(c, r.counts, nq, &d_offsets));
   PICO_CUDA(cudaMemcpyAsync(offsets_out, d_offsets, (nq + 1) * 8, cudaMemcpyDeviceToHost, c.st));
@@ -720,7 +761,9 @@ int radius_batch(const pico_b200_tree* t, const T* q, size_t nq, size_t stride, 
     r.offsets = d_offsets;
     r.hits = d_hits;
     r.base.ws = nullptr;
-    rc = launch_radius<T, true>(c, t, r, flags);
+    rc = c.span_begin();
+    if (!rc) rc = launch_radius<T, true>(c, t, r, flags);
+    if (!rc) rc = c.span_end();
     if (!rc && (flags & PICO_B200_SORT_RESULTS)) rc = sort_hits(c, d_hits, total, d_offsets, nq);
     if (rc) {
       free(h_hits);
@@ -829,6 +872,41 @@ int box_batch(const pico_b200_tree* t, const T* mins, const T* maxs, size_t nb, 
     stats->d2h_ms = elapsed(c.ev[3], c.ev[4]);
     stats->kernel_launches = 4;
   }
+  return 0;
+}
+
+int set_thread_stream(void* stream, bool has) {
+  g_cfg.user_stream = static_cast<cudaStream_t>(stream);
+  g_cfg.has_user_stream = has;
+  return 0;
+}
+
+int profile_begin() {
+  for (auto& sp : g_cfg.spans) {
+    cudaEventDestroy(sp.first);
+    cudaEventDestroy(sp.second);
+  }
+  g_cfg.spans.clear();
+  g_cfg.profiling = true;
+  return 0;
+}
+
+int profile_end(double* ms, uint64_t* launches) {
+  g_cfg.profiling = false;
+  double total = 0;
+  for (auto& sp : g_cfg.spans) {
+    PICO_CUDA(cudaEventSynchronize(sp.second));
+    float t = 0;
+    PICO_CUDA(cudaEventElapsedTime(&t, sp.first, sp.second));
+    total += t;
+  }
+  if (ms) *ms = total;
+  if (launches) *launches = g_cfg.spans.size();
+  for (auto& sp : g_cfg.spans) {
+    cudaEventDestroy(sp.first);
+    cudaEventDestroy(sp.second);
+  }
+  g_cfg.spans.clear();
   return 0;
 }
 
