@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json's metric: Mqueries/s, knn=1, float x3, 7.7M-point tree / 7.2M queries.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path (Z-order the batch, traverse, write neighbours) over one
+batch of 7,200,863 synthetic LiDAR-shape queries against the resident 7,733,372-point tree
+(configs[1]). N > 1: the tree is built on rank 0 and broadcast once over NVLink (NCCL through
+torch.distributed), every rank searches its own 7.2M-query cloud (configs[4], weak scaling, no
+collective on the query path).
+
+  value     whole-job Mq/s with queries and results resident in HBM (CUDA events, max over ranks)
+  e2e       the same through the public API with pinned HOST buffers (H2D + D2H inside the region)
+  roofline  traversal kernel: algorithmic bytes (SURVEY.md §8d model, counters from the oracle's
+            instrumented reference traversal) / its CUDA-event duration, vs the measured HBM peak
+  cpu_baseline  the reference (oracle/_ref, unmodified headers) or the oracle port on the host cores
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Mqueries/s knn=1 float x3 7.7M-tree/7.2M-query"
+UNIT = "Mq/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n-tree", type=int, default=None)
+    ap.add_argument("--n-query", type=int, default=None)
+    ap.add_argument("--k", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--warp-per-query", action="store_true")
+    ap.add_argument("--no-reorder", action="store_true")
+    return ap.parse_args()
+
+
+def config_dict(n_tree, n_query, k, n_gpus, extra=None):
+    cfg = {
+        "workload": "configs[1]: lidar-shape synthetic (9 poses x 64-ring scanner in a 50 m room, scan order), "
+                    "tree %d pts, %d queries/GPU, knn=%d, max_leaf_size=10, metric_l2_squared, "
+                    "sliding_midpoint_max_side" % (n_tree, n_query, k),
+        "n_tree": n_tree, "n_query_per_gpu": n_query, "k": k, "max_leaf_size": 10,
+        "query_order": "scan order on input; Z-ordered on device inside the timed step",
+        "parallelism": "tree replicated (NCCL broadcast once), queries sharded x%d" % n_gpus,
+        "l2": "inputs exceed L2 (tree 167 MB + queries 86 MB + results 58 MB vs 126 MB L2); no flush between steps",
+    }
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# --------------------------------------------------------------------------- reference arm
+def cpu_reference_tree(tree_pts):
+    from oracle import oracle as O
+    if O.ref_available():
+        return O.RefTree(tree_pts, 10), "reference"
+    return O.OracleTree(tree_pts, 10), "port"
+
+
+def run_reference(args, n_tree, n_query):
+    """The reference's own CPU implementation, all host threads, OpenMP dynamic,128 like its
+    Python binding (_pyco_tree/kd_tree.hpp:128); each step = a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    from pico_tree_b200 import datasets as D
+    tree_pts, q = D.lidar_shape(n_tree, seed=1), D.lidar_shape(n_query, seed=2, pose_shift=0.35)
+    t0 = time.perf_counter()
+    tree, kind = cpu_reference_tree(tree_pts)
+    build_s = time.perf_counter() - t0
+    threads = O.max_threads()
+    sample = min(n_query, 2_000_000)
+    qs = np.ascontiguousarray(q[:sample])
+    for _ in range(args.warmup):
+        tree.search_knn(qs, args.k, threads=threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        tree.search_knn(qs, args.k, threads=threads)
+    dt = (time.perf_counter() - t0) / args.steps
+    value = sample / dt / 1e6
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(n_tree, n_query, args.k, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
+                         "sample": "first %d of %d queries per step, all %d host threads, tree build %.2f s "
+                                   "(1 thread) not included" % (sample, n_query, threads, build_s)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for ln in open(self.path):
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                     f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except OSError:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
+                       samples=len(sm))
+        return out
+
+
+# --------------------------------------------------------------------------- our arm
+def run_ours(args, n_tree, n_query):
+    import torch
+    import torch.distributed as dist
+
+    import pico_tree_b200 as pt
+    from pico_tree_b200 import _lib, datasets as D
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+    k = args.k
+
+    # ---- data: rank r searches its own cloud (cfg5: cfg2 queries + reseeded clouds)
+    q_host = D.lidar_shape(n_query, seed=2 + rank, pose_shift=0.35)
+    tree_pts = D.lidar_shape(n_tree, seed=1) if (rank == 0 or world == 1) else None
+
+    # ---- tree: built on rank 0, broadcast once
+    t_build0 = time.perf_counter()
+    if rank == 0:
+        tree = pt.KdTree(tree_pts, pt.Metric.L2Squared, 10, device=local)
+        handle = tree._h
+    build_wall = time.perf_counter() - t_build0
+    bcast_ms = 0.0
+    if world > 1:
+        size = torch.zeros(1, dtype=torch.int64, device=dev)
+        if rank == 0:
+            sz = C.c_uint64()
+            _lib.check(L.pico_b200_tree_serialize_size(handle, C.byref(sz)))
+            size[0] = sz.value
+        dist.broadcast(size, 0)
+        image = torch.empty(int(size.item()), dtype=torch.uint8, device=dev)
+        if rank == 0:
+            _lib.check(L.pico_b200_tree_serialize(handle, C.c_void_p(image.data_ptr()), 1))
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dist.broadcast(image, 0)  # NCCL over NVLink / NVSwitch
+        e1.record()
+        torch.cuda.synchronize()
+        bcast_ms = e0.elapsed_time(e1)
+        if rank != 0:
+            handle = C.c_void_p()
+            _lib.check(L.pico_b200_tree_deserialize(C.c_void_p(image.data_ptr()), image.numel(), 1, local,
+                                                    C.byref(handle)))
+        del image
+    info = _lib.TreeInfo()
+    _lib.check(L.pico_b200_tree_info_get(handle, C.byref(info)))
+
+    # ---- resident inputs / outputs
+    stream = torch.cuda.Stream(device=dev)
+    q_dev = torch.from_numpy(q_host).to(dev)
+    out_dev = torch.empty((n_query, k, 2), dtype=torch.int32, device=dev)  # {int32 index, f32 distance}
+    flags = _lib.FLAG_DEVICE_POINTERS | _lib.FLAG_ASYNC
+    if args.warp_per_query:
+        flags |= _lib.FLAG_WARP_PER_QUERY
+    if args.no_reorder:
+        flags |= _lib.FLAG_NO_REORDER
+    _lib.check(L.pico_b200_set_stream(C.c_void_p(stream.cuda_stream)))
+
+    def step_resident():
+        _lib.check(L.pico_b200_knn(handle, C.c_void_p(q_dev.data_ptr()), n_query, 3, k, 0.0,
+                                   C.c_void_p(out_dev.data_ptr()), flags, None))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            step_resident()
+        barrier()
+        sampler = ClockSampler(local) if rank == 0 else None
+        _lib.check(L.pico_b200_profile_begin())
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            step_resident()
+        e1.record(stream)
+        barrier()
+        ms_total = e0.elapsed_time(e1)
+        trav_ms, trav_n = C.c_double(), C.c_uint64()
+        _lib.check(L.pico_b200_profile_end(C.byref(trav_ms), C.byref(trav_n)))
+        clocks = sampler.stop() if sampler else None
+    ms_step = ms_total / args.steps
+    kernel_ms = trav_ms.value / max(trav_n.value, 1)
+
+    # ---- e2e: public API, pinned host buffers, H2D + D2H inside the timed region
+    q_pin = torch.from_numpy(q_host).pin_memory()
+    out_pin = torch.empty((n_query, k, 2), dtype=torch.int32).pin_memory()
+    host_flags = flags & ~(_lib.FLAG_DEVICE_POINTERS | _lib.FLAG_ASYNC)
+
+    def step_e2e():
+        _lib.check(L.pico_b200_knn(handle, C.c_void_p(q_pin.data_ptr()), n_query, 3, k, 0.0,
+                                   C.c_void_p(out_pin.data_ptr()), host_flags, None))
+
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    _lib.check(L.pico_b200_set_stream(None))
+
+    # resident and host paths must agree
+    res_dev = out_dev.cpu().numpy()
+    assert np.array_equal(res_dev, out_pin.numpy()), "resident and host-buffer paths disagree"
+
+    # ---- max over ranks
+    if world > 1:
+        tmax = torch.tensor([ms_step, e2e_s, kernel_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms_step, e2e_s, kernel_ms = [float(x) for x in tmax.tolist()]
+    total_q = n_query * world
+    value = total_q / (ms_step * 1e-3) / 1e6
+    e2e_value = total_q / e2e_s / 1e6
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- CPU baseline + algorithmic-bytes counters (rank 0, N=1 only; bounded sample)
+    cpu = None
+    bytes_per_query = None
+    counters = None
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        pass
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as O
+        ref_tree, kind = cpu_reference_tree(tree_pts)
+        threads = O.max_threads()
+        t0 = time.perf_counter()
+        ref_all = ref_tree.search_knn(q_host, k, threads=threads)
+        all_s = time.perf_counter() - t0
+        one_n = min(n_query, 500_000)
+        t0 = time.perf_counter()
+        ref_tree.search_knn(np.ascontiguousarray(q_host[:one_n]), k, threads=1)
+        one_s = time.perf_counter() - t0
+        cpu = {"value": n_query / all_s / 1e6, "unit": UNIT, "cores": threads, "kind": kind,
+               "sample": "all %d queries once on %d threads (OpenMP dynamic,128); single thread: first %d queries "
+                         "-> %.3f Mq/s" % (n_query, threads, one_n, one_n / one_s / 1e6),
+               "single_thread_value": one_n / one_s / 1e6}
+        # parity of the benchmarked run itself against the CPU reference (full size)
+        got = res_dev.reshape(n_query, k, 2)
+        same_d = np.array_equal(got[..., 1].view(np.float32), ref_all["distance"])
+        idx_diff = int(np.count_nonzero(got[..., 0] != ref_all["index"]))
+        cpu["parity_vs_this_run"] = {"distances_bit_equal": bool(same_d), "index_mismatches": idx_diff,
+                                     "queries": n_query}
+        # counters from the oracle's instrumented reference traversal (sample)
+        oc = O.OracleTree(tree_pts, 10)
+        cs = min(n_query, 400_000)
+        sel = np.ascontiguousarray(q_host[:: max(n_query // cs, 1)][:cs])
+        _, cnt = oc.search_knn(sel, k, counters=True)
+        counters = (cnt / len(sel)).tolist()
+        bytes_per_query = 4 * 3 + 8 * k + counters[0] * 16 + counters[2] * 16
+    elif world == 1:
+        bytes_per_query = None
+
+    peak = peaks.get("hbm_gbs")
+    peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)"
+    if peak is None:
+        peak, peak_kind = 6650.0, "fallback (B200_PROFILING.md)"
+    roofline = None
+    if bytes_per_query is not None and kernel_ms > 0:
+        achieved = bytes_per_query * n_query / (kernel_ms * 1e-3) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("knn1_dram_bytes_per_launch")
+        except (OSError, ValueError):
+            pass
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": traffic, "kernel": "knn_thread_kernel<float,3,1,FAST>" if not args.warp_per_query
+                    else "knn_warp_kernel<float,PACKED,REG>", "kernel_ms": kernel_ms,
+                    "algorithmic_bytes_per_query": bytes_per_query,
+                    "per_query_branches_leaves_points": counters, "peak_source": peak_kind}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(n_tree, n_query, k, world, {
+            "tree_nodes": int(info.n_nodes), "tree_height": int(info.height), "build_ms_device": info.build_ms,
+            "build_wall_s": build_wall, "tree_broadcast_ms": bcast_ms, "tree_device_bytes": int(info.device_bytes)}),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(q_host.nbytes),
+                "d2h_bytes_per_step": int(n_query * k * 8), "ms_per_step": e2e_s * 1e3, "steps": e2e_steps},
+        "gpu_launches": int(args.steps * (1 + (0 if args.no_reorder else 1))),
+        "gpu_launches_note": "own kernels per step: morton_kernel + knn traversal kernel (CUB radix-sort passes "
+                             "of the Z-order step not counted)",
+        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    from pico_tree_b200 import datasets as D
+    n_tree = args.n_tree or D.N_TREE
+    n_query = args.n_query or D.N_QUERY
+    if args.impl == "reference":
+        run_reference(args, n_tree, n_query)
+    else:
+        run_ours(args, n_tree, n_query)
+
+
+if __name__ == "__main__":
+    main()

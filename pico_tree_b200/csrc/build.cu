@@ -253,16 +253,20 @@ __device__ void process_node(const BuildState<T>& s, uint32_t node_id) {
 
     if (s.rule == PICO_B200_RULE_SLIDING_MIDPOINT_MAX_SIDE && nl == cnt) {
       // all left: the largest coordinate slides right (kd_tree_builder.hpp:255-264)
+      // among equal maxima the LAST one moves (what a stable insertion of the tail gives,
+      // i.e. libstdc++'s nth_element on short ranges); positions are negated so that the
+      // "lower position wins" tie rule of arg_extreme picks the highest index
       T v = -Limits<T>::max();
       int p = 0x7fffffff;
       for (int i = begin + tid; i < end; i += G) {
         const T x = col[(size_t)idx[i] * sdim];
-        if (x > v) {
+        if (x >= v) {
           v = x;
-          p = i;
+          p = -i;
         }
       }
       Grp<G>::template arg_extreme<T, true>(v, p);
+      p = -p;
       if (tid == 0) {
         const int32_t a = idx[p];
         idx[p] = idx[end - 1];
