@@ -37,7 +37,7 @@ UNIT = "Mq/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n-tree", type=int, default=None)
@@ -110,7 +110,7 @@ def run_reference(args, n_tree, n_query):
 
 # --------------------------------------------------------------------------- clocks
 class ClockSampler:
-    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
               "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -120,11 +120,14 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+                 "-lms", "50"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except OSError:
             pass
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """Summary of the samples taken between the two time.time() stamps (all samples if fewer
+        than three fall inside, e.g. for a very short timed region)."""
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
             return out
@@ -133,27 +136,29 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        rows = []
         try:
             for ln in open(self.path):
                 f = [x.strip() for x in ln.split(",")]
                 if len(f) < 9:
                     continue
                 try:
-                    sm.append(float(f[1]))
-                    mx.append(float(f[2]))
+                    ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    rows.append((ts, float(f[1]), float(f[2]), [v.lower().startswith("active") for v in f[5:9]]))
                 except ValueError:
                     continue
-                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
-                                     f[5:9]):
-                    if val.lower().startswith("active"):
-                        reasons.add(name)
             os.unlink(self.path)
         except OSError:
             pass
-        if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
-                       samples=len(sm))
+        inside = [r for r in rows if t_begin is not None and t_begin <= r[0] <= t_end]
+        window = "timed region"
+        if len(inside) < 3:
+            inside, window = rows, "warm-up + timed region"
+        if inside:
+            names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+            reasons = sorted({n for r in inside for n, on in zip(names, r[3]) if on})
+            out.update(sm_mhz=float(np.median([r[1] for r in inside])), sm_max_mhz=float(max(r[2] for r in inside)),
+                       reasons=reasons, samples=len(inside), window=window)
         return out
 
 
@@ -235,10 +240,13 @@ def run_ours(args, n_tree, n_query):
         torch.cuda.synchronize()
 
     with torch.cuda.stream(stream):
+        sampler = ClockSampler(local) if rank == 0 else None
         for _ in range(args.warmup):
             step_resident()
         barrier()
-        sampler = ClockSampler(local) if rank == 0 else None
+        if sampler:
+            time.sleep(0.3)  # let nvidia-smi come up before the timed region
+        t_begin = time.time()
         _lib.check(L.pico_b200_profile_begin())
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
@@ -249,7 +257,7 @@ def run_ours(args, n_tree, n_query):
         ms_total = e0.elapsed_time(e1)
         trav_ms, trav_n = C.c_double(), C.c_uint64()
         _lib.check(L.pico_b200_profile_end(C.byref(trav_ms), C.byref(trav_n)))
-        clocks = sampler.stop() if sampler else None
+        clocks = sampler.stop(t_begin, time.time()) if sampler else None
     ms_step = ms_total / args.steps
     kernel_ms = trav_ms.value / max(trav_n.value, 1)
 
@@ -262,7 +270,8 @@ def run_ours(args, n_tree, n_query):
         _lib.check(L.pico_b200_knn(handle, C.c_void_p(q_pin.data_ptr()), n_query, 3, k, 0.0,
                                    C.c_void_p(out_pin.data_ptr()), host_flags, None))
 
-    e2e_steps = max(3, min(args.steps, 10))
+    _lib.check(L.pico_b200_set_stream(None))  # library-owned streams: chunked H2D / traverse / D2H pipeline
+    e2e_steps = max(3, min(args.steps, 20))
     for _ in range(2):
         step_e2e()
     barrier()
@@ -271,7 +280,6 @@ def run_ours(args, n_tree, n_query):
         step_e2e()
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
-    _lib.check(L.pico_b200_set_stream(None))
 
     # resident and host paths must agree
     res_dev = out_dev.cpu().numpy()

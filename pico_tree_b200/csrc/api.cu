@@ -36,6 +36,14 @@ int check_device(int device, int* sm_count) {
     return fail(PICO_B200_ERR_NO_DEVICE, "libpico_b200 is built for sm_100a only; found sm_" +
                                              std::to_string(prop.major) + std::to_string(prop.minor));
   *sm_count = prop.multiProcessorCount;
+  // Per-call workspaces come from the stream-ordered allocator; keep freed blocks cached in
+  // the pool instead of returning them to the driver at every synchronisation.
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    uint64_t keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  cudaGetLastError();
   return 0;
 }
 

@@ -89,10 +89,10 @@ __global__ void __launch_bounds__(kThreadsPerBlock) knn_thread_kernel(KnnArgs<T>
         st.node = static_cast<uint32_t*>(a.ws) + tid;
         st.dist = reinterpret_cast<T*>(static_cast<uint32_t*>(a.ws) + a.ws_stride * a.ws_depth) + tid;
         st.off = st.dist + a.ws_stride * a.ws_depth;
-        traverse_packed<T, DIM, FAST>(a.nodes, a.pts4, q, a.metric, a.approx != 0, a.e_inv, st, vis);
+        traverse_packed<T, DIM, FAST, true>(a.nodes, a.pts4, q, a.metric, a.approx != 0, a.e_inv, st, vis);
       } else {
         LocalStack<T, DIM, kLocalStack> st;
-        traverse_packed<T, DIM, FAST>(a.nodes, a.pts4, q, a.metric, a.approx != 0, a.e_inv, st, vis);
+        traverse_packed<T, DIM, FAST, true>(a.nodes, a.pts4, q, a.metric, a.approx != 0, a.e_inv, st, vis);
       }
       out->index = vis.idx;
       out->distance = vis.best;
@@ -106,10 +106,10 @@ __global__ void __launch_bounds__(kThreadsPerBlock) knn_thread_kernel(KnnArgs<T>
         st.node = static_cast<uint32_t*>(a.ws) + tid;
         st.dist = reinterpret_cast<T*>(static_cast<uint32_t*>(a.ws) + a.ws_stride * a.ws_depth) + tid;
         st.off = st.dist + a.ws_stride * a.ws_depth;
-        traverse_packed<T, DIM, FAST>(a.nodes, a.pts4, q, a.metric, a.approx != 0, a.e_inv, st, vis);
+        traverse_packed<T, DIM, FAST, false>(a.nodes, a.pts4, q, a.metric, a.approx != 0, a.e_inv, st, vis);
       } else {
         LocalStack<T, DIM, kLocalStack> st;
-        traverse_packed<T, DIM, FAST>(a.nodes, a.pts4, q, a.metric, a.approx != 0, a.e_inv, st, vis);
+        traverse_packed<T, DIM, FAST, false>(a.nodes, a.pts4, q, a.metric, a.approx != 0, a.e_inv, st, vis);
       }
 #pragma unroll
       for (int i = 0; i < KMAX; ++i) {
@@ -156,16 +156,16 @@ __global__ void __launch_bounds__(kThreadsPerBlock) radius_thread_kernel(RadiusA
       vis.radius = r.radius;
       vis.out = r.hits + r.offsets[qi];
       if (DEEP)
-        traverse_packed<T, DIM, false>(a.nodes, a.pts4, q, a.metric, a.approx != 0, a.e_inv, gst, vis);
+        traverse_packed<T, DIM, false, false>(a.nodes, a.pts4, q, a.metric, a.approx != 0, a.e_inv, gst, vis);
       else
-        traverse_packed<T, DIM, false>(a.nodes, a.pts4, q, a.metric, a.approx != 0, a.e_inv, lst, vis);
+        traverse_packed<T, DIM, false, false>(a.nodes, a.pts4, q, a.metric, a.approx != 0, a.e_inv, lst, vis);
     } else {
       VisitRadiusCount<T> vis;
       vis.radius = r.radius;
       if (DEEP)
-        traverse_packed<T, DIM, false>(a.nodes, a.pts4, q, a.metric, a.approx != 0, a.e_inv, gst, vis);
+        traverse_packed<T, DIM, false, false>(a.nodes, a.pts4, q, a.metric, a.approx != 0, a.e_inv, gst, vis);
       else
-        traverse_packed<T, DIM, false>(a.nodes, a.pts4, q, a.metric, a.approx != 0, a.e_inv, lst, vis);
+        traverse_packed<T, DIM, false, false>(a.nodes, a.pts4, q, a.metric, a.approx != 0, a.e_inv, lst, vis);
       r.counts[qi] = vis.count;
     }
   }
@@ -338,6 +338,11 @@ struct CallCtx {
     async_allocs.push_back(*p);
     return 0;
   }
+  // stream-ordered free of everything allocated so far (safe right after enqueueing)
+  void release() {
+    for (void* p : async_allocs) cudaFreeAsync(p, st);
+    async_allocs.clear();
+  }
   ~CallCtx() {
     for (void* p : async_allocs) cudaFreeAsync(p, st);
     if (!async && (st || !owns_stream)) cudaStreamSynchronize(st);
@@ -357,7 +362,9 @@ int stage_queries(CallCtx& c, const T* q, size_t nq, size_t stride, size_t sdim,
   }
   T* buf = nullptr;
   PICO_TRY(c.alloc(reinterpret_cast<void**>(&buf), nq * sdim * sizeof(T)));
-  if (nq)
+  if (nq && stride == sdim)
+    PICO_CUDA(cudaMemcpyAsync(buf, q, nq * sdim * sizeof(T), cudaMemcpyHostToDevice, c.st));
+  else if (nq)
     PICO_CUDA(cudaMemcpy2DAsync(buf, sdim * sizeof(T), q, stride * sizeof(T), sdim * sizeof(T), nq,
                                 cudaMemcpyHostToDevice, c.st));
   *d_q = buf;
@@ -483,19 +490,10 @@ float elapsed(cudaEvent_t a, cudaEvent_t b) {
   return ms;
 }
 
-}  // namespace
-
-// ------------------------------------------------------------------ knn
+// Enqueues one knn batch on c.st: stage queries (host pointers), Z-order, traverse, copy back.
 template <typename T>
-int knn_batch(const pico_b200_tree* t, const T* q, size_t nq, size_t stride, size_t k, double e, Neighbor<T>* out,
-              unsigned flags, pico_b200_search_stats* stats) {
-  if (nq == 0 || k == 0) return 0;
-  if (nq > 0xfffffff0u) return fail(PICO_B200_ERR_UNSUPPORTED, "more than 2^32-16 queries in one call");
-  if (k > 0x7fffffffu) return fail(PICO_B200_ERR_INVALID_ARGUMENT, "k too large");
-  const bool on_device = flags & PICO_B200_DEVICE_POINTERS;
-  const bool want_async = (flags & PICO_B200_ASYNC) && on_device;
-  CallCtx c;
-  PICO_TRY(c.init(t->device, want_async));
+int knn_enqueue(CallCtx& c, const pico_b200_tree* t, const T* q, size_t nq, size_t stride, size_t k, double e,
+                Neighbor<T>* out, unsigned flags, bool on_device, uint64_t* launches) {
   PICO_TRY(c.mark(0));
   const T* d_q = nullptr;
   size_t d_stride = 0;
@@ -512,7 +510,7 @@ int knn_batch(const pico_b200_tree* t, const T* q, size_t nq, size_t stride, siz
   fill_base(a, t, d_q, d_stride, nq, perm, e);
   a.out = d_out;
   a.k = (int)k;
-  uint64_t launches = perm ? 3 : 0;
+  *launches += perm ? 3 : 0;
   const bool use_thread = t->packed() && k <= 16 && !(flags & PICO_B200_WARP_PER_QUERY);
   if (use_thread) {
     bool deep;
@@ -558,11 +556,61 @@ int knn_batch(const pico_b200_tree* t, const T* q, size_t nq, size_t stride, siz
   }
   PICO_CUDA(cudaGetLastError());
   PICO_TRY(c.span_end());
-  ++launches;
+  *launches += 1;
   PICO_TRY(c.mark(3));
   if (!on_device)
     PICO_CUDA(cudaMemcpyAsync(out, d_out, nq * k * sizeof(Neighbor<T>), cudaMemcpyDeviceToHost, c.st));
   PICO_TRY(c.mark(4));
+  return 0;
+}
+
+constexpr size_t kHostChunk = (size_t)1 << 20;  // queries per pipelined chunk (host buffers)
+constexpr int kHostStreams = 3;
+
+}  // namespace
+
+// ------------------------------------------------------------------ knn
+template <typename T>
+int knn_batch(const pico_b200_tree* t, const T* q, size_t nq, size_t stride, size_t k, double e, Neighbor<T>* out,
+              unsigned flags, pico_b200_search_stats* stats) {
+  if (nq == 0 || k == 0) return 0;
+  if (nq > 0xfffffff0u) return fail(PICO_B200_ERR_UNSUPPORTED, "more than 2^32-16 queries in one call");
+  if (k > 0x7fffffffu) return fail(PICO_B200_ERR_INVALID_ARGUMENT, "k too large");
+  const bool on_device = flags & PICO_B200_DEVICE_POINTERS;
+  const bool want_async = (flags & PICO_B200_ASYNC) && on_device;
+  uint64_t launches = 0;
+  // Host buffers, big batch, no caller stream: split into chunks that rotate over a few
+  // streams so that H2D of chunk i+1, traversal of chunk i and D2H of chunk i-1 overlap
+  // (PCIe is full duplex). Each chunk is Z-ordered on its own.
+  if (!on_device && !g_cfg.has_user_stream && nq >= 2 * kHostChunk) {
+    CallCtx ctx[kHostStreams];
+    for (auto& c : ctx) PICO_TRY(c.init(t->device));
+    cudaEvent_t e0, e1;
+    PICO_CUDA(cudaEventCreate(&e0));
+    PICO_CUDA(cudaEventCreate(&e1));
+    PICO_CUDA(cudaEventRecord(e0, ctx[0].st));
+    int ci = 0;
+    for (size_t begin = 0; begin < nq; begin += kHostChunk, ++ci) {
+      const size_t cnt = std::min(kHostChunk, nq - begin);
+      CallCtx& c = ctx[ci % kHostStreams];
+      c.release();
+      PICO_TRY(knn_enqueue<T>(c, t, q + begin * stride, cnt, stride, k, e, out + begin * k, flags, false, &launches));
+    }
+    for (auto& c : ctx) PICO_CUDA(cudaStreamSynchronize(c.st));
+    PICO_CUDA(cudaEventRecord(e1, ctx[0].st));
+    PICO_CUDA(cudaEventSynchronize(e1));
+    if (stats) {
+      stats->h2d_ms = stats->reorder_ms = stats->d2h_ms = 0;
+      stats->kernel_ms = elapsed(e0, e1);  // whole pipelined call
+      stats->kernel_launches = launches;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return 0;
+  }
+  CallCtx c;
+  PICO_TRY(c.init(t->device, want_async));
+  PICO_TRY(knn_enqueue<T>(c, t, q, nq, stride, k, e, out, flags, on_device, &launches));
   if (c.async) return 0;
   PICO_CUDA(cudaStreamSynchronize(c.st));
   if (stats) {
