@@ -194,27 +194,13 @@ def run_ours(args, n_tree, n_query):
     build_wall = time.perf_counter() - t_build0
     bcast_ms = 0.0
     if world > 1:
-        size = torch.zeros(1, dtype=torch.int64, device=dev)
-        if rank == 0:
-            sz = C.c_uint64()
-            _lib.check(L.pico_b200_tree_serialize_size(handle, C.byref(sz)))
-            size[0] = sz.value
-        dist.broadcast(size, 0)
-        image = torch.empty(int(size.item()), dtype=torch.uint8, device=dev)
-        if rank == 0:
-            _lib.check(L.pico_b200_tree_serialize(handle, C.c_void_p(image.data_ptr()), 1))
+        from pico_tree_b200 import distributed as pd
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        dist.broadcast(image, 0)  # NCCL over NVLink / NVSwitch
-        e1.record()
+        dist.barrier()
+        t0 = time.perf_counter()
+        handle = pd.replicate_tree(tree if rank == 0 else None, 0, local)  # NCCL over NVLink / NVSwitch
         torch.cuda.synchronize()
-        bcast_ms = e0.elapsed_time(e1)
-        if rank != 0:
-            handle = C.c_void_p()
-            _lib.check(L.pico_b200_tree_deserialize(C.c_void_p(image.data_ptr()), image.numel(), 1, local,
-                                                    C.byref(handle)))
-        del image
+        bcast_ms = (time.perf_counter() - t0) * 1e3
     info = _lib.TreeInfo()
     _lib.check(L.pico_b200_tree_info_get(handle, C.byref(info)))
 
