@@ -52,7 +52,10 @@ typedef enum {
   PICO_B200_METRIC_L1 = 0,         /* metric_l1          metric.hpp:77-97   */
   PICO_B200_METRIC_L2_SQUARED = 1, /* metric_l2_squared  metric.hpp:99-123  */
   PICO_B200_METRIC_LPINF = 2,      /* metric_lpinf       metric.hpp:125-151 */
-  PICO_B200_METRIC_LNINF = 3       /* metric_lninf       metric.hpp:153-180 */
+  PICO_B200_METRIC_LNINF = 3,      /* metric_lninf       metric.hpp:153-180 */
+  /* topological spaces (search_nearest_topological, internal/kd_tree_search.hpp:122-229): */
+  PICO_B200_METRIC_SO2 = 4,        /* metric_so2         metric.hpp:197-221, sdim 1: S1 = [0,1)      */
+  PICO_B200_METRIC_SE2_SQUARED = 5 /* metric_se2_squared metric.hpp:223-257, sdim 3: R2 x S1         */
 } pico_b200_metric;
 
 /* internal/kd_tree_builder.hpp:35-75 */

@@ -1,0 +1,624 @@
+// kd_tree.hpp — pico_tree::kd_tree<Space_, Metric_, Index_> on top of libpico_b200.so.
+//
+// Source-compatible stand-in for the reference's class (src/pico_tree/pico_tree/kd_tree.hpp:19-435):
+// same template parameters, member types, constructor tags, search_* overloads, leaf_ranges,
+// space(), metric(), load / save, deduction guide and make_kd_tree. Where the reference runs
+// internal::build_kd_tree and the internal::search_* recursions on the calling thread, this class
+// makes ONE call into the C-ABI of include/pico_b200.h; the tree lives in HBM as a flat array of
+// nodes next to leaf-ordered points. The header holds no distance arithmetic and no tree walk,
+// and there is no CPU fallback: without a B200 every call throws std::runtime_error.
+//
+// Additions the reference does not have (its Python binding loops over single queries,
+// src/pyco_tree/pico_tree/_pyco_tree/kd_tree.hpp:117-268): search_nn_batch, search_knn_batch,
+// search_radius_batch, search_box_batch — a whole query set per call, which is how the device is
+// meant to be used. Single-query overloads are one-query batches (tens of microseconds of launch
+// latency each): correct, but not the fast path.
+//
+// Vocabulary types: by default from "traits.hpp" next to this file. Define
+// PICO_TREE_B200_USE_REFERENCE_TRAITS to take them from the reference's unmodified headers
+// instead (pico_tree/core.hpp, map.hpp, metric.hpp, ... must then be on the include path); the
+// Eigen / OpenCV adaptors of the reference then work unchanged. See INTEGRATION.md.
+#pragma once
+
+#include <algorithm>
+#include <cstddef>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <functional>
+#include <iterator>
+#include <limits>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <type_traits>
+#include <utility>
+#include <vector>
+
+#include "../pico_b200.h"
+
+#if defined(PICO_TREE_B200_USE_REFERENCE_TRAITS)
+#include <pico_tree/core.hpp>
+#include <pico_tree/internal/kd_tree_builder.hpp>  // build tags (max_leaf_size_t, bounds_t, rules)
+#include <pico_tree/map.hpp>
+#include <pico_tree/map_traits.hpp>
+#include <pico_tree/metric.hpp>
+#include <pico_tree/point_traits.hpp>
+#include <pico_tree/space_traits.hpp>
+#else
+#include "traits.hpp"
+#endif
+
+namespace pico_tree {
+
+namespace b200 {
+
+// Device the next kd_tree is created on. Defaults to $PICO_B200_DEVICE or 0.
+inline int& default_device() {
+  static int device = [] {
+    char const* e = std::getenv("PICO_B200_DEVICE");
+    return e ? std::atoi(e) : 0;
+  }();
+  return device;
+}
+
+inline void check(int rc) {
+  if (rc == PICO_B200_OK) return;
+  std::string msg = std::string("pico_b200: ") + pico_b200_last_error();
+  if (rc == PICO_B200_ERR_INVALID_ARGUMENT) throw std::invalid_argument(msg);
+  throw std::runtime_error(msg);
+}
+
+template <typename T_>
+struct unwrap {
+  using type = T_;
+};
+template <typename T_>
+struct unwrap<std::reference_wrapper<T_>> {
+  using type = std::remove_const_t<T_>;
+};
+template <typename T_>
+using unwrap_t = typename unwrap<T_>::type;
+
+template <typename Scalar_>
+struct scalar_id;
+template <>
+struct scalar_id<float> : std::integral_constant<int, PICO_B200_F32> {};
+template <>
+struct scalar_id<double> : std::integral_constant<int, PICO_B200_F64> {};
+
+// Metrics the device implements. A user-defined metric type has no device functor: the
+// static_assert in kd_tree points here.
+template <typename Metric_>
+struct metric_id : std::integral_constant<int, -1> {};
+template <>
+struct metric_id<metric_l1> : std::integral_constant<int, PICO_B200_METRIC_L1> {};
+template <>
+struct metric_id<metric_l2_squared> : std::integral_constant<int, PICO_B200_METRIC_L2_SQUARED> {};
+template <>
+struct metric_id<metric_lpinf> : std::integral_constant<int, PICO_B200_METRIC_LPINF> {};
+template <>
+struct metric_id<metric_lninf> : std::integral_constant<int, PICO_B200_METRIC_LNINF> {};
+template <>
+struct metric_id<metric_so2> : std::integral_constant<int, PICO_B200_METRIC_SO2> {};
+template <>
+struct metric_id<metric_se2_squared> : std::integral_constant<int, PICO_B200_METRIC_SE2_SQUARED> {};
+
+template <typename Rule_>
+struct rule_id;
+template <>
+struct rule_id<sliding_midpoint_max_side_t>
+    : std::integral_constant<int, PICO_B200_RULE_SLIDING_MIDPOINT_MAX_SIDE> {};
+template <>
+struct rule_id<midpoint_max_side_t> : std::integral_constant<int, PICO_B200_RULE_MIDPOINT_MAX_SIDE> {};
+template <>
+struct rule_id<median_max_side_t> : std::integral_constant<int, PICO_B200_RULE_MEDIAN_MAX_SIDE> {};
+
+inline std::pair<int, size_t> stop_of(max_leaf_size_t const& s) { return {PICO_B200_STOP_MAX_LEAF_SIZE, s.value}; }
+inline std::pair<int, size_t> stop_of(max_leaf_depth_t const& s) { return {PICO_B200_STOP_MAX_LEAF_DEPTH, s.value}; }
+
+// A space seen as rows of scalars: either the caller's memory (all points lie `stride` scalars
+// apart, which is what space_map, std::vector<std::array>, Eigen and cv::Mat give) or, for a
+// space whose points are scattered, a gathered copy.
+template <typename Space_>
+class rows_of {
+  using space_type = unwrap_t<Space_>;
+  using traits = space_traits<space_type>;
+  using ptraits = point_traits<std::remove_cv_t<std::remove_reference_t<typename traits::point_type>>>;
+
+ public:
+  using scalar_type = typename traits::scalar_type;
+
+  explicit rows_of(space_type const& s) : n_(traits::size(s)), sdim_(dim_of(s)), stride_(sdim_) {
+    if (n_ == 0) return;
+    scalar_type const* const p0 = at(s, 0);
+    data_ = p0;
+    bool regular = true;
+    if (n_ > 1) {
+      auto const a = reinterpret_cast<std::uintptr_t>(p0);
+      auto const b = reinterpret_cast<std::uintptr_t>(at(s, 1));
+      regular = b > a && (b - a) % sizeof(scalar_type) == 0 && (b - a) / sizeof(scalar_type) >= sdim_;
+      if (regular) {
+        stride_ = (b - a) / sizeof(scalar_type);
+        for (size_t i = 2; i < n_ && regular; ++i) regular = at(s, i) == p0 + i * stride_;
+      }
+    }
+    if (!regular) {
+      copy_.resize(n_ * sdim_);
+      for (size_t i = 0; i < n_; ++i) std::copy_n(at(s, i), sdim_, copy_.data() + i * sdim_);
+      data_ = copy_.data();
+      stride_ = sdim_;
+    }
+  }
+
+  scalar_type const* data() const { return data_; }
+  size_t size() const { return n_; }
+  size_t sdim() const { return sdim_; }
+  size_t stride() const { return stride_; }
+
+  static size_t dim_of(space_type const& s) {
+    if constexpr (traits::dim != dynamic_extent) {
+      return traits::dim;
+    } else {
+      return traits::sdim(s);
+    }
+  }
+
+ private:
+  static scalar_type const* at(space_type const& s, size_t i) { return ptraits::data(traits::point_at(s, i)); }
+
+  size_t n_;
+  size_t sdim_;
+  size_t stride_;
+  scalar_type const* data_ = nullptr;
+  std::vector<scalar_type> copy_;
+};
+
+template <typename Point_>
+using point_traits_of = point_traits<std::remove_cv_t<std::remove_reference_t<Point_>>>;
+
+struct tree_deleter {
+  void operator()(pico_b200_tree* t) const { pico_b200_tree_destroy(t); }
+};
+
+// frees a buffer handed out by the library (ragged radius / box results)
+struct lib_buffer {
+  void* p = nullptr;
+  ~lib_buffer() { pico_b200_free(p); }
+};
+
+}  // namespace b200
+
+template <typename Space_, typename Metric_ = metric_l2_squared, typename Index_ = int>
+class kd_tree {
+  static_assert(std::is_same_v<std::remove_cv_t<Space_>, Space_>, "SPACE_TYPE_MUST_BE_NON-CONST_NON-VOLATILE");
+  static_assert(b200::metric_id<Metric_>::value >= 0,
+                "METRIC_HAS_NO_DEVICE_IMPLEMENTATION: libpico_b200 implements metric_l1, metric_l2_squared, "
+                "metric_lpinf, metric_lninf, metric_so2 and metric_se2_squared");
+  static_assert(std::is_integral_v<Index_>, "INDEX_NOT_AN_INTEGRAL_TYPE");
+
+  using unwrapped_space = b200::unwrap_t<Space_>;
+  using traits = space_traits<unwrapped_space>;
+  using rows_type = b200::rows_of<Space_>;
+
+  template <typename It_>
+  class iterator_range {
+   public:
+    using iterator_type = It_;
+    using difference_type = typename std::iterator_traits<It_>::difference_type;
+    constexpr iterator_range(It_ b, It_ e) : begin_(b), end_(e) {}
+    constexpr It_ begin() const { return begin_; }
+    constexpr It_ end() const { return end_; }
+
+   private:
+    It_ begin_, end_;
+  };
+
+ public:
+  using size_type = size_t;
+  using index_type = Index_;
+  using scalar_type = typename traits::scalar_type;
+  static constexpr size_type dim = traits::dim;
+  using space_type = Space_;
+  using metric_type = Metric_;
+  using neighbor_type = neighbor<index_type, scalar_type>;
+  using leaf_range_type = iterator_range<typename std::vector<index_type>::const_iterator>;
+
+  static_assert(std::is_same_v<scalar_type, float> || std::is_same_v<scalar_type, double>,
+                "SCALAR_TYPE_MUST_BE_FLOAT_OR_DOUBLE");
+
+  // Builds the tree on the device (pico_b200_tree_create). The space is taken by value like in
+  // the reference: move it in, or pass a std::reference_wrapper, to avoid a host copy. The
+  // device always gets its own copy of the coordinates.
+  template <typename Stop_, typename Bounds_ = bounds_from_space_t, typename Rule_ = sliding_midpoint_max_side_t>
+  kd_tree(space_type space, splitter_stop_condition_t<Stop_> const& stop_condition,
+          splitter_start_bounds_t<Bounds_> const& start_bounds = Bounds_{},
+          splitter_rule_t<Rule_> const& = Rule_{})
+      : space_(std::move(space)), metric_() {
+    rows_type rows(unwrapped());
+    auto const stop = b200::stop_of(stop_condition.derived());
+    scalar_type const* bmin = nullptr;
+    scalar_type const* bmax = nullptr;
+    if constexpr (!std::is_same_v<Bounds_, bounds_from_space_t>) {
+      bmin = b200::point_traits_of<decltype(start_bounds.derived().min())>::data(start_bounds.derived().min());
+      bmax = b200::point_traits_of<decltype(start_bounds.derived().max())>::data(start_bounds.derived().max());
+    }
+    pico_b200_tree* h = nullptr;
+    b200::check(pico_b200_tree_create(rows.data(), rows.size(), rows.sdim(), rows.stride(),
+                                      b200::scalar_id<scalar_type>::value, b200::metric_id<Metric_>::value,
+                                      b200::rule_id<Rule_>::value, stop.first, stop.second, bmin, bmax,
+                                      b200::default_device(), &h));
+    handle_.reset(h);
+    n_ = rows.size();
+    sdim_ = rows.sdim();
+  }
+
+  kd_tree(kd_tree const&) = delete;
+  kd_tree(kd_tree&&) = default;
+  kd_tree& operator=(kd_tree const&) = delete;
+  kd_tree& operator=(kd_tree&&) = default;
+
+  // ---------------------------------------------------------------- single query
+  // Hands the neighbours of x to `visitor` in ascending order of distance until one lies
+  // beyond visitor.max(). The reference calls the visitor for every point of every leaf its
+  // depth-first search reaches (kd_tree.hpp:106-120, internal/kd_tree_search.hpp:52-105); a
+  // visitor therefore cannot tell which far points it will see, only that every point closer
+  // than its final max() was offered — which the ordered stream guarantees too, with max()
+  // only ever shrinking. The stream is produced by exact device knn calls with a growing k.
+  template <typename P_, typename V_>
+  void search_nearest(P_ const& x, V_& visitor) const {
+    scalar_type const* q = query_data(x);
+    size_type fed = 0;
+    std::vector<neighbor_type> buf;
+    for (size_type k = std::min<size_type>(n_, 32);; k = std::min(n_, k * 4)) {
+      buf.resize(k);
+      knn_call(q, 1, sdim_, k, 0.0, buf.data());
+      for (; fed < k; ++fed) {
+        if (buf[fed].distance > visitor.max()) return;
+        visitor(buf[fed].index, buf[fed].distance);
+      }
+      if (k == n_) return;
+    }
+  }
+
+  template <typename P_>
+  void search_nn(P_ const& x, neighbor_type& nn) const {
+    knn_call(query_data(x), 1, sdim_, 1, 0.0, &nn);
+  }
+
+  // Approximate nearest neighbour: at most a factor e farther than the true one; the returned
+  // distance is scaled by 1/e like the reference's (search_visitor.hpp:178-183).
+  template <typename P_>
+  void search_nn(P_ const& x, scalar_type const e, neighbor_type& nn) const {
+    knn_call(query_data(x), 1, sdim_, 1, static_cast<double>(e), &nn);
+  }
+
+  template <typename P_, typename RandomAccessIterator_>
+  void search_knn(P_ const& x, RandomAccessIterator_ begin, RandomAccessIterator_ end) const {
+    knn_range(x, 0.0, begin, end);
+  }
+
+  template <typename P_>
+  void search_knn(P_ const& x, size_type const k, std::vector<neighbor_type>& knn) const {
+    knn.resize(std::min(k, n_));  // fewer points than k: all of them (kd_tree.hpp:190-195)
+    knn_call(query_data(x), 1, sdim_, knn.size(), 0.0, knn.data());
+  }
+
+  template <typename P_, typename RandomAccessIterator_>
+  void search_knn(P_ const& x, scalar_type const e, RandomAccessIterator_ begin, RandomAccessIterator_ end) const {
+    knn_range(x, static_cast<double>(e), begin, end);
+  }
+
+  template <typename P_>
+  void search_knn(P_ const& x, size_type const k, scalar_type const e, std::vector<neighbor_type>& knn) const {
+    knn.resize(std::min(k, n_));
+    knn_call(query_data(x), 1, sdim_, knn.size(), static_cast<double>(e), knn.data());
+  }
+
+  template <typename P_>
+  void search_radius(P_ const& x, scalar_type const radius, std::vector<neighbor_type>& n,
+                     bool const sort = false) const {
+    radius_one(query_data(x), radius, 0.0, n, sort);
+  }
+
+  template <typename P_>
+  void search_radius(P_ const& x, scalar_type const radius, scalar_type const e, std::vector<neighbor_type>& n,
+                     bool const sort = false) const {
+    radius_one(query_data(x), radius, static_cast<double>(e), n, sort);
+  }
+
+  template <typename P_>
+  void search_box(P_ const& min, P_ const& max, std::vector<index_type>& idxs) const {
+    std::uint64_t offsets[2] = {0, 0};
+    b200::lib_buffer out;
+    std::int32_t* raw = nullptr;
+    b200::check(pico_b200_box(handle_.get(), query_data(min), query_data(max), 1, sdim_, offsets, &raw, 0, nullptr));
+    out.p = raw;
+    idxs.assign(raw, raw + offsets[1]);
+  }
+
+  // ---------------------------------------------------------------- batches (one device call)
+  // queries: any space (space_map, std::vector<std::array>, Eigen matrix, ...) of the tree's
+  // scalar type and dimension. knn receives queries.size() rows of min(k, n) neighbours.
+  template <typename Queries_>
+  void search_knn_batch(Queries_ const& queries, size_type const k, std::vector<neighbor_type>& knn) const {
+    knn_batch(queries, k, 0.0, knn);
+  }
+
+  template <typename Queries_>
+  void search_knn_batch(Queries_ const& queries, size_type const k, scalar_type const e,
+                        std::vector<neighbor_type>& knn) const {
+    knn_batch(queries, k, static_cast<double>(e), knn);
+  }
+
+  template <typename Queries_>
+  void search_nn_batch(Queries_ const& queries, std::vector<neighbor_type>& nns) const {
+    knn_batch(queries, 1, 0.0, nns);
+  }
+
+  // Ragged results: the neighbours of query i are flat[offsets[i] .. offsets[i + 1]).
+  template <typename Queries_>
+  void search_radius_batch(Queries_ const& queries, scalar_type const radius, std::vector<size_type>& offsets,
+                           std::vector<neighbor_type>& flat, bool const sort = false,
+                           scalar_type const e = scalar_type(0)) const {
+    b200::rows_of<Queries_> rows(unwrap_queries(queries));
+    check_queries(rows);
+    std::vector<std::uint64_t> offs(rows.size() + 1, 0);
+    b200::lib_buffer out;
+    b200::check(pico_b200_radius(handle_.get(), rows.data(), rows.size(), rows.stride(), static_cast<double>(radius),
+                                 static_cast<double>(e), offs.data(), &out.p, sort ? unsigned(PICO_B200_SORT_RESULTS) : 0u,
+                                 nullptr));
+    offsets.assign(offs.begin(), offs.end());
+    flat.resize(offs.back());
+    take_neighbors(out.p, flat.size(), flat.data());
+  }
+
+  // Same, as one vector per query (what the reference's binding returns through its DArray).
+  template <typename Queries_>
+  void search_radius_batch(Queries_ const& queries, scalar_type const radius,
+                           std::vector<std::vector<neighbor_type>>& nns, bool const sort = false,
+                           scalar_type const e = scalar_type(0)) const {
+    std::vector<size_type> offsets;
+    std::vector<neighbor_type> flat;
+    search_radius_batch(queries, radius, offsets, flat, sort, e);
+    nns.resize(offsets.size() - 1);
+    for (size_type i = 0; i + 1 < offsets.size(); ++i)
+      nns[i].assign(flat.begin() + static_cast<std::ptrdiff_t>(offsets[i]),
+                    flat.begin() + static_cast<std::ptrdiff_t>(offsets[i + 1]));
+  }
+
+  // Box i is [mins[i], maxs[i]] (inclusive); indices of box i are flat[offsets[i] .. offsets[i+1]).
+  template <typename Queries_>
+  void search_box_batch(Queries_ const& mins, Queries_ const& maxs, std::vector<size_type>& offsets,
+                        std::vector<index_type>& flat) const {
+    b200::rows_of<Queries_> lo(unwrap_queries(mins)), hi(unwrap_queries(maxs));
+    check_queries(lo);
+    check_queries(hi);
+    if (lo.size() != hi.size()) throw std::invalid_argument("query min and max don't have equal size");
+    if (lo.stride() != hi.stride()) throw std::invalid_argument("query min and max have different strides");
+    std::vector<std::uint64_t> offs(lo.size() + 1, 0);
+    b200::lib_buffer out;
+    std::int32_t* raw = nullptr;
+    b200::check(pico_b200_box(handle_.get(), lo.data(), hi.data(), lo.size(), lo.stride(), offs.data(), &raw, 0,
+                              nullptr));
+    out.p = raw;
+    offsets.assign(offs.begin(), offs.end());
+    flat.assign(raw, raw + offs.back());
+  }
+
+  // ---------------------------------------------------------------- structure
+  // Index ranges of all non-empty leaves in depth-first order (kd_tree.hpp:325). The ranges
+  // point into a host copy of the index permutation fetched from the device on first use.
+  std::vector<leaf_range_type> leaf_ranges() const {
+    host_mirror const& m = mirror();
+    std::vector<leaf_range_type> ranges;
+    ranges.reserve(m.leaves.size());
+    for (auto const& be : m.leaves)
+      ranges.emplace_back(m.indices.begin() + be.first, m.indices.begin() + be.second);
+    return ranges;
+  }
+
+  space_type const& space() const { return space_; }
+  metric_type const& metric() const { return metric_; }
+
+  // Shape of the device tree and the device time of its build.
+  pico_b200_tree_info info() const {
+    pico_b200_tree_info i;
+    b200::check(pico_b200_tree_info_get(handle_.get(), &i));
+    return i;
+  }
+
+  // The C handle, for callers that drive the C-ABI directly (device-resident batches, streams).
+  pico_b200_tree const* native_handle() const { return handle_.get(); }
+
+  // ---------------------------------------------------------------- load / save
+  // Byte-compatible with the reference's stream (kd_tree.hpp:336-370): trees saved by either
+  // library load in the other. The points are not stored.
+  static kd_tree load(space_type space, std::string const& filename) {
+    std::fstream stream(filename, std::ios::in | std::ios::binary);
+    if (!stream.is_open()) throw std::runtime_error("unable to open file: " + filename);
+    return load(std::move(space), stream);
+  }
+
+  static kd_tree load(space_type space, std::iostream& stream) {
+    static_assert(sizeof(index_type) == 4, "LOAD_AND_SAVE_NEED_A_32_BIT_INDEX_TYPE");
+    auto const pos = stream.tellg();
+    std::vector<char> bytes((std::istreambuf_iterator<char>(stream)), std::istreambuf_iterator<char>());
+    std::uint64_t consumed = 0;
+    kd_tree tree(std::move(space), bytes.data(), bytes.size(), &consumed);
+    stream.clear();
+    stream.seekg(pos + static_cast<std::streamoff>(consumed));
+    return tree;
+  }
+
+  static void save(kd_tree const& tree, std::string const& filename) {
+    std::fstream stream(filename, std::ios::out | std::ios::binary);
+    if (!stream.is_open()) throw std::runtime_error("unable to open file: " + filename);
+    save(tree, stream);
+  }
+
+  static void save(kd_tree const& tree, std::iostream& stream) {
+    static_assert(sizeof(index_type) == 4, "LOAD_AND_SAVE_NEED_A_32_BIT_INDEX_TYPE");
+    std::uint64_t bytes = 0;
+    b200::check(pico_b200_tree_save_size(tree.handle_.get(), &bytes));
+    std::vector<char> buf(bytes);
+    b200::check(pico_b200_tree_save(tree.handle_.get(), buf.data()));
+    stream.write(buf.data(), static_cast<std::streamsize>(buf.size()));
+  }
+
+ private:
+  struct host_mirror {
+    std::vector<index_type> indices;
+    std::vector<std::pair<std::ptrdiff_t, std::ptrdiff_t>> leaves;
+  };
+  struct lazy_mirror {
+    std::once_flag once;
+    host_mirror data;
+  };
+
+  kd_tree(space_type space, char const* bytes, size_type size, std::uint64_t* consumed)
+      : space_(std::move(space)), metric_() {
+    rows_type rows(unwrapped());
+    pico_b200_tree* h = nullptr;
+    b200::check(pico_b200_tree_load(rows.data(), rows.size(), rows.sdim(), rows.stride(),
+                                    b200::scalar_id<scalar_type>::value, b200::metric_id<Metric_>::value, bytes, size,
+                                    b200::default_device(), &h, consumed));
+    handle_.reset(h);
+    n_ = rows.size();
+    sdim_ = rows.sdim();
+  }
+
+  unwrapped_space const& unwrapped() const { return space_; }
+
+  template <typename Q_>
+  static b200::unwrap_t<Q_> const& unwrap_queries(Q_ const& q) {
+    return q;
+  }
+
+  template <typename P_>
+  scalar_type const* query_data(P_ const& x) const {
+    using pt = b200::point_traits_of<P_>;
+    static_assert(std::is_same_v<scalar_type, typename pt::scalar_type>, "POINT_AND_TREE_SCALAR_TYPES_DIFFER");
+    static_assert(dim == pt::dim || dim == dynamic_extent || pt::dim == dynamic_extent, "POINT_AND_TREE_DIMS_DIFFER");
+    if constexpr (pt::dim == dynamic_extent) {
+      if (pt::size(x) != sdim_) throw std::invalid_argument("point and tree dimensions differ");
+    }
+    return pt::data(x);
+  }
+
+  template <typename Rows_>
+  void check_queries(Rows_ const& rows) const {
+    static_assert(std::is_same_v<scalar_type, typename Rows_::scalar_type>, "POINT_AND_TREE_SCALAR_TYPES_DIFFER");
+    if (rows.size() != 0 && rows.sdim() != sdim_) throw std::invalid_argument("query and tree dimensions differ");
+  }
+
+  static constexpr bool abi_layout =
+      sizeof(index_type) == 4 && sizeof(neighbor_type) == (sizeof(scalar_type) == 4 ? 8 : 16) &&
+      offsetof(neighbor_type, distance) == sizeof(scalar_type);
+
+  // library records {int32 index; Scalar distance} -> neighbor_type
+  static void take_neighbors(void const* src, size_type count, neighbor_type* dst) {
+    if constexpr (abi_layout) {
+      if (count) std::memcpy(dst, src, count * sizeof(neighbor_type));
+    } else {
+      struct rec {
+        std::int32_t index;
+        scalar_type distance;
+      };
+      rec const* r = static_cast<rec const*>(src);
+      for (size_type i = 0; i < count; ++i) dst[i] = neighbor_type(static_cast<index_type>(r[i].index), r[i].distance);
+    }
+  }
+
+  void knn_call(scalar_type const* q, size_type nq, size_type stride, size_type k, double e,
+                neighbor_type* out) const {
+    if (nq == 0 || k == 0) return;
+    if constexpr (abi_layout) {
+      b200::check(pico_b200_knn(handle_.get(), q, nq, stride, k, e, out, 0, nullptr));
+    } else {
+      std::vector<unsigned char> tmp(nq * k * (sizeof(scalar_type) == 4 ? 8 : 16));
+      b200::check(pico_b200_knn(handle_.get(), q, nq, stride, k, e, tmp.data(), 0, nullptr));
+      take_neighbors(tmp.data(), nq * k, out);
+    }
+  }
+
+  template <typename P_, typename It_>
+  void knn_range(P_ const& x, double e, It_ begin, It_ end) const {
+    static_assert(std::is_same_v<typename std::iterator_traits<It_>::value_type, neighbor_type>,
+                  "ITERATOR_VALUE_TYPE_DOES_NOT_EQUAL_NEIGHBOR_TYPE");
+    size_type const k = static_cast<size_type>(std::distance(begin, end));
+    size_type const kk = std::min(k, n_);
+    std::vector<neighbor_type> tmp(kk);
+    knn_call(query_data(x), 1, sdim_, kk, e, tmp.data());
+    It_ it = std::copy(tmp.begin(), tmp.end(), begin);
+    // range longer than the point set: the reference leaves the tail unspecified apart from
+    // an infinite last distance (search_visitor.hpp:98-103)
+    for (; it != end; ++it) *it = neighbor_type(index_type(0), std::numeric_limits<scalar_type>::max());
+  }
+
+  template <typename Queries_>
+  void knn_batch(Queries_ const& queries, size_type k, double e, std::vector<neighbor_type>& knn) const {
+    b200::rows_of<Queries_> rows(unwrap_queries(queries));
+    check_queries(rows);
+    k = std::min(k, n_);
+    knn.resize(rows.size() * k);
+    knn_call(rows.data(), rows.size(), rows.stride(), k, e, knn.data());
+  }
+
+  void radius_one(scalar_type const* q, scalar_type radius, double e, std::vector<neighbor_type>& n, bool sort) const {
+    std::uint64_t offsets[2] = {0, 0};
+    b200::lib_buffer out;
+    b200::check(pico_b200_radius(handle_.get(), q, 1, sdim_, static_cast<double>(radius), e, offsets, &out.p,
+                                 sort ? unsigned(PICO_B200_SORT_RESULTS) : 0u, nullptr));
+    n.resize(offsets[1]);
+    take_neighbors(out.p, n.size(), n.data());
+  }
+
+  host_mirror const& mirror() const {
+    std::call_once(mirror_->once, [this] {
+      pico_b200_tree_info const i = info();
+      std::vector<std::int32_t> idx(i.n_points);
+      host_mirror& m = mirror_->data;
+      auto collect = [&](auto const& nodes) {
+        for (auto const& nd : nodes)
+          if (nd.split_dim == PICO_B200_LEAF && nd.b.end_idx > nd.a.begin_idx)
+            m.leaves.emplace_back(static_cast<std::ptrdiff_t>(nd.a.begin_idx),
+                                  static_cast<std::ptrdiff_t>(nd.b.end_idx));
+      };
+      if constexpr (sizeof(scalar_type) == 4) {
+        std::vector<pico_b200_node_f32> nodes(i.n_nodes);
+        b200::check(pico_b200_tree_export(handle_.get(), nodes.data(), idx.data(), nullptr));
+        collect(nodes);  // pre-order == depth-first order
+      } else {
+        std::vector<pico_b200_node_f64> nodes(i.n_nodes);
+        b200::check(pico_b200_tree_export(handle_.get(), nodes.data(), idx.data(), nullptr));
+        collect(nodes);
+      }
+      m.indices.assign(idx.begin(), idx.end());
+    });
+    return mirror_->data;
+  }
+
+  space_type space_;
+  metric_type metric_;
+  std::unique_ptr<pico_b200_tree, b200::tree_deleter> handle_;
+  size_type n_ = 0;
+  size_type sdim_ = 0;
+  std::unique_ptr<lazy_mirror> mirror_ = std::make_unique<lazy_mirror>();
+};
+
+template <typename Space_, typename... Args>
+kd_tree(Space_, Args...) -> kd_tree<Space_, metric_l2_squared, int>;
+
+template <typename Metric_ = metric_l2_squared, typename Index_ = int, typename Bounds_ = bounds_from_space_t,
+          typename Rule_ = sliding_midpoint_max_side_t, typename Space_, typename Stop_>
+kd_tree<std::decay_t<Space_>, Metric_, Index_> make_kd_tree(
+    Space_&& space, splitter_stop_condition_t<Stop_> const& stop_condition,
+    splitter_start_bounds_t<Bounds_> const& start_bounds = Bounds_{}, splitter_rule_t<Rule_> const& rule = Rule_{}) {
+  return kd_tree<std::decay_t<Space_>, Metric_, Index_>(std::forward<Space_>(space), stop_condition, start_bounds,
+                                                        rule);
+}
+
+}  // namespace pico_tree
