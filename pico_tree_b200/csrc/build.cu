@@ -35,6 +35,14 @@ namespace {
 
 constexpr int kWarpNodeMax = 1024;  // nodes up to this many points are split by one warp
 constexpr int kBigThreads = 1024;   // CTA size for bigger nodes
+// Nodes above kHugeMin points (the first ~8 levels of a multi-million point tree) are not given
+// to a single CTA: all such nodes of a level are cut into chunks of kChunk index positions and
+// split by five grid-wide passes (plan, count, resolve, scatter, swap) so that every SM works
+// on them. profiles/r1/launches_knn1_v2.csv: one CTA per node spent 38 of 45 ms there.
+constexpr int kHugeMin = 32768;
+constexpr int kChunkThreads = 256;
+constexpr int kChunkItems = 8;
+constexpr int kChunk = kChunkThreads * kChunkItems;
 
 template <typename T>
 struct BNode {
@@ -47,6 +55,30 @@ struct BNode {
   T left_max, right_min;
 };
 
+// one huge node of the current level
+template <typename T>
+struct HugeNode {
+  uint32_t node;         // BFS id
+  int32_t begin, end;
+  int32_t sd;
+  T split_val;
+  uint32_t first_chunk;  // exclusive scan of the chunk counts over the level's huge list
+  int32_t split;
+  int32_t nl;            // points left of split_val
+  int32_t m;             // misplaced pairs to exchange
+  int32_t mode;          // 0 = partition by exchanges, 1 = nothing (more) to move
+};
+
+// what one chunk contributes to its node
+template <typename T>
+struct ChunkStat {
+  int32_t lt;         // points with coord < split_val
+  int32_t lt_prefix;  // exclusive prefix of lt inside the node (huge_resolve)
+  T mn, mn2, mx;      // smallest, second smallest (may equal mn), largest coordinate
+  int32_t mn_pos;     // first position of mn
+  int32_t mx_pos;     // last position of mx
+};
+
 template <typename T>
 struct BuildState {
   const T* raw;        // [n][sdim] packed row-major
@@ -55,9 +87,13 @@ struct BuildState {
   int32_t* tmp;        // [n] scratch for the partition
   BNode<T>* nodes;     // BFS table
   T* boxes;            // [cap][2*sdim]: cut box on the way down, tight box on the way up
-  uint32_t* counters;  // [0] n_nodes  [1] n_big_next  [2] n_leaves
+  uint32_t* counters;  // [0] n_nodes  [1] n_big_next  [2] n_leaves  [3] n_huge_next  [4] chunks of this level
   uint32_t* big_next;  // ids of next-level nodes that need a CTA
+  uint32_t* huge_next; // ids of next-level nodes that need the chunked passes
+  HugeNode<T>* huge;   // the current level's huge nodes
+  ChunkStat<T>* chunks;
   int32_t rule, stop_kind, stop_value;
+  int32_t huge_min;    // nodes with more points take the chunked passes (kHugeMin; PICO_B200_HUGE_MIN overrides)
 };
 
 // ------------------------------------------------------------------ cooperative groups
@@ -206,6 +242,56 @@ __device__ void finish_leaf(const BuildState<T>& s, BNode<T>& nd, T* box) {
   }
 }
 
+// is_leaf of a node that does not exist yet (kd_tree_builder.hpp:410-425)
+template <typename T>
+__device__ __forceinline__ bool will_be_leaf(const BuildState<T>& s, int cnt, int depth) {
+  return (s.stop_kind == PICO_B200_STOP_MAX_LEAF_SIZE) ? (cnt <= s.stop_value) : (depth == s.stop_value || cnt <= 1);
+}
+
+// Appends the two children of `node_id` to the BFS table, files them for the next level and
+// writes their cut boxes (kd_tree_builder.hpp:379-383). Called by the whole group.
+template <typename T, int G>
+__device__ void emit_children(const BuildState<T>& s, uint32_t node_id, int sd, int split, T split_val) {
+  BNode<T>& nd = s.nodes[node_id];
+  const int tid = Grp<G>::tid();
+  const int begin = nd.begin, end = nd.end, depth = nd.depth, sdim = s.sdim;
+  const T* box = s.boxes + (size_t)node_id * 2 * sdim;
+  if (tid == 0) {
+    const uint32_t c = atomicAdd(&s.counters[0], 2u);
+    nd.left = (int32_t)c;
+    nd.right = (int32_t)c + 1;
+    nd.split_dim = sd;
+    BNode<T>& l = s.nodes[c];
+    BNode<T>& r = s.nodes[c + 1];
+    l.begin = begin;
+    l.end = split;
+    l.depth = depth + 1;
+    r.begin = split;
+    r.end = end;
+    r.depth = depth + 1;
+    l.left = l.right = r.left = r.right = -1;
+    l.split_dim = r.split_dim = -1;
+    const int cnts[2] = {split - begin, end - split};
+    for (int k = 0; k < 2; ++k) {
+      const bool huge = cnts[k] > s.huge_min && s.rule != PICO_B200_RULE_MEDIAN_MAX_SIDE &&
+                        !will_be_leaf(s, cnts[k], depth + 1);
+      if (huge)
+        s.huge_next[atomicAdd(&s.counters[3], 1u)] = c + k;
+      else if (cnts[k] > kWarpNodeMax)
+        s.big_next[atomicAdd(&s.counters[1], 1u)] = c + k;
+    }
+  }
+  Grp<G>::sync();
+  const uint32_t cc = (uint32_t)nd.left;
+  T* lb = s.boxes + (size_t)cc * 2 * sdim;
+  T* rb = lb + 2 * sdim;
+  for (int d = tid; d < 2 * sdim; d += G) {
+    const T v = box[d];
+    lb[d] = (d == sdim + sd) ? split_val : v;
+    rb[d] = (d == sd) ? split_val : v;
+  }
+}
+
 template <typename T, int G>
 __device__ void process_node(const BuildState<T>& s, uint32_t node_id) {
   BNode<T>& nd = s.nodes[node_id];
@@ -341,36 +427,7 @@ __device__ void process_node(const BuildState<T>& s, uint32_t node_id) {
     // midpoint with nl == 0 or nl == cnt: one child is empty, nothing moves.
   }
 
-  if (tid == 0) {
-    const uint32_t c = atomicAdd(&s.counters[0], 2u);
-    nd.left = (int32_t)c;
-    nd.right = (int32_t)c + 1;
-    nd.split_dim = sd;
-    BNode<T>& l = s.nodes[c];
-    BNode<T>& r = s.nodes[c + 1];
-    l.begin = begin;
-    l.end = split;
-    l.depth = depth + 1;
-    r.begin = split;
-    r.end = end;
-    r.depth = depth + 1;
-    l.left = l.right = r.left = r.right = -1;
-    l.split_dim = r.split_dim = -1;
-    if (split - begin > kWarpNodeMax) s.big_next[atomicAdd(&s.counters[1], 1u)] = c;
-    if (end - split > kWarpNodeMax) s.big_next[atomicAdd(&s.counters[1], 1u)] = c + 1;
-  }
-  Grp<G>::sync();
-  // children's cut boxes: kd_tree_builder.hpp:379-383
-  {
-    const uint32_t cc = (uint32_t)nd.left;
-    T* lb = s.boxes + (size_t)cc * 2 * sdim;
-    T* rb = lb + 2 * sdim;
-    for (int d = tid; d < 2 * sdim; d += G) {
-      const T v = box[d];
-      lb[d] = (d == sdim + sd) ? split_val : v;
-      rb[d] = (d == sd) ? split_val : v;
-    }
-  }
+  emit_children<T, G>(s, node_id, sd, split, split_val);
 }
 
 template <typename T>
@@ -384,6 +441,268 @@ __global__ void __launch_bounds__(256) split_level_warp(BuildState<T> s, uint32_
 template <typename T>
 __global__ void __launch_bounds__(kBigThreads) split_level_block(BuildState<T> s, const uint32_t* big_list) {
   process_node<T, kBigThreads>(s, big_list[blockIdx.x]);
+}
+
+// ------------------------------------------------------------------ huge nodes: chunked passes
+// The exchanges std::partition makes are a function of the exclusive prefix count P(i) of
+// "coord < split_val" flags alone: with nl = P(end) and split = begin + nl,
+//   the j-th misplaced element of the left part  (i <  split, flag 0) has j = (i - begin) - P(i),
+//   the j-th misplaced element from the right end (i >= split, flag 1) has j = nl - P(i) - 1,
+// and element j of one list is exchanged with element j of the other. So a huge node needs one
+// counting pass, one scan over its chunk counts, one pass that writes the two lists and one that
+// exchanges — each spread over all SMs — instead of one CTA crawling over millions of indices.
+
+// which huge node does chunk c belong to (largest h with first_chunk[h] <= c)
+template <typename T>
+__device__ __forceinline__ int huge_of_chunk(const HugeNode<T>* huge, int n_huge, uint32_t c) {
+  int lo = 0, hi = n_huge - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (huge[mid].first_chunk <= c)
+      lo = mid;
+    else
+      hi = mid - 1;
+  }
+  return lo;
+}
+
+// 1 CTA: split dimension / value of every huge node (box_base::max_side + kd_tree_builder.hpp:204,240)
+// and the chunk layout of the level.
+template <typename T>
+__global__ void huge_plan(BuildState<T> s, const uint32_t* list, int n_huge) {
+  const int sdim = s.sdim;
+  for (int h = threadIdx.x; h < n_huge; h += blockDim.x) {
+    const uint32_t id = list[h];
+    const BNode<T>& nd = s.nodes[id];
+    const T* box = s.boxes + (size_t)id * 2 * sdim;
+    int sd = 0;
+    T max_delta = -Limits<T>::max();
+    for (int d = 0; d < sdim; ++d) {
+      const T delta = box[sdim + d] - box[d];
+      if (delta > max_delta) {
+        max_delta = delta;
+        sd = d;
+      }
+    }
+    HugeNode<T>& hn = s.huge[h];
+    hn.node = id;
+    hn.begin = nd.begin;
+    hn.end = nd.end;
+    hn.sd = sd;
+    hn.split_val = (s.rule == PICO_B200_RULE_MIDPOINT_MAX_SIDE) ? (max_delta * T(0.5) + box[sd])
+                                                                : (max_delta / T(2.0) + box[sd]);
+    hn.split = hn.nl = hn.m = 0;
+    hn.mode = 1;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t acc = 0;
+    for (int h = 0; h < n_huge; ++h) {
+      s.huge[h].first_chunk = acc;
+      acc += (uint32_t)((s.huge[h].end - s.huge[h].begin + kChunk - 1) / kChunk);
+    }
+    s.counters[4] = acc;
+  }
+}
+
+template <typename T>
+struct Extremes {
+  T mn, mn2, mx;
+  int mn_pos, mx_pos;
+  __device__ __forceinline__ void init() {
+    mn = mn2 = Limits<T>::max();
+    mx = -Limits<T>::max();
+    mn_pos = 0x7fffffff;
+    mx_pos = -1;
+  }
+  __device__ __forceinline__ void add(T x, int pos) { merge(x, Limits<T>::max(), pos, x, pos); }
+  // smallest: first position wins ties; largest: last position wins ties
+  __device__ __forceinline__ void merge(T omn, T omn2, int omn_pos, T omx, int omx_pos) {
+    if (omn < mn || (omn == mn && omn_pos < mn_pos)) {
+      const T second = omn2 < mn ? omn2 : mn;
+      mn2 = second;
+      mn = omn;
+      mn_pos = omn_pos;
+    } else {
+      const T second = omn < mn2 ? omn : mn2;
+      mn2 = omn2 < second ? omn2 : second;
+    }
+    if (omx > mx || (omx == mx && omx_pos > mx_pos)) {
+      mx = omx;
+      mx_pos = omx_pos;
+    }
+  }
+  __device__ __forceinline__ void merge_lane(int o) {
+    const T a = __shfl_xor_sync(0xffffffffu, mn, o), b = __shfl_xor_sync(0xffffffffu, mn2, o),
+            c = __shfl_xor_sync(0xffffffffu, mx, o);
+    const int pa = __shfl_xor_sync(0xffffffffu, mn_pos, o), pc = __shfl_xor_sync(0xffffffffu, mx_pos, o);
+    merge(a, b, pa, c, pc);
+  }
+};
+
+// grid = chunks of the level: flags counted, extremes kept for the slide cases
+template <typename T>
+__global__ void __launch_bounds__(kChunkThreads) huge_count(BuildState<T> s, int n_huge) {
+  const uint32_t c = blockIdx.x;
+  if (c >= s.counters[4]) return;
+  const HugeNode<T>& hn = s.huge[huge_of_chunk(s.huge, n_huge, c)];
+  const int lo = hn.begin + (int)(c - hn.first_chunk) * kChunk;
+  const int hi = min(lo + kChunk, hn.end);
+  const T* col = s.raw + hn.sd;
+  const T sv = hn.split_val;
+  int lt = 0;
+  Extremes<T> ex;
+  ex.init();
+  for (int i = lo + threadIdx.x; i < hi; i += kChunkThreads) {
+    const T x = col[(size_t)s.idx[i] * s.sdim];
+    lt += x < sv;
+    ex.add(x, i);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    lt += __shfl_xor_sync(0xffffffffu, lt, o);
+    ex.merge_lane(o);
+  }
+  __shared__ int s_lt[kChunkThreads / 32];
+  __shared__ Extremes<T> s_ex[kChunkThreads / 32];
+  if ((threadIdx.x & 31) == 0) {
+    s_lt[threadIdx.x >> 5] = lt;
+    s_ex[threadIdx.x >> 5] = ex;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < kChunkThreads / 32; ++w) {
+      lt += s_lt[w];
+      ex.merge(s_ex[w].mn, s_ex[w].mn2, s_ex[w].mn_pos, s_ex[w].mx, s_ex[w].mx_pos);
+    }
+    ChunkStat<T>& cs = s.chunks[c];
+    cs.lt = lt;
+    cs.lt_prefix = 0;
+    cs.mn = ex.mn;
+    cs.mn2 = ex.mn2;
+    cs.mx = ex.mx;
+    cs.mn_pos = ex.mn_pos;
+    cs.mx_pos = ex.mx_pos;
+  }
+}
+
+// one warp per huge node: scan of the chunk counts, slide fix-up, children
+template <typename T>
+__global__ void __launch_bounds__(32) huge_resolve(BuildState<T> s, int n_huge) {
+  const int h = blockIdx.x;
+  if (h >= n_huge) return;
+  HugeNode<T>& hn = s.huge[h];
+  const int lane = threadIdx.x;
+  const int cnt = hn.end - hn.begin;
+  const int n_chunks = (cnt + kChunk - 1) / kChunk;
+  ChunkStat<T>* cs = s.chunks + hn.first_chunk;
+  int carry = 0;
+  Extremes<T> ex;
+  ex.init();
+  for (int base = 0; base < n_chunks; base += 32) {
+    const int c = base + lane;
+    int v = c < n_chunks ? cs[c].lt : 0;
+    if (c < n_chunks) ex.merge(cs[c].mn, cs[c].mn2, cs[c].mn_pos, cs[c].mx, cs[c].mx_pos);
+    int incl = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (c < n_chunks) cs[c].lt_prefix = carry + incl - v;
+    carry += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  for (int o = 16; o > 0; o >>= 1) ex.merge_lane(o);
+  const int nl = carry;
+  int split = hn.begin + nl;
+  T split_val = hn.split_val;
+  int mode = 0;
+  if (s.rule == PICO_B200_RULE_SLIDING_MIDPOINT_MAX_SIDE && nl == cnt) {
+    // all left: the largest coordinate slides right (kd_tree_builder.hpp:255-264)
+    if (lane == 0) {
+      const int32_t a = s.idx[ex.mx_pos];
+      s.idx[ex.mx_pos] = s.idx[hn.end - 1];
+      s.idx[hn.end - 1] = a;
+    }
+    split = hn.end - 1;
+    split_val = ex.mx;
+    mode = 1;
+  } else if (s.rule == PICO_B200_RULE_SLIDING_MIDPOINT_MAX_SIDE && nl == 0) {
+    // all right: the smallest slides left, split_val = second smallest (:265-275)
+    if (lane == 0) {
+      const int32_t a = s.idx[ex.mn_pos];
+      s.idx[ex.mn_pos] = s.idx[hn.begin];
+      s.idx[hn.begin] = a;
+    }
+    split = hn.begin + 1;
+    split_val = ex.mn2;
+    mode = 1;
+  } else if (nl == 0 || nl == cnt) {
+    mode = 1;  // midpoint rule: one child is empty, nothing moves
+  }
+  if (lane == 0) {
+    hn.nl = nl;
+    hn.split = split;
+    hn.mode = mode;
+    hn.m = 0;
+  }
+  __syncwarp();
+  emit_children<T, 32>(s, hn.node, hn.sd, split, split_val);
+}
+
+// grid = chunks: the two lists of misplaced positions (left list at tmp[begin + j], right list,
+// counted from the right end, at tmp[end - 1 - j])
+template <typename T>
+__global__ void __launch_bounds__(kChunkThreads) huge_scatter(BuildState<T> s, int n_huge) {
+  const uint32_t c = blockIdx.x;
+  if (c >= s.counters[4]) return;
+  HugeNode<T>& hn = s.huge[huge_of_chunk(s.huge, n_huge, c)];
+  if (hn.mode != 0) return;
+  const int lo = hn.begin + (int)(c - hn.first_chunk) * kChunk;
+  const int hi = min(lo + kChunk, hn.end);
+  const T* col = s.raw + hn.sd;
+  const T sv = hn.split_val;
+  const int begin = hn.begin, end = hn.end, split = hn.split, nl = hn.nl;
+  __shared__ int s_w[kChunkThreads / 32];
+  int base = s.chunks[c].lt_prefix;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int slab = lo; slab < hi; slab += kChunkThreads) {
+    const int i = slab + threadIdx.x;
+    const bool in = i < hi;
+    const bool lt = in && (col[(size_t)s.idx[i] * s.sdim] < sv);
+    const unsigned b = __ballot_sync(0xffffffffu, lt);
+    __syncthreads();
+    if (lane == 0) s_w[w] = __popc(b);
+    __syncthreads();
+    int before = 0, tot = 0;
+#pragma unroll
+    for (int k = 0; k < kChunkThreads / 32; ++k) {
+      const int v = s_w[k];
+      if (k < w) before += v;
+      tot += v;
+    }
+    const int P = base + before + __popc(b & ((1u << lane) - 1u));  // flags set in [begin, i)
+    if (in) {
+      if (i == split) hn.m = nl - P;
+      if (i < split && !lt) s.tmp[begin + (i - begin) - P] = i;
+      if (i >= split && lt) s.tmp[end - 1 - (nl - P - 1)] = i;
+    }
+    base += tot;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kChunkThreads) huge_swap(BuildState<T> s, int n_huge) {
+  const uint32_t c = blockIdx.x;
+  if (c >= s.counters[4]) return;
+  const HugeNode<T>& hn = s.huge[huge_of_chunk(s.huge, n_huge, c)];
+  if (hn.mode != 0) return;
+  const int j0 = (int)(c - hn.first_chunk) * kChunk;
+  const int j1 = min(j0 + kChunk, hn.m);
+  for (int j = j0 + threadIdx.x; j < j1; j += kChunkThreads) {
+    const int a = s.tmp[hn.begin + j], b = s.tmp[hn.end - 1 - j];
+    const int32_t va = s.idx[a];
+    s.idx[a] = s.idx[b];
+    s.idx[b] = va;
+  }
 }
 
 // ------------------------------------------------------------------ median rule
@@ -501,36 +820,8 @@ __device__ void median_node(const BuildState<T>& s, uint32_t node_id) {
   Grp<G>::sync();
   const int split = begin + kth;
   split_val = col[(size_t)idx[split] * sdim];
-
-  if (tid == 0) {
-    const uint32_t c = atomicAdd(&s.counters[0], 2u);
-    nd.left = (int32_t)c;
-    nd.right = (int32_t)c + 1;
-    nd.split_dim = sd;
-    BNode<T>& l = s.nodes[c];
-    BNode<T>& r = s.nodes[c + 1];
-    l.begin = begin;
-    l.end = split;
-    l.depth = depth + 1;
-    r.begin = split;
-    r.end = end;
-    r.depth = depth + 1;
-    l.left = l.right = r.left = r.right = -1;
-    l.split_dim = r.split_dim = -1;
-    if (split - begin > kWarpNodeMax) s.big_next[atomicAdd(&s.counters[1], 1u)] = c;
-    if (end - split > kWarpNodeMax) s.big_next[atomicAdd(&s.counters[1], 1u)] = c + 1;
-  }
   Grp<G>::sync();
-  {
-    const uint32_t cc = (uint32_t)nd.left;
-    T* lb = s.boxes + (size_t)cc * 2 * sdim;
-    T* rb = lb + 2 * sdim;
-    for (int d = tid; d < 2 * sdim; d += G) {
-      const T v = box[d];
-      lb[d] = (d == sdim + sd) ? split_val : v;
-      rb[d] = (d == sd) ? split_val : v;
-    }
-  }
+  emit_children<T, G>(s, node_id, sd, split, split_val);
 }
 
 template <typename T>
@@ -738,7 +1029,7 @@ int build_tree(pico_b200_tree* t, const T* h_pts, size_t stride, int rule, int s
     ~StreamGuard() { cudaStreamDestroy(s); }
   } guard{st};
 
-  DevBuf raw, tmp, nodes, boxes, counters, big_a, big_b, partial;
+  DevBuf raw, tmp, nodes, boxes, counters, big_a, big_b, partial, huge_a, huge_b, huge_nodes, chunk_stats;
   PICO_TRY(alloc(raw, n * sdim * sizeof(T)));
   PICO_TRY(stage_points(h_pts, n, sdim, stride, raw.as<T>(), st));
   PICO_CUDA(cudaMalloc(&t->d_indices, n * sizeof(int32_t)));
@@ -786,9 +1077,18 @@ int build_tree(pico_b200_tree* t, const T* h_pts, size_t stride, int rule, int s
   size_t cap = 2 * n + 1024;
   PICO_TRY(alloc(nodes, cap * sizeof(BNode<T>)));
   PICO_TRY(alloc(boxes, cap * 2 * sdim * sizeof(T)));
-  PICO_TRY(alloc(counters, 4 * sizeof(uint32_t)));
+  PICO_TRY(alloc(counters, 8 * sizeof(uint32_t)));
   PICO_TRY(alloc(big_a, cap * sizeof(uint32_t)));
   PICO_TRY(alloc(big_b, cap * sizeof(uint32_t)));
+  // huge nodes of one level are disjoint ranges of more than kHugeMin points each
+  int huge_min = kHugeMin;
+  if (const char* e = getenv("PICO_B200_HUGE_MIN")) huge_min = std::max(atoi(e), kWarpNodeMax);  // test hook
+  const size_t huge_cap = n / (size_t)huge_min + 16;
+  const size_t chunk_cap = n / kChunk + huge_cap + 16;
+  PICO_TRY(alloc(huge_a, huge_cap * sizeof(uint32_t)));
+  PICO_TRY(alloc(huge_b, huge_cap * sizeof(uint32_t)));
+  PICO_TRY(alloc(huge_nodes, huge_cap * sizeof(HugeNode<T>)));
+  PICO_TRY(alloc(chunk_stats, chunk_cap * sizeof(ChunkStat<T>)));
 
   BuildState<T> s;
   s.raw = raw.as<T>();
@@ -798,6 +1098,9 @@ int build_tree(pico_b200_tree* t, const T* h_pts, size_t stride, int rule, int s
   s.nodes = nodes.as<BNode<T>>();
   s.boxes = boxes.as<T>();
   s.counters = counters.as<uint32_t>();
+  s.huge = huge_nodes.as<HugeNode<T>>();
+  s.chunks = chunk_stats.as<ChunkStat<T>>();
+  s.huge_min = huge_min;
   s.rule = rule;
   s.stop_kind = stop_kind;
   s.stop_value = (int32_t)std::min<size_t>(stop_value, 0x7fffffff);
@@ -813,20 +1116,27 @@ int build_tree(pico_b200_tree* t, const T* h_pts, size_t stride, int rule, int s
     root.preorder = 0;
     PICO_CUDA(cudaMemcpyAsync(s.nodes, &root, sizeof(root), cudaMemcpyHostToDevice, st));
     PICO_CUDA(cudaMemcpyAsync(s.boxes, d_root, 2 * sdim * sizeof(T), cudaMemcpyDeviceToDevice, st));
-    const uint32_t h_cnt[4] = {1u, 0u, 0u, 0u};
+    const uint32_t h_cnt[8] = {1u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
     PICO_CUDA(cudaMemcpyAsync(s.counters, h_cnt, sizeof(h_cnt), cudaMemcpyHostToDevice, st));
     const uint32_t zero = 0;
     PICO_CUDA(cudaMemcpyAsync(big_a.p, &zero, sizeof(zero), cudaMemcpyHostToDevice, st));
+    PICO_CUDA(cudaMemcpyAsync(huge_a.p, &zero, sizeof(zero), cudaMemcpyHostToDevice, st));
   }
 
   std::vector<uint32_t> level_start;  // BFS id of the first node of each level
   level_start.push_back(0);
   uint32_t level_begin = 0, level_end = 1;
-  uint32_t n_big = (n > (size_t)kWarpNodeMax) ? 1u : 0u;  // the root
+  // the root: leaf / warp / CTA / chunked passes
+  const bool root_leaf = (stop_kind == PICO_B200_STOP_MAX_LEAF_SIZE) ? (n <= (size_t)s.stop_value)
+                                                                     : (s.stop_value == 0 || n <= 1);
+  uint32_t n_huge = (n > (size_t)huge_min && rule != PICO_B200_RULE_MEDIAN_MAX_SIDE && !root_leaf) ? 1u : 0u;
+  uint32_t n_big = (!n_huge && n > (size_t)kWarpNodeMax) ? 1u : 0u;
   uint32_t* big_cur = big_a.as<uint32_t>();
   uint32_t* big_nxt = big_b.as<uint32_t>();
+  uint32_t* huge_cur = huge_a.as<uint32_t>();
+  uint32_t* huge_nxt = huge_b.as<uint32_t>();
   uint32_t* h_counters = nullptr;
-  PICO_CUDA(cudaMallocHost(&h_counters, 4 * sizeof(uint32_t)));
+  PICO_CUDA(cudaMallocHost(&h_counters, 8 * sizeof(uint32_t)));
   struct PinGuard {
     uint32_t* p;
     ~PinGuard() { cudaFreeHost(p); }
@@ -857,7 +1167,18 @@ int build_tree(pico_b200_tree* t, const T* h_pts, size_t stride, int rule, int s
       cap = ncap;
     }
     s.big_next = big_nxt;
+    s.huge_next = huge_nxt;
     PICO_CUDA(cudaMemsetAsync(s.counters + 1, 0, sizeof(uint32_t), st));
+    PICO_CUDA(cudaMemsetAsync(s.counters + 3, 0, 2 * sizeof(uint32_t), st));
+    if (n_huge) {
+      // every chunk kernel is launched over an upper bound of the level's chunk count
+      const unsigned chunk_grid = (unsigned)std::min<size_t>(n / kChunk + n_huge + 1, chunk_cap);
+      huge_plan<T><<<1, 256, 0, st>>>(s, huge_cur, (int)n_huge);
+      huge_count<T><<<chunk_grid, kChunkThreads, 0, st>>>(s, (int)n_huge);
+      huge_resolve<T><<<n_huge, 32, 0, st>>>(s, (int)n_huge);
+      huge_scatter<T><<<chunk_grid, kChunkThreads, 0, st>>>(s, (int)n_huge);
+      huge_swap<T><<<chunk_grid, kChunkThreads, 0, st>>>(s, (int)n_huge);
+    }
     const unsigned warp_blocks = (unsigned)(((size_t)width * 32 + 255) / 256);
     if (rule == PICO_B200_RULE_MEDIAN_MAX_SIDE) {
       median_level_warp<T><<<warp_blocks, 256, 0, st>>>(s, level_begin, level_end);
@@ -867,12 +1188,14 @@ int build_tree(pico_b200_tree* t, const T* h_pts, size_t stride, int rule, int s
       if (n_big) split_level_block<T><<<n_big, kBigThreads, 0, st>>>(s, big_cur);
     }
     PICO_CUDA(cudaGetLastError());
-    PICO_CUDA(cudaMemcpyAsync(h_counters, s.counters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    PICO_CUDA(cudaMemcpyAsync(h_counters, s.counters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     PICO_CUDA(cudaStreamSynchronize(st));
     level_begin = level_end;
     level_end = h_counters[0];
     n_big = h_counters[1];
+    n_huge = h_counters[3];
     std::swap(big_cur, big_nxt);
+    std::swap(huge_cur, huge_nxt);
     if (level_begin < level_end) level_start.push_back(level_begin);
     if ((size_t)level_end >= 0x7ffffff0u) return fail(PICO_B200_ERR_UNSUPPORTED, "node table overflow");
     if (level_start.size() > (1u << 20))

@@ -324,6 +324,39 @@ def test_deep_tree_uses_global_stack(pt, oracle):
     assert_radius_parity(nns._offsets, nns._flat[:len(flat)], offs, flat, ordered=False)
 
 
+def test_build_paths_agree(pt, monkeypatch):
+    """The three ways a node can be split on the device — one warp, one CTA, grid-wide chunked passes
+    (build.cu, PICO_B200_HUGE_MIN is the test hook for the threshold) — must leave the very same
+    tree AND the very same index permutation (std::partition's exchange order), slides included."""
+    from pico_tree_b200 import datasets as D
+    rng = np.random.default_rng(21)
+    clustered = rng.random((150_000, 3)).astype(np.float32)
+    clustered[:50_000, 2] = 0.25            # a plane: slides towards it
+    clustered[50_000:70_000, 0] = 0.5
+    clustered[::13] = clustered[7]          # duplicates of one point
+    cases = [
+        (D.lidar_shape(300_000, seed=3), {}),
+        (clustered, {}),
+        (rng.random((120_000, 2)), {}),  # float64
+        (D.uniform(100_000, 3, seed=9), {"rule": pt.kd_tree.Rule.MidpointMaxSide}),
+        (D.uniform(90_000, 3, seed=9), {"max_leaf_depth": 6}),
+        (D.sift_shape(40_000, 16, seed=4), {}),
+    ]
+    for pts, kw in cases:
+        got = []
+        for huge_min in ("2147483647", "1024", "20000"):
+            monkeypatch.setenv("PICO_B200_HUGE_MIN", huge_min)
+            t = pt.KdTree(pts, pt.Metric.L2Squared, 10, **kw) if "max_leaf_depth" not in kw else \
+                pt.KdTree(pts, pt.Metric.L2Squared, **kw)
+            nodes, indices, box = t.export()
+            got.append((nodes.tobytes(), indices.copy(), box.copy()))
+        for other in got[1:]:
+            assert other[0] == got[0][0], "node tables differ between build paths"
+            assert np.array_equal(other[1], got[0][1]), "index permutations differ between build paths"
+            assert np.array_equal(other[2], got[0][2])
+    monkeypatch.delenv("PICO_B200_HUGE_MIN")
+
+
 # ---------------------------------------------------------------- BASELINE sizes: properties
 def test_full_size_properties(pt):
     """cfg2 at full size (7,733,372 / 7,200,863): size-independent properties instead of the oracle —
