@@ -142,10 +142,14 @@ int pico_b200_tree_create(const void* pts, size_t n, size_t sdim, size_t stride,
  * Uploads an existing tree (pre-order nodes + index permutation + root box).
  * Replaces kd_tree_data::load / read_node (internal/kd_tree_data.hpp:43-52,89-107), i.e.
  * kd_tree::load (kd_tree.hpp:336-353).
+ *   outer_bounds: NULL for the euclidean metrics. For metric_so2 / metric_se2_squared the nodes
+ *   are kd_tree_node_topological (internal/kd_tree_node.hpp:99-117) with four bounds per branch;
+ *   left_max / right_min live in the node record, {left_min, right_max} come as n_nodes pairs here.
  */
 int pico_b200_tree_create_from_nodes(const void* pts, size_t n, size_t sdim, size_t stride, int scalar,
                                      int metric, const void* nodes, size_t n_nodes, const int32_t* indices,
-                                     const void* root_box_min_then_max, int device, pico_b200_tree** out);
+                                     const void* root_box_min_then_max, const void* outer_bounds, int device,
+                                     pico_b200_tree** out);
 
 void pico_b200_tree_destroy(pico_b200_tree* tree);
 
@@ -159,6 +163,8 @@ int pico_b200_tree_info_get(const pico_b200_tree* tree, pico_b200_tree_info* inf
  * kd_tree::leaf_ranges (kd_tree.hpp:325, kd_tree_data.hpp:60-62,76-87).
  */
 int pico_b200_tree_export(const pico_b200_tree* tree, void* nodes_out, int32_t* indices_out, void* root_box_out);
+/* topological metrics only: n_nodes pairs {left_min, right_max} (zeros for leaves) */
+int pico_b200_tree_export_outer_bounds(const pico_b200_tree* tree, void* outer_out);
 
 /*
  * k nearest neighbours for a batch of queries; out holds nq*k neighbour records,
@@ -216,7 +222,8 @@ int pico_b200_tree_deserialize(const void* src, uint64_t bytes, int src_is_devic
  * write_node/read_node, internal/kd_tree_data.hpp:43-58,89-135): size_t sdim; size_t n;
  * int32 indices[n]; Scalar min[sdim]; Scalar max[sdim]; then the nodes in pre-order, each a
  * 1-byte is_leaf flag followed by the raw leaf {int32 begin, end} or the raw branch
- * {int32 split_dim; Scalar left_max; Scalar right_min} (12 B for f32, 24 B for f64).
+ * {int32 split_dim; Scalar left_max; Scalar right_min} (12 B for f32, 24 B for f64); topological metrics:
+ * {int32 split_dim; Scalar left_min, left_max, right_min, right_max} (20 B / 40 B, kd_tree_node.hpp:52-59).
  * Trees written by either side load in the other. The points are not part of the image.
  *   pico_b200_tree_load: `consumed` (may be NULL) receives the number of bytes read, so a
  *   caller can keep reading its own trailer/header around the image (the .pkd header of

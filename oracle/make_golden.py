@@ -46,23 +46,45 @@ CASES = [
     ("uniform8_f32", "uniform", 3000, 8, np.float32, "l2_squared", "sliding_midpoint", "max_leaf_size", 10),
     ("uniform3_f64", "uniform", 3000, 3, np.float64, "l2_squared", "sliding_midpoint", "max_leaf_size", 10),
     ("clustered5_f64_l1", "clustered", 3000, 5, np.float64, "l1", "sliding_midpoint", "max_leaf_size", 5),
+    # topological spaces (search_nearest_topological, metric_box_map): S1 = [0, 1) and R2 x S1
+    ("so2_f32", "uniform", 3000, 1, np.float32, "so2", "sliding_midpoint", "max_leaf_size", 10),
+    ("se2_f32", "uniform", 4000, 3, np.float32, "se2_squared", "sliding_midpoint", "max_leaf_size", 10),
+    ("se2_f64", "uniform", 3000, 3, np.float64, "se2_squared", "sliding_midpoint", "max_leaf_size", 6),
 ]
 
 
-def main():
+def main(only=None):
+    """`python oracle/make_golden.py [name ...]` regenerates the named fixtures (all by default)."""
     assert O.ref_available(), "build oracle/_ref first (make -C oracle)"
     os.makedirs(OUT, exist_ok=True)
     for name, kind, n, sdim, dtype, metric, rule, stop, sv in CASES:
+        if only and name not in only:
+            continue
         pts = cloud(kind, n, sdim, 100 + len(name), dtype)
         rng = np.random.default_rng(7)
-        q = np.ascontiguousarray(np.concatenate([rng.random((300, sdim)) * 1.2 - 0.1, pts[:100]]).astype(dtype))
-        r = O.RefTree(pts, sv, metric=metric, rule=rule, stop=stop)
-        _, idx, box, nodes = r.structure()
-        rad = 0.02 if metric == "l2_squared" else 0.12
+        topo = metric in O.TOPOLOGICAL
+        extra = {}
+        if topo:
+            # coordinates on the circle stay inside [0, 1); boxes on S1 dimensions partly wrap (min > max)
+            q = np.ascontiguousarray(np.concatenate([rng.random((300, sdim)), pts[:100]]).astype(dtype))
+            r = O.RefTree(pts, sv, metric=metric, rule=rule, stop=stop)
+            _, idx, box, nodes, outer = r.structure()
+            extra["node_outer"] = outer
+            rad = 0.03 if metric == "so2" else 0.004
+            mins = (q - dtype(0.06)).astype(dtype)
+            maxs = (q + dtype(0.045)).astype(dtype)
+            s1 = slice(0, None) if metric == "so2" else slice(2, None)
+            mins[:, s1] = np.mod(mins[:, s1], 1)
+            maxs[:, s1] = np.mod(maxs[:, s1], 1)
+        else:
+            q = np.ascontiguousarray(np.concatenate([rng.random((300, sdim)) * 1.2 - 0.1, pts[:100]]).astype(dtype))
+            r = O.RefTree(pts, sv, metric=metric, rule=rule, stop=stop)
+            _, idx, box, nodes = r.structure()
+            rad = 0.02 if metric == "l2_squared" else 0.12
+            mins = np.minimum(q, q[::-1]) - dtype(0.02)
+            maxs = np.maximum(q, q[::-1]) * dtype(0.5) + mins * dtype(0.5) + dtype(0.05)
         ro, rn = r.search_radius(q, rad)
         so, sn = r.search_radius(q, rad, e=1.5, sort=True)
-        mins = np.minimum(q, q[::-1]) - dtype(0.02)
-        maxs = np.maximum(q, q[::-1]) * dtype(0.5) + mins * dtype(0.5) + dtype(0.05)
         bo, bi = r.search_box(mins, maxs)
         k = min(7, n)
         np.savez_compressed(
@@ -77,9 +99,9 @@ def main():
             radius_offsets=ro, radius_index=rn["index"], radius_distance=rn["distance"],
             aradius_offsets=so, aradius_distance=sn["distance"],
             box_min=mins, box_max=maxs, box_offsets=bo, box_index=bi,
-            saved_stream=np.frombuffer(r.saved(), dtype=np.uint8))
+            saved_stream=np.frombuffer(r.saved(), dtype=np.uint8), **extra)
         print(name, len(nodes), "nodes", int(ro[-1]), "radius hits", int(bo[-1]), "box hits")
 
 
 if __name__ == "__main__":
-    main()
+    main(set(sys.argv[1:]))

@@ -15,7 +15,8 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-METRICS = {"l1": 0, "l2_squared": 1, "lpinf": 2, "lninf": 3}
+METRICS = {"l1": 0, "l2_squared": 1, "lpinf": 2, "lninf": 3, "so2": 4, "se2_squared": 5}
+TOPOLOGICAL = ("so2", "se2_squared")
 RULES = {"sliding_midpoint": 0, "midpoint": 1, "median": 2}
 STOPS = {"max_leaf_size": 0, "max_leaf_depth": 1}
 
@@ -59,7 +60,7 @@ def lib():
             for f in ("po_num_nodes", "po_height"):
                 getattr(L, f"{f}_{s}").restype = C.c_size_t
                 getattr(L, f"{f}_{s}").argtypes = [C.c_void_p]
-            for f in ("po_nodes", "po_indices", "po_root_box"):
+            for f in ("po_nodes", "po_indices", "po_root_box", "po_outer_bounds"):
                 getattr(L, f"{f}_{s}").restype = C.c_void_p
                 getattr(L, f"{f}_{s}").argtypes = [C.c_void_p]
             getattr(L, f"po_knn_batch_{s}").argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t,
@@ -149,6 +150,13 @@ class OracleTree(_Base):
         return np.frombuffer(buf, dtype=dt).copy()
 
     @property
+    def outer_bounds(self):
+        """(n_nodes, 2): left_min, right_max of every branch (kd_tree_branch_double)."""
+        m = self.num_nodes
+        buf = (C.c_char * (m * 2 * self.dtype.itemsize)).from_address(self._f("po_outer_bounds")(self._h))
+        return np.frombuffer(buf, dtype=self.dtype).copy().reshape(m, 2)
+
+    @property
     def indices(self):
         buf = (C.c_char * (self.n * 4)).from_address(self._f("po_indices")(self._h))
         return np.frombuffer(buf, dtype=np.int32).copy()
@@ -223,9 +231,11 @@ def ref_lib():
     return _ref
 
 
-def parse_saved_tree(blob, scalar_dtype):
+def parse_saved_tree(blob, scalar_dtype, topological=False):
     """Decode a kd_tree::save stream (internal/kd_tree_data.hpp:43-58,89-135) into
-    (sdim, indices, root_box[2,sdim], nodes) with nodes in the oracle's NODE_* dtype."""
+    (sdim, indices, root_box[2,sdim], nodes) with nodes in the oracle's NODE_* dtype. With
+    ``topological`` the branches are kd_tree_branch_double records (kd_tree_node.hpp:52-59) and a
+    fifth value is returned: outer[n_nodes, 2] = (left_min, right_max)."""
     scalar_dtype = np.dtype(scalar_dtype)
     mv = memoryview(blob)
     pos = 0
@@ -235,7 +245,13 @@ def parse_saved_tree(blob, scalar_dtype):
     box = np.frombuffer(mv[pos:pos + 2 * sdim * scalar_dtype.itemsize], dtype=scalar_dtype).copy().reshape(2, sdim)
     pos += 2 * sdim * scalar_dtype.itemsize
     f32 = scalar_dtype == np.float32
-    branch_dt = np.dtype([("split_dim", "<i4"), ("left_max", scalar_dtype), ("right_min", scalar_dtype)], align=True)
+    if topological:
+        branch_dt = np.dtype([("split_dim", "<i4"), ("left_min", scalar_dtype), ("left_max", scalar_dtype),
+                              ("right_min", scalar_dtype), ("right_max", scalar_dtype)], align=True)
+    else:
+        branch_dt = np.dtype([("split_dim", "<i4"), ("left_max", scalar_dtype), ("right_min", scalar_dtype)],
+                             align=True)
+    outer = []
     out_dt = NODE_F32 if f32 else NODE_F64
     raw = np.frombuffer(mv[pos:], dtype=np.uint8)
     # Pre-order stream: 1-byte is_leaf flag + 8-byte leaf or sizeof(branch) bytes.
@@ -247,9 +263,11 @@ def parse_saved_tree(blob, scalar_dtype):
         if is_leaf:
             b, e = np.frombuffer(raw[p:p + 8].tobytes(), dtype="<i4"); p += 8
             nodes.append((0, 0, -1, b, e, -1, -1))
+            outer.append((0, 0))
         else:
             br = np.frombuffer(raw[p:p + bs].tobytes(), dtype=branch_dt)[0]; p += bs
             nodes.append((br["left_max"], br["right_min"], br["split_dim"], 0, 0, 0, 0))
+            outer.append((br["left_min"], br["right_max"]) if topological else (0, 0))
     arr = np.array(nodes, dtype=out_dt)
     # Link children: pre-order, left = self+1, right = first node after the left subtree.
     stack = []
@@ -265,6 +283,8 @@ def parse_saved_tree(blob, scalar_dtype):
             stack[-1][1] += 1
         if arr["split_dim"][i] >= 0:
             stack.append([i, 0])
+    if topological:
+        return sdim, indices, box, arr, np.array(outer, dtype=scalar_dtype).reshape(-1, 2)
     return sdim, indices, box, arr
 
 
@@ -274,6 +294,7 @@ class RefTree(_Base):
     def __init__(self, pts, max_leaf_size=10, metric="l2_squared", rule="sliding_midpoint", stop="max_leaf_size",
                  bounds=None, force_dynamic=False):
         self._prep(pts)
+        self.metric = metric
         bmin = bmax = None
         if bounds is not None:
             bmin = np.ascontiguousarray(bounds[0], dtype=self.dtype)
@@ -295,7 +316,7 @@ class RefTree(_Base):
         return blob
 
     def structure(self):
-        return parse_saved_tree(self.saved(), self.dtype)
+        return parse_saved_tree(self.saved(), self.dtype, self.metric in TOPOLOGICAL)
 
     def search_knn(self, q, k, e=0.0, threads=1):
         q = self._q(q)

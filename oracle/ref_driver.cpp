@@ -18,7 +18,7 @@
 
 namespace {
 
-enum { METRIC_L1 = 0, METRIC_L2SQ = 1, METRIC_LPINF = 2, METRIC_LNINF = 3 };
+enum { METRIC_L1 = 0, METRIC_L2SQ = 1, METRIC_LPINF = 2, METRIC_LNINF = 3, METRIC_SO2 = 4, METRIC_SE2SQ = 5 };
 enum { RULE_SLIDING = 0, RULE_MIDPOINT = 1, RULE_MEDIAN = 2 };
 enum { STOP_SIZE = 0, STOP_DEPTH = 1 };
 
@@ -161,6 +161,12 @@ tree_base* make_metric(
           pts, n, sdim, rule, stop_kind, stop_value, bmin, bmax);
     case METRIC_LNINF:
       return new tree_impl<T, Dim, pico_tree::metric_lninf>(
+          pts, n, sdim, rule, stop_kind, stop_value, bmin, bmax);
+    case METRIC_SO2:  // topological spaces: search_nearest_topological, kd_tree_search.hpp:122-229
+      return new tree_impl<T, Dim, pico_tree::metric_so2>(
+          pts, n, sdim, rule, stop_kind, stop_value, bmin, bmax);
+    case METRIC_SE2SQ:
+      return new tree_impl<T, Dim, pico_tree::metric_se2_squared>(
           pts, n, sdim, rule, stop_kind, stop_value, bmin, bmax);
     default:
       return new tree_impl<T, Dim, pico_tree::metric_l2_squared>(

@@ -21,6 +21,7 @@ FLAG_ASYNC = 1 << 4
 EXPORTS = [
     "pico_b200_last_error", "pico_b200_abi_version", "pico_b200_device_count", "pico_b200_tree_create",
     "pico_b200_tree_create_from_nodes", "pico_b200_tree_destroy", "pico_b200_tree_info_get", "pico_b200_tree_export",
+    "pico_b200_tree_export_outer_bounds",
     "pico_b200_knn", "pico_b200_radius", "pico_b200_box", "pico_b200_tree_broadcast",
     "pico_b200_tree_serialize_size", "pico_b200_tree_serialize", "pico_b200_tree_deserialize", "pico_b200_free",
     "pico_b200_tree_save_size", "pico_b200_tree_save", "pico_b200_tree_load", "pico_b200_set_stream",
@@ -65,7 +66,8 @@ def lib():
     L.pico_b200_last_error.restype = C.c_char_p
     L.pico_b200_device_count.argtypes = [C.POINTER(C.c_int)]
     L.pico_b200_tree_create.argtypes = [vp, sz, sz, sz, i32, i32, i32, i32, sz, vp, vp, i32, C.POINTER(vp)]
-    L.pico_b200_tree_create_from_nodes.argtypes = [vp, sz, sz, sz, i32, i32, vp, sz, vp, vp, i32, C.POINTER(vp)]
+    L.pico_b200_tree_create_from_nodes.argtypes = [vp, sz, sz, sz, i32, i32, vp, sz, vp, vp, vp, i32, C.POINTER(vp)]
+    L.pico_b200_tree_export_outer_bounds.argtypes = [vp, vp]
     L.pico_b200_tree_destroy.argtypes = [vp]
     L.pico_b200_tree_destroy.restype = None
     L.pico_b200_tree_info_get.argtypes = [vp, C.POINTER(TreeInfo)]

@@ -54,9 +54,13 @@ int check_common(const void* pts, size_t n, size_t sdim, size_t stride, int scal
   if (stride < sdim) return fail(PICO_B200_ERR_INVALID_ARGUMENT, "stride smaller than sdim");
   if (scalar != PICO_B200_F32 && scalar != PICO_B200_F64)
     return fail(PICO_B200_ERR_INVALID_ARGUMENT, "unknown scalar type");
-  if (metric < PICO_B200_METRIC_L1 || metric > PICO_B200_METRIC_LNINF)
-    return fail(PICO_B200_ERR_UNSUPPORTED,
-                "metric not available on the device path (topological metrics so2 / se2_squared are not built yet)");
+  if (metric < PICO_B200_METRIC_L1 || metric > PICO_B200_METRIC_SE2_SQUARED)
+    return fail(PICO_B200_ERR_INVALID_ARGUMENT, "unknown metric");
+  // metric_so2 reads coordinate 0, metric_se2_squared coordinates 0..2 (metric.hpp:203-208,229-238)
+  if (metric == PICO_B200_METRIC_SO2 && sdim != 1)
+    return fail(PICO_B200_ERR_INVALID_ARGUMENT, "metric_so2 needs sdim == 1");
+  if (metric == PICO_B200_METRIC_SE2_SQUARED && sdim != 3)
+    return fail(PICO_B200_ERR_INVALID_ARGUMENT, "metric_se2_squared needs sdim == 3");
   if (sdim > 0x7fff) return fail(PICO_B200_ERR_UNSUPPORTED, "sdim > 32767");
   return 0;
 }
@@ -68,6 +72,7 @@ void release(pico_b200_tree* t) {
   cudaFree(t->d_pts);
   cudaFree(t->d_indices);
   cudaFree(t->d_root_box);
+  cudaFree(t->d_outer);
   delete t;
 }
 
@@ -84,7 +89,7 @@ size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
 size_t image_bytes(const pico_b200_tree* t) {
   return align16(sizeof(ImageHeader)) + align16(2 * t->sdim * t->scalar_size()) + align16(t->n_nodes * t->node_size()) +
-         align16(t->n * 4) + align16(t->pts_bytes());
+         align16(t->n * 4) + align16(t->pts_bytes()) + align16(t->outer_bytes());
 }
 
 }  // namespace
@@ -150,7 +155,7 @@ int pico_b200_tree_create(const void* pts, size_t n, size_t sdim, size_t stride,
 
 int pico_b200_tree_create_from_nodes(const void* pts, size_t n, size_t sdim, size_t stride, int scalar, int metric,
                                      const void* nodes, size_t n_nodes, const int32_t* indices, const void* root_box,
-                                     int device, pico_b200_tree** out) {
+                                     const void* outer_bounds, int device, pico_b200_tree** out) {
   if (!out) return fail(PICO_B200_ERR_INVALID_ARGUMENT, "out is null");
   *out = nullptr;
   PICO_TRY(check_common(pts, n, sdim, stride, scalar, metric));
@@ -168,10 +173,10 @@ int pico_b200_tree_create_from_nodes(const void* pts, size_t n, size_t sdim, siz
   int rc;
   if (scalar == PICO_B200_F32)
     rc = upload_tree<float>(t, static_cast<const float*>(pts), stride, nodes, n_nodes, indices,
-                            static_cast<const float*>(root_box));
+                            static_cast<const float*>(root_box), static_cast<const float*>(outer_bounds));
   else
     rc = upload_tree<double>(t, static_cast<const double*>(pts), stride, nodes, n_nodes, indices,
-                             static_cast<const double*>(root_box));
+                             static_cast<const double*>(root_box), static_cast<const double*>(outer_bounds));
   if (rc) {
     release(t);
     return rc;
@@ -195,6 +200,14 @@ int pico_b200_tree_info_get(const pico_b200_tree* t, pico_b200_tree_info* info) 
   info->reserved_ = 0;
   info->build_ms = t->build_ms;
   info->device_bytes = t->device_bytes;
+  return 0;
+}
+
+int pico_b200_tree_export_outer_bounds(const pico_b200_tree* t, void* outer_out) {
+  if (!t || !outer_out) return fail(PICO_B200_ERR_INVALID_ARGUMENT, "null argument");
+  if (!t->topological()) return fail(PICO_B200_ERR_INVALID_ARGUMENT, "only trees of a topological metric keep outer bounds");
+  PICO_CUDA(cudaSetDevice(t->device));
+  PICO_CUDA(cudaMemcpy(outer_out, t->d_outer, t->outer_bytes(), cudaMemcpyDeviceToHost));
   return 0;
 }
 
@@ -290,6 +303,8 @@ int pico_b200_tree_serialize(const pico_b200_tree* t, void* dst, int dst_is_devi
   PICO_CUDA(cudaMemcpy(p, t->d_indices, t->n * 4, kd));
   p += align16(t->n * 4);
   PICO_CUDA(cudaMemcpy(p, t->d_pts, t->pts_bytes(), kd));
+  p += align16(t->pts_bytes());
+  if (t->topological()) PICO_CUDA(cudaMemcpy(p, t->d_outer, t->outer_bytes(), kd));
   return 0;
 }
 
@@ -331,11 +346,13 @@ int pico_b200_tree_deserialize(const void* src, uint64_t bytes, int src_is_devic
   if (!rc) rc = up(&t->d_nodes, t->n_nodes * t->node_size());
   if (!rc) rc = up(reinterpret_cast<void**>(&t->d_indices), t->n * 4);
   if (!rc) rc = up(&t->d_pts, t->pts_bytes());
+  if (!rc && t->topological()) rc = up(&t->d_outer, t->outer_bytes());
   if (rc) {
     release(t);
     return rc;
   }
-  t->device_bytes = t->pts_bytes() + t->n_nodes * t->node_size() + t->n * 4 + 2 * t->sdim * t->scalar_size();
+  t->device_bytes =
+      t->pts_bytes() + t->n_nodes * t->node_size() + t->n * 4 + 2 * t->sdim * t->scalar_size() + t->outer_bytes();
   *out = t;
   return 0;
 }
@@ -354,10 +371,25 @@ struct RefBranch {  // kd_tree_branch_single<T>, internal/kd_tree_node.hpp:42-50
 static_assert(sizeof(RefBranch<float>) == 12 && sizeof(RefBranch<double>) == 24, "raw struct sizes of the reference");
 
 template <typename T>
+struct RefBranchDouble {  // kd_tree_branch_double<T>, internal/kd_tree_node.hpp:52-59 (topological metrics)
+  int32_t split_dim;
+  T left_min;
+  T left_max;
+  T right_min;
+  T right_max;
+};
+static_assert(sizeof(RefBranchDouble<float>) == 20 && sizeof(RefBranchDouble<double>) == 40, "raw struct sizes");
+
+template <typename T>
+size_t ref_branch_bytes(bool topo) {
+  return topo ? sizeof(RefBranchDouble<T>) : sizeof(RefBranch<T>);
+}
+
+template <typename T>
 uint64_t ref_stream_bytes(const pico_b200_tree* t) {
   const uint64_t branches = t->n_nodes - t->n_leaves;
   return 8 + 8 + 4 * (uint64_t)t->n + 2 * t->sdim * sizeof(T) + t->n_leaves * (1 + 8) +
-         branches * (1 + sizeof(RefBranch<T>));
+         branches * (1 + ref_branch_bytes<T>(t->topological()));
 }
 
 template <typename T>
@@ -367,6 +399,10 @@ int ref_stream_write(const pico_b200_tree* t, unsigned char* dst) {
   std::vector<int32_t> idx(t->n);
   std::vector<T> box(2 * t->sdim);
   PICO_TRY(pico_b200_tree_export(t, nodes.data(), idx.data(), box.data()));
+  const bool topo = t->topological();
+  std::vector<T> outer(topo ? 2 * t->n_nodes : 0);
+  if (topo) PICO_TRY(pico_b200_tree_export_outer_bounds(t, outer.data()));
+  size_t node_index = 0;
   unsigned char* p = dst;
   auto put = [&](const void* src, size_t n) {
     memcpy(p, src, n);
@@ -383,6 +419,17 @@ int ref_stream_write(const pico_b200_tree* t, unsigned char* dst) {
       const int32_t be[2] = {(int32_t)nd.a.begin_idx, (int32_t)nd.b.end_idx};
       put(&flag, 1);
       put(be, 8);
+    } else if (topo) {
+      const unsigned char flag = 0;
+      RefBranchDouble<T> b;
+      memset(&b, 0, sizeof(b));
+      b.split_dim = (int32_t)nd.split_dim;
+      b.left_min = outer[2 * node_index];
+      b.left_max = nd.a.left_max;
+      b.right_min = nd.b.right_min;
+      b.right_max = outer[2 * node_index + 1];
+      put(&flag, 1);
+      put(&b, sizeof(b));
     } else {
       const unsigned char flag = 0;
       RefBranch<T> b;
@@ -393,13 +440,15 @@ int ref_stream_write(const pico_b200_tree* t, unsigned char* dst) {
       put(&flag, 1);
       put(&b, sizeof(b));
     }
+    ++node_index;
   }
   return 0;
 }
 
 template <typename T>
-int ref_stream_read(const unsigned char* src, uint64_t bytes, size_t n, size_t sdim, std::vector<int32_t>& idx,
-                    std::vector<T>& box, std::vector<typename NodeOf<T>::type>& nodes, uint64_t* consumed) {
+int ref_stream_read(const unsigned char* src, uint64_t bytes, size_t n, size_t sdim, bool topo,
+                    std::vector<int32_t>& idx, std::vector<T>& box, std::vector<typename NodeOf<T>::type>& nodes,
+                    std::vector<T>& outer, uint64_t* consumed) {
   using NodeT = typename NodeOf<T>::type;
   const unsigned char* p = src;
   const unsigned char* end = src + bytes;
@@ -420,6 +469,7 @@ int ref_stream_read(const unsigned char* src, uint64_t bytes, size_t n, size_t s
   // read_node recursion (kd_tree_data.hpp:89-107) with an explicit stack of branches whose
   // right child is still to come
   nodes.clear();
+  outer.clear();
   std::vector<uint32_t> pending;
   bool done = false;
   while (!done) {
@@ -435,6 +485,7 @@ int ref_stream_read(const unsigned char* src, uint64_t bytes, size_t n, size_t s
       nd.right = PICO_B200_LEAF;
       nd.split_dim = PICO_B200_LEAF;
       nodes.push_back(nd);
+      if (topo) outer.insert(outer.end(), 2, T(0));
       // a finished subtree: the innermost pending branch gets its right child next
       if (pending.empty()) {
         done = true;
@@ -442,6 +493,17 @@ int ref_stream_read(const unsigned char* src, uint64_t bytes, size_t n, size_t s
         nodes[pending.back()].right = (uint32_t)nodes.size();
         pending.pop_back();
       }
+    } else if (topo) {
+      RefBranchDouble<T> b;
+      if (!get(&b, sizeof(b))) return fail(PICO_B200_ERR_INVALID_ARGUMENT, "tree stream truncated");
+      nd.a.left_max = b.left_max;
+      nd.b.right_min = b.right_min;
+      nd.split_dim = (uint32_t)b.split_dim;
+      nd.right = 0;
+      pending.push_back((uint32_t)nodes.size());
+      nodes.push_back(nd);
+      outer.push_back(b.left_min);
+      outer.push_back(b.right_max);
     } else {
       RefBranch<T> b;
       if (!get(&b, sizeof(b))) return fail(PICO_B200_ERR_INVALID_ARGUMENT, "tree stream truncated");
@@ -481,21 +543,22 @@ int pico_b200_tree_load(const void* pts, size_t n, size_t sdim, size_t stride, i
   *out = nullptr;
   if (!stream) return fail(PICO_B200_ERR_INVALID_ARGUMENT, "stream is null");
   PICO_TRY(check_common(pts, n, sdim, stride, scalar, metric));
+  const bool topo = metric >= PICO_B200_METRIC_SO2;
   std::vector<int32_t> idx;
   if (scalar == PICO_B200_F32) {
-    std::vector<float> box;
+    std::vector<float> box, outer;
     std::vector<pico_b200_node_f32> nodes;
-    PICO_TRY(ref_stream_read<float>(static_cast<const unsigned char*>(stream), stream_bytes, n, sdim, idx, box, nodes,
-                                    consumed));
+    PICO_TRY(ref_stream_read<float>(static_cast<const unsigned char*>(stream), stream_bytes, n, sdim, topo, idx, box,
+                                    nodes, outer, consumed));
     return pico_b200_tree_create_from_nodes(pts, n, sdim, stride, scalar, metric, nodes.data(), nodes.size(),
-                                            idx.data(), box.data(), device, out);
+                                            idx.data(), box.data(), topo ? outer.data() : nullptr, device, out);
   }
-  std::vector<double> box;
+  std::vector<double> box, outer;
   std::vector<pico_b200_node_f64> nodes;
-  PICO_TRY(ref_stream_read<double>(static_cast<const unsigned char*>(stream), stream_bytes, n, sdim, idx, box, nodes,
-                                   consumed));
+  PICO_TRY(ref_stream_read<double>(static_cast<const unsigned char*>(stream), stream_bytes, n, sdim, topo, idx, box,
+                                   nodes, outer, consumed));
   return pico_b200_tree_create_from_nodes(pts, n, sdim, stride, scalar, metric, nodes.data(), nodes.size(),
-                                          idx.data(), box.data(), device, out);
+                                          idx.data(), box.data(), topo ? outer.data() : nullptr, device, out);
 }
 
 // ---------------------------------------------------------------- NCCL broadcast

@@ -53,6 +53,7 @@ struct BNode {
   uint32_t subtree;      // nodes in this subtree (bottom-up)
   uint32_t preorder;     // final index (top-down)
   T left_max, right_min;
+  T left_min, right_max;  // the other two bounds of kd_tree_branch_double (topological metrics)
 };
 
 // one huge node of the current level
@@ -902,6 +903,8 @@ __global__ void merge_level(BNode<T>* nodes, T* boxes, int sdim, uint32_t level_
   T* box = boxes + (size_t)node * 2 * sdim;
   nd.left_max = lb[sdim + nd.split_dim];
   nd.right_min = rb[nd.split_dim];
+  nd.left_min = lb[nd.split_dim];  // kd_tree_node_topological::set_branch, kd_tree_node.hpp:104-113
+  nd.right_max = rb[sdim + nd.split_dim];
   for (int d = 0; d < sdim; ++d) {
     T mn = lb[d], mx = lb[sdim + d];
     if (rb[d] < mn) mn = rb[d];
@@ -923,7 +926,7 @@ __global__ void number_level(BNode<T>* nodes, uint32_t level_begin, uint32_t lev
 }
 
 template <typename T>
-__global__ void emit_nodes(const BNode<T>* nodes, uint32_t n_nodes, typename NodeOf<T>::type* out) {
+__global__ void emit_nodes(const BNode<T>* nodes, uint32_t n_nodes, typename NodeOf<T>::type* out, T* outer) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_nodes) return;
   const BNode<T>& nd = nodes[i];
@@ -941,6 +944,11 @@ __global__ void emit_nodes(const BNode<T>* nodes, uint32_t n_nodes, typename Nod
     o.split_dim = (uint32_t)nd.split_dim;
   }
   out[nd.preorder] = o;
+  if (outer) {
+    const bool leaf = nd.split_dim < 0;
+    outer[2 * (size_t)nd.preorder] = leaf ? T(0) : nd.left_min;
+    outer[2 * (size_t)nd.preorder + 1] = leaf ? T(0) : nd.right_max;
+  }
 }
 
 // leaf-ordered point storage
@@ -1009,7 +1017,7 @@ int finalize_storage(pico_b200_tree* t, const T* d_raw, cudaStream_t st) {
                                                                       static_cast<T*>(t->d_pts));
   }
   PICO_CUDA(cudaGetLastError());
-  t->device_bytes = t->pts_bytes() + t->n_nodes * t->node_size() + n * 4 + 2 * t->sdim * sizeof(T);
+  t->device_bytes = t->pts_bytes() + t->n_nodes * t->node_size() + n * 4 + 2 * t->sdim * sizeof(T) + t->outer_bytes();
   return 0;
 }
 
@@ -1218,8 +1226,10 @@ int build_tree(pico_b200_tree* t, const T* h_pts, size_t stride, int rule, int s
     number_level<T><<<(le - lb + 127) / 128, 128, 0, st>>>(s.nodes, lb, le);
   }
   PICO_CUDA(cudaMalloc(&t->d_nodes, (size_t)n_nodes * t->node_size()));
+  if (t->topological()) PICO_CUDA(cudaMalloc(&t->d_outer, t->outer_bytes()));
   emit_nodes<T><<<(n_nodes + 255) / 256, 256, 0, st>>>(s.nodes, n_nodes,
-                                                        static_cast<typename NodeOf<T>::type*>(t->d_nodes));
+                                                        static_cast<typename NodeOf<T>::type*>(t->d_nodes),
+                                                        static_cast<T*>(t->d_outer));
   PICO_CUDA(cudaGetLastError());
   PICO_TRY(finalize_storage<T>(t, raw.as<T>(), st));
   PICO_CUDA(cudaEventRecord(ev1, st));
@@ -1235,7 +1245,7 @@ int build_tree(pico_b200_tree* t, const T* h_pts, size_t stride, int rule, int s
 // Upload of an existing tree (kd_tree::load path).
 template <typename T>
 int upload_tree(pico_b200_tree* t, const T* h_pts, size_t stride, const void* h_nodes, size_t n_nodes,
-                const int32_t* indices, const T* root_box) {
+                const int32_t* indices, const T* root_box, const T* outer_bounds) {
   using NodeT = typename NodeOf<T>::type;
   const size_t n = t->n;
   const int sdim = (int)t->sdim;
@@ -1284,6 +1294,11 @@ int upload_tree(pico_b200_tree* t, const T* h_pts, size_t stride, const void* h_
   PICO_CUDA(cudaMemcpyAsync(t->d_indices, indices, n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   PICO_CUDA(cudaMemcpyAsync(t->d_root_box, root_box, 2 * sdim * sizeof(T), cudaMemcpyHostToDevice, st));
   PICO_CUDA(cudaMemcpyAsync(t->d_nodes, nodes, n_nodes * sizeof(NodeT), cudaMemcpyHostToDevice, st));
+  if (t->topological()) {
+    if (!outer_bounds) return fail(PICO_B200_ERR_INVALID_ARGUMENT, "topological metric needs the outer bounds");
+    PICO_CUDA(cudaMalloc(&t->d_outer, t->outer_bytes()));
+    PICO_CUDA(cudaMemcpyAsync(t->d_outer, outer_bounds, t->outer_bytes(), cudaMemcpyHostToDevice, st));
+  }
   for (int d = 0; d < sdim && d < 4; ++d) {
     t->root_box_host[d] = (double)root_box[d];
     t->root_box_host[4 + d] = (double)root_box[sdim + d];
@@ -1297,8 +1312,8 @@ template int build_tree<float>(pico_b200_tree*, const float*, size_t, int, int, 
 template int build_tree<double>(pico_b200_tree*, const double*, size_t, int, int, size_t, const double*,
                                 const double*);
 template int upload_tree<float>(pico_b200_tree*, const float*, size_t, const void*, size_t, const int32_t*,
-                                const float*);
+                                const float*, const float*);
 template int upload_tree<double>(pico_b200_tree*, const double*, size_t, const void*, size_t, const int32_t*,
-                                 const double*);
+                                 const double*, const double*);
 
 }  // namespace pico

@@ -5,6 +5,7 @@
 //   pts4    : Vec4<T>[n] for sdim <= 3, LEAF ORDER, .w carries the original index
 //   ptsN    : T[n * sdim] row-major for sdim > 3, LEAF ORDER
 //   indices : int32[n], leaf position -> original index (kd_tree_data::indices)
+//   outer   : T[n_nodes][2] = {left_min, right_max}, topological metrics only
 #pragma once
 
 #include <cuda_runtime.h>
@@ -94,6 +95,7 @@ struct pico_b200_tree {
   void* d_pts = nullptr;       // pts4 or ptsN (see above)
   int32_t* d_indices = nullptr;
   void* d_root_box = nullptr;  // min[sdim] then max[sdim], device copy
+  void* d_outer = nullptr;     // topological metrics: {left_min, right_max}[n_nodes] (kd_tree_node.hpp:52-59)
   double root_box_host[2 * 4] = {0};  // first min(sdim,4) dims, as double, for query ordering
   double build_ms = 0.0;
   size_t device_bytes = 0;
@@ -101,6 +103,8 @@ struct pico_b200_tree {
   size_t scalar_size() const { return scalar == PICO_B200_F64 ? 8 : 4; }
   size_t node_size() const { return scalar == PICO_B200_F64 ? 32 : 16; }
   bool packed() const { return sdim <= (size_t)pico::kMaxPackedDim; }
+  bool topological() const { return metric >= PICO_B200_METRIC_SO2; }
+  size_t outer_bytes() const { return topological() ? n_nodes * 2 * scalar_size() : 0; }
   size_t pts_bytes() const { return packed() ? n * 4 * scalar_size() : n * sdim * scalar_size(); }
 };
 
@@ -112,7 +116,7 @@ int build_tree(pico_b200_tree* t, const T* h_pts, size_t stride, int rule, int s
                const T* bounds_min, const T* bounds_max);
 template <typename T>
 int upload_tree(pico_b200_tree* t, const T* h_pts, size_t stride, const void* nodes, size_t n_nodes,
-                const int32_t* indices, const T* root_box);
+                const int32_t* indices, const T* root_box, const T* outer_bounds);
 
 // search.cu
 int set_thread_stream(void* stream, bool has);

@@ -54,6 +54,7 @@ __global__ void morton_kernel(const T* __restrict__ q, size_t stride, uint32_t n
 template <typename T>
 struct KnnArgs {
   const typename NodeOf<T>::type* nodes;
+  const T* outer;  // {left_min, right_max} per node, topological metrics only
   const typename Vec4Of<T>::type* pts4;
   const T* rows;
   const int32_t* indices;
@@ -89,10 +90,10 @@ __global__ void __launch_bounds__(kThreadsPerBlock) knn_thread_kernel(KnnArgs<T>
         st.node = static_cast<uint32_t*>(a.ws) + tid;
         st.dist = reinterpret_cast<T*>(static_cast<uint32_t*>(a.ws) + a.ws_stride * a.ws_depth) + tid;
         st.off = st.dist + a.ws_stride * a.ws_depth;
-        traverse_packed<T, DIM, FAST, true>(a.nodes, a.pts4, q, a.metric, a.approx != 0, a.e_inv, st, vis);
+        traverse_packed<T, DIM, FAST, true>(a.nodes, a.pts4, a.outer, q, a.metric, a.approx != 0, a.e_inv, st, vis);
       } else {
         LocalStack<T, DIM, kLocalStack> st;
-        traverse_packed<T, DIM, FAST, true>(a.nodes, a.pts4, q, a.metric, a.approx != 0, a.e_inv, st, vis);
+        traverse_packed<T, DIM, FAST, true>(a.nodes, a.pts4, a.outer, q, a.metric, a.approx != 0, a.e_inv, st, vis);
       }
       out->index = vis.idx;
       out->distance = vis.best;
@@ -106,10 +107,10 @@ __global__ void __launch_bounds__(kThreadsPerBlock) knn_thread_kernel(KnnArgs<T>
         st.node = static_cast<uint32_t*>(a.ws) + tid;
         st.dist = reinterpret_cast<T*>(static_cast<uint32_t*>(a.ws) + a.ws_stride * a.ws_depth) + tid;
         st.off = st.dist + a.ws_stride * a.ws_depth;
-        traverse_packed<T, DIM, FAST, false>(a.nodes, a.pts4, q, a.metric, a.approx != 0, a.e_inv, st, vis);
+        traverse_packed<T, DIM, FAST, false>(a.nodes, a.pts4, a.outer, q, a.metric, a.approx != 0, a.e_inv, st, vis);
       } else {
         LocalStack<T, DIM, kLocalStack> st;
-        traverse_packed<T, DIM, FAST, false>(a.nodes, a.pts4, q, a.metric, a.approx != 0, a.e_inv, st, vis);
+        traverse_packed<T, DIM, FAST, false>(a.nodes, a.pts4, a.outer, q, a.metric, a.approx != 0, a.e_inv, st, vis);
       }
 #pragma unroll
       for (int i = 0; i < KMAX; ++i) {
@@ -156,16 +157,16 @@ __global__ void __launch_bounds__(kThreadsPerBlock) radius_thread_kernel(RadiusA
       vis.radius = r.radius;
       vis.out = r.hits + r.offsets[qi];
       if (DEEP)
-        traverse_packed<T, DIM, false, false>(a.nodes, a.pts4, q, a.metric, a.approx != 0, a.e_inv, gst, vis);
+        traverse_packed<T, DIM, false, false>(a.nodes, a.pts4, a.outer, q, a.metric, a.approx != 0, a.e_inv, gst, vis);
       else
-        traverse_packed<T, DIM, false, false>(a.nodes, a.pts4, q, a.metric, a.approx != 0, a.e_inv, lst, vis);
+        traverse_packed<T, DIM, false, false>(a.nodes, a.pts4, a.outer, q, a.metric, a.approx != 0, a.e_inv, lst, vis);
     } else {
       VisitRadiusCount<T> vis;
       vis.radius = r.radius;
       if (DEEP)
-        traverse_packed<T, DIM, false, false>(a.nodes, a.pts4, q, a.metric, a.approx != 0, a.e_inv, gst, vis);
+        traverse_packed<T, DIM, false, false>(a.nodes, a.pts4, a.outer, q, a.metric, a.approx != 0, a.e_inv, gst, vis);
       else
-        traverse_packed<T, DIM, false, false>(a.nodes, a.pts4, q, a.metric, a.approx != 0, a.e_inv, lst, vis);
+        traverse_packed<T, DIM, false, false>(a.nodes, a.pts4, a.outer, q, a.metric, a.approx != 0, a.e_inv, lst, vis);
       r.counts[qi] = vis.count;
     }
   }
@@ -197,12 +198,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) knn_warp_kernel(KnnArgs<T
     if (REGLIST) {
       WarpVisitKnn<T, WarpKnnReg<T>> vis;
       vis.list.init(a.k);
-      traverse_warp<T, PACKED>(a.nodes, ps, sq, so, stack, a.metric, a.approx != 0, a.e_inv, vis);
+      traverse_warp<T, PACKED>(a.nodes, a.outer, ps, sq, so, stack, a.metric, a.approx != 0, a.e_inv, vis);
       vis.list.store(row);
     } else {
       WarpVisitKnn<T, WarpKnnMem<T>> vis;
       vis.list.init(row, a.k);
-      traverse_warp<T, PACKED>(a.nodes, ps, sq, so, stack, a.metric, a.approx != 0, a.e_inv, vis);
+      traverse_warp<T, PACKED>(a.nodes, a.outer, ps, sq, so, stack, a.metric, a.approx != 0, a.e_inv, vis);
     }
   }
 }
@@ -231,7 +232,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) radius_warp_kernel(Radius
     WarpVisitRadius<T> vis;
     vis.radius = r.radius;
     vis.out = r.hits ? r.hits + r.offsets[qi] : nullptr;
-    traverse_warp<T, PACKED>(a.nodes, ps, sq, so, stack, a.metric, a.approx != 0, a.e_inv, vis);
+    traverse_warp<T, PACKED>(a.nodes, a.outer, ps, sq, so, stack, a.metric, a.approx != 0, a.e_inv, vis);
     if (!r.hits && lane == 0) r.counts[qi] = vis.count;
   }
 }
@@ -239,6 +240,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) radius_warp_kernel(Radius
 template <typename T>
 struct BoxArgs {
   const typename NodeOf<T>::type* nodes;
+  const T* outer;
+  int metric;
   const typename Vec4Of<T>::type* pts4;
   const T* rows;
   const int32_t* indices;
@@ -280,7 +283,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) box_warp_kernel(BoxArgs<T
     for (int j = lane; j < 2 * a.sdim; j += 32) sbox[j] = a.root_box[j];
     __syncwarp();
     int32_t* out = a.hits ? a.hits + a.offsets[bi] : nullptr;
-    const uint32_t c = traverse_box_warp<T, PACKED>(a.nodes, ps, a.indices, qmin, qmax, sbox, stack, saved, out);
+    const uint32_t c = traverse_box_warp<T, PACKED>(a.nodes, a.outer, a.metric, ps, a.indices, qmin, qmax, sbox, stack, saved, out);
     if (!a.hits && lane == 0) a.counts[bi] = c;
   }
 }
@@ -407,6 +410,7 @@ template <typename T>
 void fill_base(KnnArgs<T>& a, const pico_b200_tree* t, const T* d_q, size_t d_stride, size_t nq, const uint32_t* perm,
                double e) {
   a.nodes = static_cast<const typename NodeOf<T>::type*>(t->d_nodes);
+  a.outer = static_cast<const T*>(t->d_outer);
   a.pts4 = t->packed() ? static_cast<const typename Vec4Of<T>::type*>(t->d_pts) : nullptr;
   a.rows = t->packed() ? nullptr : static_cast<const T*>(t->d_pts);
   a.indices = t->d_indices;
@@ -857,6 +861,8 @@ int box_batch(const pico_b200_tree* t, const T* mins, const T* maxs, size_t nb, 
 
   BoxArgs<T> a;
   a.nodes = static_cast<const typename NodeOf<T>::type*>(t->d_nodes);
+  a.outer = static_cast<const T*>(t->d_outer);
+  a.metric = t->metric;
   a.pts4 = t->packed() ? static_cast<const typename Vec4Of<T>::type*>(t->d_pts) : nullptr;
   a.rows = t->packed() ? nullptr : static_cast<const T*>(t->d_pts);
   a.indices = t->d_indices;

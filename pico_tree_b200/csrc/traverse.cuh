@@ -60,15 +60,33 @@ __device__ __forceinline__ void load_node(const pico_b200_node_f64* nodes, uint3
   sd = r1.y;
 }
 
-// metric(x): metric.hpp:93-96,119-122,147-150,176-179
+// metric(x): metric.hpp:93-96,119-122,147-150,176-179,210-213,240-243
 template <typename T>
 __device__ __forceinline__ T metric1(int metric, T x) {
-  return metric == PICO_B200_METRIC_L2_SQUARED ? mul_rn(x, x) : abs_t(x);
+  return (metric == PICO_B200_METRIC_L2_SQUARED || metric == PICO_B200_METRIC_SE2_SQUARED) ? mul_rn(x, x) : abs_t(x);
 }
 
-// One term folded into the running distance, j ascending (metric.hpp:36-51, :131-145, :158-174).
+__device__ __forceinline__ bool is_topological(int metric) { return metric >= PICO_B200_METRIC_SO2; }
+
+// s1_distance, distance.hpp:19-22: d = |x - y|; std::min(d, 1 - d)
 template <typename T>
-__device__ __forceinline__ T metric_fold(int metric, T d, T qj, T pj) {
+__device__ __forceinline__ T s1_distance(T x, T y) {
+  const T d = abs_t(sub_rn(x, y));
+  const T o = sub_rn(T(1.0), d);
+  return o < d ? o : d;
+}
+
+// apply_dim_space: metric_so2 sees every dimension as the circle (metric.hpp:215-218),
+// metric_se2_squared dimensions 0 and 1 as the line and the rest as the circle (:245-252).
+__device__ __forceinline__ bool dim_is_s1(int metric, uint32_t dim) {
+  return metric == PICO_B200_METRIC_SO2 || (metric == PICO_B200_METRIC_SE2_SQUARED && dim >= 2);
+}
+
+// One term folded into the running distance, j ascending (metric.hpp:36-51, :131-145, :158-174;
+// so2 :203-208 looks at coordinate 0 only; se2_squared :229-238 sums two squared differences and
+// adds the squared circle distance of the third coordinate).
+template <typename T>
+__device__ __forceinline__ T metric_fold(int metric, T d, T qj, T pj, int j) {
   const T t = sub_rn(qj, pj);
   switch (metric) {
     case PICO_B200_METRIC_L2_SQUARED:
@@ -79,10 +97,72 @@ __device__ __forceinline__ T metric_fold(int metric, T d, T qj, T pj) {
       const T a = abs_t(t);
       return d < a ? a : d;
     }
-    default: {
+    case PICO_B200_METRIC_LNINF: {
       const T a = abs_t(t);
       return a < d ? a : d;
     }
+    case PICO_B200_METRIC_SO2:
+      return j == 0 ? s1_distance(qj, pj) : d;
+    default: {  // PICO_B200_METRIC_SE2_SQUARED
+      if (j < 2) return add_rn(d, mul_rn(t, t));
+      if (j > 2) return d;
+      const T c = s1_distance(qj, pj);
+      return add_rn(d, mul_rn(c, c));
+    }
+  }
+}
+
+// search_nearest_topological::box_distance (kd_tree_search.hpp:205-229): distance of v to the
+// segment [mn, mx] on the line (segment.hpp:34-42) or on the circle (:76-100), then metric(d).
+template <typename T>
+__device__ __forceinline__ T topo_box_distance(int metric, T mn, T mx, T v, uint32_t dim) {
+  T d = T(0);
+  if (!dim_is_s1(metric, dim)) {
+    if (v < mn)
+      d = sub_rn(mn, v);
+    else if (v > mx)
+      d = sub_rn(v, mx);
+  } else {
+    const T a = s1_distance(v, mn), b = s1_distance(v, mx);
+    const T m = b < a ? b : a;
+    if (mn <= mx) {
+      if (v < mn || v > mx) d = m;
+    } else {
+      if (!(v < mx || v > mn)) d = m;
+    }
+  }
+  return metric1(metric, d);
+}
+
+// {left_min, right_max} of node i (kd_tree_branch_double's two extra bounds, kd_tree_node.hpp:52-59)
+__device__ __forceinline__ void load_outer(const float* outer, uint32_t i, float& lmin, float& rmax) {
+  const float2 r = __ldg(reinterpret_cast<const float2*>(outer) + i);
+  lmin = r.x;
+  rmax = r.y;
+}
+__device__ __forceinline__ void load_outer(const double* outer, uint32_t i, double& lmin, double& rmax) {
+  const double2 r = __ldg(reinterpret_cast<const double2*>(outer) + i);
+  lmin = r.x;
+  rmax = r.y;
+}
+
+// Which child is nearer, and the box offset of the other one on split_dim.
+//   euclidean   (kd_tree_search.hpp:76-88): left iff (left_max + right_min - v - v) > 0, evaluated left
+//               to right; offset = metric(bound - v)
+//   topological (kd_tree_search.hpp:166-186): left iff d(left box) < d(right box); offset = the larger one
+template <typename T>
+__device__ __forceinline__ void branch_choice(int metric, const T* __restrict__ outer, uint32_t node, T a, T b, T v,
+                                              uint32_t sd, bool& go_left, T& new_off) {
+  if (is_topological(metric)) {
+    T lmin, rmax;
+    load_outer(outer, node, lmin, rmax);
+    const T d1 = topo_box_distance(metric, lmin, a, v, sd);
+    const T d2 = topo_box_distance(metric, b, rmax, v, sd);
+    go_left = d1 < d2;
+    new_off = go_left ? d2 : d1;
+  } else {
+    go_left = sub_rn(sub_rn(add_rn(a, b), v), v) > T(0);
+    new_off = metric1(metric, sub_rn(go_left ? b : a, v));
   }
 }
 template <typename T>
@@ -151,8 +231,8 @@ struct GlobalStack {
 template <typename T, int DIM, bool FAST, bool PRIME, typename Stack, typename Visitor>
 __device__ __forceinline__ void traverse_packed(const typename NodeOf<T>::type* __restrict__ nodes,
                                                 const typename Vec4Of<T>::type* __restrict__ pts4,
-                                                const T (&q)[DIM], int metric_rt, bool approx_rt, T e_inv, Stack& stack,
-                                                Visitor& vis) {
+                                                const T* __restrict__ outer, const T (&q)[DIM], int metric_rt,
+                                                bool approx_rt, T e_inv, Stack& stack, Visitor& vis) {
   const int metric = FAST ? (int)PICO_B200_METRIC_L2_SQUARED : metric_rt;
   const bool approx = FAST ? false : approx_rt;
   T off[DIM];
@@ -172,15 +252,18 @@ __device__ __forceinline__ void traverse_packed(const typename NodeOf<T>::type* 
 #pragma unroll
       for (int j = 1; j < DIM; ++j)
         if (sd == (uint32_t)j) v = q[j];
-      node = (sub_rn(sub_rn(add_rn(a, b), v), v) > T(0)) ? node + 1 : right;
+      bool go_left;
+      T unused;
+      branch_choice(metric, outer, node, a, b, v, sd, go_left, unused);
+      node = go_left ? node + 1 : right;
       load_node(nodes, node, a, b, right, sd, lb, le);
     }
     for (int i = lb; i < le; ++i) {
       const typename Vec4Of<T>::type p = ldg4(pts4 + i);
       T d = metric_init<T>(metric);
-      d = metric_fold(metric, d, q[0], p.x);
-      if (DIM > 1) d = metric_fold(metric, d, q[DIM > 1 ? 1 : 0], p.y);
-      if (DIM > 2) d = metric_fold(metric, d, q[DIM > 2 ? 2 : 0], p.z);
+      d = metric_fold(metric, d, q[0], p.x, 0);
+      if (DIM > 1) d = metric_fold(metric, d, q[DIM > 1 ? 1 : 0], p.y, 1);
+      if (DIM > 2) d = metric_fold(metric, d, q[DIM > 2 ? 2 : 0], p.z, 2);
       if (approx) d = mul_rn(d, e_inv);
       vis.visit(index_of(p), d);
     }
@@ -202,9 +285,9 @@ __device__ __forceinline__ void traverse_packed(const typename NodeOf<T>::type* 
           old = off[j];
         }
       }
-      // (left_max + right_min - v - v) > 0, evaluated left to right
-      const bool go_left = sub_rn(sub_rn(add_rn(a, b), v), v) > T(0);
-      const T new_off = metric1(metric, sub_rn(go_left ? b : a, v));
+      bool go_left;
+      T new_off;
+      branch_choice(metric, outer, node, a, b, v, sd, go_left, new_off);
       const uint32_t far = go_left ? right : node + 1;
       node = go_left ? node + 1 : right;
       // node_box_distance - old_offset + new_offset (kd_tree_search.hpp:93-94)
@@ -225,9 +308,9 @@ __device__ __forceinline__ void traverse_packed(const typename NodeOf<T>::type* 
     for (int i = lb; i < le; ++i) {
       const typename Vec4Of<T>::type p = ldg4(pts4 + i);
       T d = metric_init<T>(metric);
-      d = metric_fold(metric, d, q[0], p.x);
-      if (DIM > 1) d = metric_fold(metric, d, q[DIM > 1 ? 1 : 0], p.y);
-      if (DIM > 2) d = metric_fold(metric, d, q[DIM > 2 ? 2 : 0], p.z);
+      d = metric_fold(metric, d, q[0], p.x, 0);
+      if (DIM > 1) d = metric_fold(metric, d, q[DIM > 1 ? 1 : 0], p.y, 1);
+      if (DIM > 2) d = metric_fold(metric, d, q[DIM > 2 ? 2 : 0], p.z, 2);
       if (approx) d = mul_rn(d, e_inv);
       vis.visit(index_of(p), d);
     }

@@ -36,31 +36,35 @@ struct PointSet {
     T d = metric_init<T>(metric);
     if (PACKED) {
       const typename Vec4Of<T>::type p = ldg4(pts4 + i);
-      d = metric_fold(metric, d, q[0], p.x);
-      if (sdim > 1) d = metric_fold(metric, d, q[1], p.y);
-      if (sdim > 2) d = metric_fold(metric, d, q[2], p.z);
+      d = metric_fold(metric, d, q[0], p.x, 0);
+      if (sdim > 1) d = metric_fold(metric, d, q[1], p.y, 1);
+      if (sdim > 2) d = metric_fold(metric, d, q[2], p.z, 2);
       index = index_of(p);
     } else {
       const T* p = rows + (size_t)i * sdim;
-      for (int j = 0; j < sdim; ++j) d = metric_fold(metric, d, q[j], __ldg(p + j));
+      for (int j = 0; j < sdim; ++j) d = metric_fold(metric, d, q[j], __ldg(p + j), j);
       index = __ldg(indices + i);
     }
     return d;
   }
-  __device__ __forceinline__ bool inside(int i, const T* qmin, const T* qmax, int& index) const {
-    // box_base::contains(point), box.hpp:31-40 (inclusive)
+  // is coordinate x of dimension j inside the query interval: box_base::contains(point), box.hpp:31-40
+  // (inclusive); topological spaces: metric_box_map::contains, box.hpp:305-312 — an interval on the
+  // circle with min > max wraps around (segment_s1::contains, segment.hpp:63-69)
+  __device__ __forceinline__ static bool coord_inside(int metric, int j, T mn, T mx, T x) {
+    if (!is_topological(metric)) return !(mn > x || mx < x);
+    if (!dim_is_s1(metric, (uint32_t)j) || mn <= mx) return mn <= x && x <= mx;
+    return x >= mn || x <= mx;
+  }
+  __device__ __forceinline__ bool inside(int i, const T* qmin, const T* qmax, int metric, int& index) const {
     bool ok = true;
     if (PACKED) {
       const typename Vec4Of<T>::type p = ldg4(pts4 + i);
       const T c[3] = {p.x, p.y, p.z};
-      for (int j = 0; j < sdim; ++j) ok = ok && !(qmin[j] > c[j] || qmax[j] < c[j]);
+      for (int j = 0; j < sdim; ++j) ok = ok && coord_inside(metric, j, qmin[j], qmax[j], c[j]);
       index = index_of(p);
     } else {
       const T* p = rows + (size_t)i * sdim;
-      for (int j = 0; j < sdim; ++j) {
-        const T x = __ldg(p + j);
-        ok = ok && !(qmin[j] > x || qmax[j] < x);
-      }
+      for (int j = 0; j < sdim; ++j) ok = ok && coord_inside(metric, j, qmin[j], qmax[j], __ldg(p + j));
       index = __ldg(indices + i);
     }
     return ok;
@@ -191,9 +195,9 @@ struct WarpVisitRadius {
 // ---------------------------------------------------------------- nearest traversal
 // `sq` = query, `so` = node_box_offset_ (both shared, sdim entries, warp-private).
 template <typename T, bool PACKED, typename Visitor>
-__device__ void traverse_warp(const typename NodeOf<T>::type* __restrict__ nodes, const PointSet<T, PACKED>& ps,
-                              const T* sq, T* so, WarpFrame<T>* stack, int metric, bool approx, T e_inv,
-                              Visitor& vis) {
+__device__ void traverse_warp(const typename NodeOf<T>::type* __restrict__ nodes, const T* __restrict__ outer,
+                              const PointSet<T, PACKED>& ps, const T* sq, T* so, WarpFrame<T>* stack, int metric,
+                              bool approx, T e_inv, Visitor& vis) {
   const int lane = threadIdx.x & 31;
   uint32_t node = 0;
   T node_dist = T(0);
@@ -205,8 +209,9 @@ __device__ void traverse_warp(const typename NodeOf<T>::type* __restrict__ nodes
     load_node(nodes, node, a, b, right, sd, lb, le);
     while (sd != PICO_B200_LEAF) {
       const T v = sq[sd];
-      const bool go_left = sub_rn(sub_rn(add_rn(a, b), v), v) > T(0);
-      const T new_off = metric1(metric, sub_rn(go_left ? b : a, v));
+      bool go_left;
+      T new_off;
+      branch_choice(metric, outer, node, a, b, v, sd, go_left, new_off);
       if (lane == 0) {
         WarpFrame<T> f;
         f.far = go_left ? right : node + 1;
@@ -276,9 +281,9 @@ struct BoxFrame {
 // frame has to put back. With out == nullptr only counts.
 template <typename T, bool PACKED>
 __device__ uint32_t traverse_box_warp(const typename NodeOf<T>::type* __restrict__ nodes,
-                                      const PointSet<T, PACKED>& ps, const int32_t* __restrict__ indices,
-                                      const T* qmin, const T* qmax, T* sbox, BoxFrame* stack, T* saved,
-                                      int32_t* out) {
+                                      const T* __restrict__ outer, int metric, const PointSet<T, PACKED>& ps,
+                                      const int32_t* __restrict__ indices, const T* qmin, const T* qmax, T* sbox,
+                                      BoxFrame* stack, T* saved, int32_t* out) {
   const int lane = threadIdx.x & 31;
   const int sdim = ps.sdim;
   uint32_t count = 0;
@@ -299,7 +304,7 @@ __device__ uint32_t traverse_box_warp(const typename NodeOf<T>::type* __restrict
       for (int base = lb; base < le; base += 32) {
         const int i = base + lane;
         int idx = -1;
-        const bool in = (i < le) && ps.inside(i, qmin, qmax, idx);
+        const bool in = (i < le) && ps.inside(i, qmin, qmax, metric, idx);
         const unsigned hits = __ballot_sync(0xffffffffu, in);
         if (out && in) out[count + __popc(hits & ((1u << lane) - 1u))] = idx;
         count += __popc(hits);
@@ -330,12 +335,26 @@ __device__ uint32_t traverse_box_warp(const typename NodeOf<T>::type* __restrict
       stack[sp - 1].stage = f.stage + 1;
     }
     __syncwarp();
-    // query.contains(box_) := contains(box.min) && contains(box.max)  (box.hpp:44-47)
+    // query.contains(box_) := contains(box.min) && contains(box.max)  (box.hpp:44-47); topological:
+    // metric_box_map::contains(box), box.hpp:317-329 — per dimension the cell [min, max] must lie in
+    // the query segment, which on the circle may wrap (segment_s1::contains(segment_r1), segment.hpp:71-77)
     bool contained = true;
-    for (int j = lane; j < 2 * sdim; j += 32) {
-      const int dj = j < sdim ? j : j - sdim;
-      const T x = sbox[j];
-      if (qmin[dj] > x || qmax[dj] < x) contained = false;
+    if (!is_topological(metric)) {
+      for (int j = lane; j < 2 * sdim; j += 32) {
+        const int dj = j < sdim ? j : j - sdim;
+        const T x = sbox[j];
+        if (qmin[dj] > x || qmax[dj] < x) contained = false;
+      }
+    } else {
+      for (int j = lane; j < sdim; j += 32) {
+        const T mn = qmin[j], mx = qmax[j], cmin = sbox[j], cmax = sbox[sdim + j];
+        bool in;
+        if (!dim_is_s1(metric, (uint32_t)j) || mn <= mx)
+          in = mn <= cmin && cmax <= mx;
+        else
+          in = cmin >= mn || cmax <= mx;
+        if (!in) contained = false;
+      }
     }
     contained = __all_sync(0xffffffffu, contained);
     if (contained) {
@@ -358,7 +377,13 @@ __device__ uint32_t traverse_box_warp(const typename NodeOf<T>::type* __restrict
         for (int i = rb + lane; i < re; i += 32) out[count + (i - rb)] = __ldg(indices + i);
       count += (uint32_t)(re - rb);
     } else {
-      const bool intersects = (f.stage == 0) ? (qmin[sd] <= a) : (qmax[sd] >= b);
+      // intersects_left / intersects_right, kd_tree_search.hpp:310-328
+      bool intersects = (f.stage == 0) ? (qmin[sd] <= a) : (qmax[sd] >= b);
+      if (is_topological(metric)) {
+        T lmin, rmax;
+        load_outer(outer, f.node, lmin, rmax);
+        intersects = intersects || ((f.stage == 0) ? (qmax[sd] >= lmin) : (qmin[sd] <= rmax));
+      }
       if (intersects) {
         if (lane == 0) {
           stack[sp].node = child;

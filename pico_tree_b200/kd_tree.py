@@ -24,6 +24,8 @@ class Metric(enum.Enum):
     L2Squared = 1
     LPInf = 2
     LNInf = 3
+    SO2 = 4          # the circle [0, 1), sdim 1 (metric.hpp:197-221; C++ API only in the reference)
+    SE2Squared = 5   # R2 x S1, sdim 3 (metric.hpp:223-257)
 
 
 class Rule(enum.Enum):
@@ -202,7 +204,7 @@ class KdTree:
     def metric(self, scalar):
         """Metric applied to a scalar (metric.hpp:93-96,119-122,147-150): |x| or x*x."""
         x = self._dtype.type(scalar)
-        return float(x * x) if self._metric == Metric.L2Squared else float(abs(x))
+        return float(x * x) if self._metric in (Metric.L2Squared, Metric.SE2Squared) else float(abs(x))
 
     def info(self):
         inf = _lib.TreeInfo()
@@ -221,6 +223,12 @@ class KdTree:
         box = np.empty((2, self.sdim), dtype=self._dtype)
         _lib.check(_lib.lib().pico_b200_tree_export(self._h, _ptr(nodes), _ptr(indices), _ptr(box)))
         return nodes, indices, box
+
+    def export_outer_bounds(self):
+        """(n_nodes, 2) = (left_min, right_max) per node — topological metrics only."""
+        out = np.empty((self.info()["n_nodes"], 2), dtype=self._dtype)
+        _lib.check(_lib.lib().pico_b200_tree_export_outer_bounds(self._h, _ptr(out)))
+        return out
 
     def leaf_ranges(self):
         """Index ranges of all non-empty leaves in DFS order (kd_tree.hpp:325)."""

@@ -188,7 +188,6 @@ TEST(KdTreeTest, QueryKnn1) { query_knn<point_2f>(1024 * 1024, 100.0f, 1); }
 
 TEST(KdTreeTest, QueryKnn10) { query_knn<point_2f>(1024 * 1024, 100.0f, 10); }
 
-#if defined(PICO_TEST_TOPOLOGICAL)
 TEST(KdTreeTest, QuerySo2Knn4) {
   using space_type = space<point_1f>;
   std::vector<point_1f> random = generate_random_n<point_1f>(256 * 256, 0.0f, 1.0f);
@@ -196,6 +195,20 @@ TEST(KdTreeTest, QuerySo2Knn4) {
   test_knn(tree, 8, point_1f{1.0f});
   test_knn(tree, 8, point_1f{0.02f});
   test_knn(tree, 1, point_1f{0.999f});
+  // boxes on the circle: [0.90, 1.00] and the wrapping [0.95, 0.05] (kd_tree_test.cpp:95-97)
+  for (auto const& mm : {std::pair<float, float>{0.90f, 1.00f}, std::pair<float, float>{0.95f, 0.05f}}) {
+    point_1f lo{mm.first}, hi{mm.second};
+    std::vector<int> idxs;
+    tree.search_box(lo, hi, idxs);
+    auto inside = [&](float x) {
+      return mm.first <= mm.second ? (mm.first <= x && x <= mm.second) : (x >= mm.first || x <= mm.second);
+    };
+    std::size_t count = 0;
+    for (auto const& p : random) count += inside(p[0]);
+    for (int j : idxs) EXPECT_TRUE(inside(random[static_cast<std::size_t>(j)][0]));
+    EXPECT_EQ(count, idxs.size());
+    EXPECT_GE(count, 1000u);
+  }
 }
 
 TEST(KdTreeTest, QuerySe2Knn) {
@@ -206,7 +219,6 @@ TEST(KdTreeTest, QuerySe2Knn) {
   test_knn(tree, 3, point_3f{0.1f, 0.9f, 0.01f});
   test_radius(tree, 0.05f);
 }
-#endif
 
 TEST(KdTreeTest, WriteRead) {
   std::vector<point_2f> random = generate_random_n<point_2f>(100, 2.0f);

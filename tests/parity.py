@@ -17,6 +17,17 @@ def ref_distance(pts, q, idx, metric="l2_squared"):
     in the scalar type of `pts`; q: (m, d), idx: (m,)."""
     p = pts[idx]
     t = q.astype(pts.dtype) - p
+    one = pts.dtype.type(1.0)
+    if metric == "so2":  # s1_distance of coordinate 0, distance.hpp:19-22
+        d = np.abs(t[:, 0])
+        return np.minimum(d, one - d)
+    if metric == "se2_squared":  # metric.hpp:229-238
+        d = np.zeros(len(q), dtype=pts.dtype)
+        for j in range(2):
+            d = d + t[:, j] * t[:, j]
+        c = np.abs(t[:, 2])
+        c = np.minimum(c, one - c)
+        return d + c * c
     if metric == "l2_squared":
         terms = t * t
     else:

@@ -11,7 +11,8 @@ from parity import (assert_knn_parity, assert_radius_parity, assert_same_structu
 
 pytestmark = pytest.mark.gpu
 
-METRIC = {"l2_squared": "L2Squared", "l1": "L1", "lpinf": "LPInf", "lninf": "LNInf"}
+METRIC = {"l2_squared": "L2Squared", "l1": "L1", "lpinf": "LPInf", "lninf": "LNInf", "so2": "SO2",
+          "se2_squared": "SE2Squared"}
 RULE = {"sliding_midpoint": "SlidingMidpointMaxSide", "midpoint": "MidpointMaxSide", "median": "MedianMaxSide"}
 
 
@@ -61,6 +62,8 @@ def test_fixture_build_and_search(pt, path):
         for f in ("split_dim", "begin", "end", "left", "right"):
             assert np.array_equal(got[f], want[f]), f
     assert sorted(indices.tolist()) == list(range(len(pts)))
+    if "node_outer" in g:  # topological metrics: the two extra bounds of kd_tree_branch_double
+        assert np.array_equal(t.export_outer_bounds(), g["node_outer"])
 
     k = g["knn_index"].shape[1]
     ties = 0
@@ -126,11 +129,14 @@ def test_fixture_reference_tree_uploaded(pt, oracle, path, tmp_path):
     else:
         # the reference writes its raw branch struct {int; double; double}: 4 padding bytes per
         # branch are uninitialised there, so compare the decoded content instead
-        a = oracle.parse_saved_tree(out.read_bytes()[len(header):], pts.dtype)
-        b = oracle.parse_saved_tree(f.read_bytes()[len(header):], pts.dtype)
+        topo = metric in oracle.TOPOLOGICAL
+        a = oracle.parse_saved_tree(out.read_bytes()[len(header):], pts.dtype, topo)
+        b = oracle.parse_saved_tree(f.read_bytes()[len(header):], pts.dtype, topo)
         assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
         for fld in a[3].dtype.names:
             assert np.array_equal(a[3][fld], b[3][fld])
+        if topo:
+            assert np.array_equal(a[4], b[4])
         t2 = pt.load_kd_tree(pts, str(out))
         assert np.array_equal(t2.search_knn(q, k)["index"], g["knn_index"])
 
@@ -203,6 +209,49 @@ def test_other_metrics_and_approximate(pt, oracle, metric):
     # approximate results depend on the traversal; identical trees -> identical answers
     got, want = t.search_knn(q, 3, 1.7), o.search_knn(q, 3, e=1.7)
     assert np.array_equal(got["distance"], want["distance"]) and np.array_equal(got["index"], want["index"])
+
+
+@pytest.mark.parametrize("metric,sdim,dtype", [("so2", 1, np.float32), ("se2_squared", 3, np.float32),
+                                               ("se2_squared", 3, np.float64)])
+def test_topological_metrics(pt, oracle, metric, sdim, dtype):
+    """search_nearest_topological (kd_tree_search.hpp:122-229) and the wrapped box search on device:
+    circle S1 = [0, 1) and R2 x S1, against the oracle (itself pinned to the reference's fixtures)."""
+    rng = np.random.default_rng(17)
+    pts = rng.random((60_000, sdim)).astype(dtype)
+    q = rng.random((8_000, sdim)).astype(dtype)
+    q[:50] = pts[:50]
+    q[50:60, -1] = dtype(0.0)
+    q[60:70, -1] = np.nextafter(dtype(1.0), dtype(0.0))
+    o = oracle.OracleTree(pts, 10, metric=metric)
+    t = make_tree(pt, pts, metric)
+    nodes, indices, box = t.export()
+    assert_same_structure(nodes_from_export(nodes, pts.dtype), o.nodes)
+    assert np.array_equal(t.export_outer_bounds(), o.outer_bounds)
+    assert leaf_sets_equal(o.nodes, indices, o.indices)
+    for kw in ({}, {"warp_per_query": True}):
+        for k in (1, 8, 20):
+            assert_knn_parity(t.search_knn(q, k, **kw), o.search_knn(q, k), pts, q, metric)
+        got, want = t.search_knn(q, 4, 1.8, **kw), o.search_knn(q, 4, e=1.8)
+        assert_knn_parity(got, want, pts, q, metric, e=1.8)
+        r = 0.002 if metric == "so2" else 0.001
+        nns = t.search_radius(q, r, **kw)
+        offs, flat = o.search_radius(q, r)
+        assert_radius_parity(nns._offsets, nns._flat[:len(flat)], offs, flat, ordered=False)
+    mins = (q[:3000] - dtype(0.03)).astype(dtype)
+    maxs = (q[:3000] + dtype(0.02)).astype(dtype)
+    s1 = slice(0, None) if metric == "so2" else slice(2, None)
+    mins[:, s1] = np.mod(mins[:, s1], 1)
+    maxs[:, s1] = np.mod(maxs[:, s1], 1)
+    assert np.any(mins[:, -1] > maxs[:, -1])  # some boxes wrap around the circle
+    boxes = np.empty((2 * len(mins), sdim), dtype)
+    boxes[0::2], boxes[1::2] = mins, maxs
+    res = t.search_box(boxes)
+    offs, flat = o.search_box(mins, maxs)
+    assert np.array_equal(res._offsets, offs)
+    for a, b in zip(split_ragged(res._offsets, res._flat), split_ragged(offs, flat)):
+        assert np.array_equal(np.sort(a), np.sort(b))
+    with pytest.raises(pt._lib.PicoB200Error):
+        pt.KdTree(np.zeros((10, 2), dtype), pt.Metric.SO2, 10)
 
 
 def test_high_dim_runtime_path(pt, oracle):

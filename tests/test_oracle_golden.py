@@ -73,6 +73,24 @@ def test_metric_kat(oracle, metric, want, want1):
     assert np.isclose(d, want1, rtol=1e-6)
 
 
+def test_topological_metric_kats(oracle):
+    # metric_test.cpp:66-90: SO2 distance(0.5, 0.6) = 0.1; SE2Squared = 73 + 0.01; metric(-0.1)
+    t = oracle.OracleTree(np.array([[0.6]], np.float32), 1, metric="so2")
+    d = t.search_knn(np.array([[0.5]], np.float32), 1)["distance"][0, 0]
+    assert np.isclose(d, 0.1, rtol=1e-6)
+    # wrap-around: 0.95 and 0.05 are 0.1 apart on the circle (distance_test.cpp / segment_test.cpp:25-51)
+    t = oracle.OracleTree(np.array([[0.95]], np.float32), 1, metric="so2")
+    assert np.isclose(t.search_knn(np.array([[0.05]], np.float32), 1)["distance"][0, 0], 0.1, rtol=1e-5)
+    t = oracle.OracleTree(np.array([[10.0, 1.0, 0.6]], np.float32), 1, metric="se2_squared")
+    d = t.search_knn(np.array([[2.0, 4.0, 0.5]], np.float32), 1)["distance"][0, 0]
+    assert np.isclose(d, 73.0 + 0.01, rtol=1e-6)
+    # segment_s1 box distances steer the descent: a query next to 0 must find the point next to 1
+    pts = np.linspace(0.0, 0.999, 400, dtype=np.float32).reshape(-1, 1)
+    t = oracle.OracleTree(pts, 4, metric="so2")
+    nn = t.search_knn(np.array([[0.9995]], np.float32), 2)
+    assert set(nn["index"][0].tolist()) == {399, 0}
+
+
 def test_python_three_point_cases(oracle):
     # kd_tree_test.py:53-69 (knn), :90-118 (radius), :151-192 (box counts [1, 0, 3, 1])
     a = np.array([[2, 1], [4, 3], [8, 7]], np.float32)
@@ -96,7 +114,7 @@ def _golden_files():
 
 
 def test_golden_fixtures_present():
-    assert len(_golden_files()) >= 10
+    assert len(_golden_files()) >= 14
 
 
 @pytest.mark.parametrize("path", _golden_files(), ids=lambda p: os.path.basename(p)[:-4])
@@ -111,6 +129,8 @@ def test_oracle_matches_reference_fixture(oracle, path):
     assert len(nodes) == len(g["node_split_dim"])
     for f in GOLDEN_NODE_FIELDS:
         assert np.array_equal(nodes[f], g["node_" + f]), f
+    if "node_outer" in g:  # topological: left_min / right_max of kd_tree_branch_double
+        assert np.array_equal(t.outer_bounds, g["node_outer"])
     k = g["knn_index"].shape[1]
     for name, kk, e in (("nn", 1, 0.0), ("knn", k, 0.0), ("aknn", k, 1.5)):
         r = t.search_knn(q, kk, e=e)
