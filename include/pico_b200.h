@@ -183,7 +183,9 @@ int pico_b200_knn(const pico_b200_tree* tree, const void* queries, size_t nq, si
 /*
  * All neighbours with distance < radius (strict), ragged: offsets_out[nq+1] and one
  * malloc'd array of neighbour records (free with pico_b200_free). Visit order unless
- * PICO_B200_SORT_RESULTS. Replaces kd_tree::search_radius (kd_tree.hpp:256-290) with
+ * PICO_B200_SORT_RESULTS. With PICO_B200_DEVICE_POINTERS `queries` and `offsets_out` are device
+ * pointers and *neighbors_out receives a device buffer (pico_b200_free_device): results stay in
+ * HBM for a consumer kernel. Replaces kd_tree::search_radius (kd_tree.hpp:256-290) with
  * the search_radius / search_approximate_radius visitors
  * (internal/search_visitor.hpp:126-156,253-288) and the binding loop
  * (_pyco_tree/kd_tree.hpp:170-238).
@@ -251,6 +253,8 @@ int pico_b200_profile_begin(void);
 int pico_b200_profile_end(double* traversal_ms, uint64_t* traversal_launches);
 
 void pico_b200_free(void* p);
+/* frees a device buffer returned by pico_b200_radius / pico_b200_box under PICO_B200_DEVICE_POINTERS */
+void pico_b200_free_device(void* p);
 
 #ifdef __cplusplus
 }

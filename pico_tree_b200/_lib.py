@@ -24,6 +24,7 @@ EXPORTS = [
     "pico_b200_tree_export_outer_bounds",
     "pico_b200_knn", "pico_b200_radius", "pico_b200_box", "pico_b200_tree_broadcast",
     "pico_b200_tree_serialize_size", "pico_b200_tree_serialize", "pico_b200_tree_deserialize", "pico_b200_free",
+    "pico_b200_free_device",
     "pico_b200_tree_save_size", "pico_b200_tree_save", "pico_b200_tree_load", "pico_b200_set_stream",
     "pico_b200_profile_begin", "pico_b200_profile_end",
 ]
@@ -81,6 +82,8 @@ def lib():
     L.pico_b200_tree_deserialize.argtypes = [vp, C.c_uint64, i32, i32, C.POINTER(vp)]
     L.pico_b200_free.argtypes = [vp]
     L.pico_b200_free.restype = None
+    L.pico_b200_free_device.argtypes = [vp]
+    L.pico_b200_free_device.restype = None
     L.pico_b200_tree_save_size.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.pico_b200_tree_save.argtypes = [vp, vp]
     L.pico_b200_tree_load.argtypes = [vp, sz, sz, sz, i32, i32, vp, C.c_uint64, i32, C.POINTER(vp),

@@ -262,6 +262,9 @@ int pico_b200_box(const pico_b200_tree* t, const void* mins, const void* maxs, s
 }
 
 void pico_b200_free(void* p) { free(p); }
+void pico_b200_free_device(void* p) {
+  if (p) cudaFree(p);
+}
 
 int pico_b200_set_stream(void* cuda_stream) { return set_thread_stream(cuda_stream, cuda_stream != nullptr); }
 int pico_b200_profile_begin(void) { return profile_begin(); }

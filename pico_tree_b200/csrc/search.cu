@@ -11,6 +11,9 @@
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <cstring>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 #include "traverse_warp.cuh"
@@ -354,6 +357,71 @@ struct CallCtx {
       if (e) cudaEventDestroy(e);
   }
 };
+
+
+// ------------------------------------------------------------------ big results: device -> pageable host
+// Ragged radius / box results can be gigabytes (cfg3: 760 M neighbours = 6 GB) and land in fresh
+// malloc'd memory. A plain cudaMemcpy into pageable memory runs at ~2 GB/s. Instead the device
+// streams chunks into two pinned staging buffers while host threads move the previous chunk to its
+// destination (that copy is page-fault bound, hence several threads).
+constexpr size_t kStageBytes = (size_t)64 << 20;
+
+struct Staging {
+  std::mutex mu;
+  void* buf[2] = {nullptr, nullptr};
+};
+Staging g_staging;
+
+void parallel_memcpy(char* dst, const char* src, size_t bytes) {
+  unsigned nt = std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+  if (bytes < ((size_t)4 << 20)) nt = 1;
+  const size_t per = (bytes / nt + 4095) & ~(size_t)4095;
+  std::vector<std::thread> th;
+  for (unsigned i = 1; i < nt; ++i) {
+    const size_t off = std::min(bytes, i * per), len = std::min(bytes, (i + 1) * per) - off;
+    if (len) th.emplace_back([=] { memcpy(dst + off, src + off, len); });
+  }
+  memcpy(dst, src, std::min(bytes, per));
+  for (auto& t : th) t.join();
+}
+
+int copy_out(cudaStream_t st, void* h_dst, const void* d_src, size_t bytes) {
+  if (bytes <= ((size_t)8 << 20)) {
+    PICO_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, st));
+    PICO_CUDA(cudaStreamSynchronize(st));
+    return 0;
+  }
+  std::lock_guard<std::mutex> lock(g_staging.mu);
+  for (auto& b : g_staging.buf)
+    if (!b) PICO_CUDA(cudaHostAlloc(&b, kStageBytes, cudaHostAllocDefault));
+  cudaEvent_t ev[2];
+  PICO_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+  PICO_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+  char* dst = static_cast<char*>(h_dst);
+  const char* src = static_cast<const char*>(d_src);
+  size_t prev_off = 0, prev_len = 0;
+  int rc = 0;
+  int slot = 0;
+  for (size_t off = 0; off < bytes && !rc; off += kStageBytes, slot ^= 1) {
+    const size_t len = std::min(kStageBytes, bytes - off);
+    if (cudaMemcpyAsync(g_staging.buf[slot], src + off, len, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaEventRecord(ev[slot], st) != cudaSuccess)
+      rc = fail(PICO_B200_ERR_CUDA, "staged device-to-host copy failed");
+    if (prev_len && !rc) {
+      if (cudaEventSynchronize(ev[slot ^ 1]) != cudaSuccess) rc = fail(PICO_B200_ERR_CUDA, "staged copy sync failed");
+      if (!rc) parallel_memcpy(dst + prev_off, static_cast<const char*>(g_staging.buf[slot ^ 1]), prev_len);
+    }
+    prev_off = off;
+    prev_len = len;
+  }
+  if (!rc && prev_len) {
+    if (cudaEventSynchronize(ev[slot ^ 1]) != cudaSuccess) rc = fail(PICO_B200_ERR_CUDA, "staged copy sync failed");
+    if (!rc) parallel_memcpy(dst + prev_off, static_cast<const char*>(g_staging.buf[slot ^ 1]), prev_len);
+  }
+  cudaEventDestroy(ev[0]);
+  cudaEventDestroy(ev[1]);
+  return rc;
+}
 
 template <typename T>
 int stage_queries(CallCtx& c, const T* q, size_t nq, size_t stride, size_t sdim, bool on_device, const T** d_q,
@@ -770,16 +838,22 @@ int radius_batch(const pico_b200_tree* t, const T* q, size_t nq, size_t stride, 
                  uint64_t* offsets_out, void** out, unsigned flags, pico_b200_search_stats* stats) {
   *out = nullptr;
   if (nq > 0xfffffff0u) return fail(PICO_B200_ERR_UNSUPPORTED, "more than 2^32-16 queries in one call");
+  // PICO_B200_DEVICE_POINTERS: queries and offsets_out are device pointers and *out receives a device
+  // buffer (pico_b200_free_device); the call still synchronises once to learn the total.
   const bool on_device = flags & PICO_B200_DEVICE_POINTERS;
-  if (on_device) return fail(PICO_B200_ERR_UNSUPPORTED, "radius search returns host buffers; pass host pointers");
-  offsets_out[0] = 0;
-  if (nq == 0) return 0;
   CallCtx c;
   PICO_TRY(c.init(t->device));
+  if (nq == 0) {
+    if (on_device)
+      PICO_CUDA(cudaMemsetAsync(offsets_out, 0, 8, c.st));
+    else
+      offsets_out[0] = 0;
+    return 0;
+  }
   PICO_CUDA(cudaEventRecord(c.ev[0], c.st));
   const T* d_q = nullptr;
   size_t d_stride = 0;
-  PICO_TRY(stage_queries(c, q, nq, stride, t->sdim, false, &d_q, &d_stride));
+  PICO_TRY(stage_queries(c, q, nq, stride, t->sdim, on_device, &d_q, &d_stride));
   PICO_CUDA(cudaEventRecord(c.ev[1], c.st));
   uint32_t* perm = nullptr;
   PICO_TRY(make_perm(c, t, d_q, d_stride, nq, flags, &perm));
@@ -797,38 +871,54 @@ int radius_batch(const pico_b200_tree* t, const T* q, size_t nq, size_t stride, 
   PICO_TRY(c.span_end());
   uint64_t* d_offsets = nullptr;
   PICO_TRY(scan_counts(c, r.counts, nq, &d_offsets));
-  PICO_CUDA(cudaMemcpyAsync(offsets_out, d_offsets, (nq + 1) * 8, cudaMemcpyDeviceToHost, c.st));
+  uint64_t total64 = 0;
+  if (on_device) {
+    PICO_CUDA(cudaMemcpyAsync(offsets_out, d_offsets, (nq + 1) * 8, cudaMemcpyDeviceToDevice, c.st));
+    PICO_CUDA(cudaMemcpyAsync(&total64, d_offsets + nq, 8, cudaMemcpyDeviceToHost, c.st));
+  } else {
+    PICO_CUDA(cudaMemcpyAsync(offsets_out, d_offsets, (nq + 1) * 8, cudaMemcpyDeviceToHost, c.st));
+  }
   PICO_CUDA(cudaStreamSynchronize(c.st));
-  const size_t total = offsets_out[nq];
-  Neighbor<T>* h_hits = static_cast<Neighbor<T>*>(malloc((total ? total : 1) * sizeof(Neighbor<T>)));
-  if (!h_hits) return fail(PICO_B200_ERR_OUT_OF_MEMORY, "host allocation of radius results failed");
+  const size_t total = on_device ? (size_t)total64 : (size_t)offsets_out[nq];
+  const size_t bytes = (total ? total : 1) * sizeof(Neighbor<T>);
+  Neighbor<T>* h_hits = nullptr;
+  Neighbor<T>* d_hits = nullptr;
+  if (on_device) {
+    PICO_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_hits), bytes));
+  } else {
+    h_hits = static_cast<Neighbor<T>*>(malloc(bytes));
+    if (!h_hits) return fail(PICO_B200_ERR_OUT_OF_MEMORY, "host allocation of radius results failed");
+  }
+  auto give_up = [&](int rc) {
+    free(h_hits);
+    if (on_device) cudaFree(d_hits);
+    return rc;
+  };
   if (total) {
-    Neighbor<T>* d_hits = nullptr;
-    int rc = c.alloc(reinterpret_cast<void**>(&d_hits), total * sizeof(Neighbor<T>));
-    if (rc) {
-      free(h_hits);
-      return rc;
+    if (!on_device) {
+      int rc = c.alloc(reinterpret_cast<void**>(&d_hits), bytes);
+      if (rc) return give_up(rc);
     }
-    if (sizeof(T) == 8) cudaMemsetAsync(d_hits, 0, total * sizeof(Neighbor<T>), c.st);  // defined padding
+    if (sizeof(T) == 8) cudaMemsetAsync(d_hits, 0, bytes, c.st);  // defined padding
     r.offsets = d_offsets;
     r.hits = d_hits;
     r.base.ws = nullptr;
-    rc = c.span_begin();
+    int rc = c.span_begin();
     if (!rc) rc = launch_radius<T, true>(c, t, r, flags);
     if (!rc) rc = c.span_end();
     if (!rc && (flags & PICO_B200_SORT_RESULTS)) rc = sort_hits(c, d_hits, total, d_offsets, nq);
-    if (rc) {
-      free(h_hits);
-      return rc;
-    }
+    if (rc) return give_up(rc);
     PICO_CUDA(cudaEventRecord(c.ev[3], c.st));
-    PICO_CUDA(cudaMemcpyAsync(h_hits, d_hits, total * sizeof(Neighbor<T>), cudaMemcpyDeviceToHost, c.st));
+    if (!on_device) {
+      rc = copy_out(c.st, h_hits, d_hits, total * sizeof(Neighbor<T>));
+      if (rc) return give_up(rc);
+    }
   } else {
     PICO_CUDA(cudaEventRecord(c.ev[3], c.st));
   }
   PICO_CUDA(cudaEventRecord(c.ev[4], c.st));
   PICO_CUDA(cudaStreamSynchronize(c.st));
-  *out = h_hits;
+  *out = on_device ? static_cast<void*>(d_hits) : static_cast<void*>(h_hits);
   if (stats) {
     stats->h2d_ms = elapsed(c.ev[0], c.ev[1]);
     stats->reorder_ms = elapsed(c.ev[1], c.ev[2]);
@@ -845,17 +935,21 @@ int box_batch(const pico_b200_tree* t, const T* mins, const T* maxs, size_t nb, 
               int32_t** out, unsigned flags, pico_b200_search_stats* stats) {
   *out = nullptr;
   if (nb > 0xfffffff0u) return fail(PICO_B200_ERR_UNSUPPORTED, "more than 2^32-16 boxes in one call");
-  if (flags & PICO_B200_DEVICE_POINTERS)
-    return fail(PICO_B200_ERR_UNSUPPORTED, "box search returns host buffers; pass host pointers");
-  offsets_out[0] = 0;
-  if (nb == 0) return 0;
+  const bool on_device = flags & PICO_B200_DEVICE_POINTERS;  // same convention as radius_batch
   CallCtx c;
   PICO_TRY(c.init(t->device));
+  if (nb == 0) {
+    if (on_device)
+      PICO_CUDA(cudaMemsetAsync(offsets_out, 0, 8, c.st));
+    else
+      offsets_out[0] = 0;
+    return 0;
+  }
   PICO_CUDA(cudaEventRecord(c.ev[0], c.st));
   const T *d_min = nullptr, *d_max = nullptr;
   size_t d_stride = 0;
-  PICO_TRY(stage_queries(c, mins, nb, stride, t->sdim, false, &d_min, &d_stride));
-  PICO_TRY(stage_queries(c, maxs, nb, stride, t->sdim, false, &d_max, &d_stride));
+  PICO_TRY(stage_queries(c, mins, nb, stride, t->sdim, on_device, &d_min, &d_stride));
+  PICO_TRY(stage_queries(c, maxs, nb, stride, t->sdim, on_device, &d_max, &d_stride));
   PICO_CUDA(cudaEventRecord(c.ev[1], c.st));
   PICO_CUDA(cudaEventRecord(c.ev[2], c.st));
 
@@ -894,31 +988,48 @@ int box_batch(const pico_b200_tree* t, const T* mins, const T* maxs, size_t nb, 
   PICO_TRY(launch());
   uint64_t* d_offsets = nullptr;
   PICO_TRY(scan_counts(c, a.counts, nb, &d_offsets));
-  PICO_CUDA(cudaMemcpyAsync(offsets_out, d_offsets, (nb + 1) * 8, cudaMemcpyDeviceToHost, c.st));
+  uint64_t total64 = 0;
+  if (on_device) {
+    PICO_CUDA(cudaMemcpyAsync(offsets_out, d_offsets, (nb + 1) * 8, cudaMemcpyDeviceToDevice, c.st));
+    PICO_CUDA(cudaMemcpyAsync(&total64, d_offsets + nb, 8, cudaMemcpyDeviceToHost, c.st));
+  } else {
+    PICO_CUDA(cudaMemcpyAsync(offsets_out, d_offsets, (nb + 1) * 8, cudaMemcpyDeviceToHost, c.st));
+  }
   PICO_CUDA(cudaStreamSynchronize(c.st));
-  const size_t total = offsets_out[nb];
-  int32_t* h_hits = static_cast<int32_t*>(malloc((total ? total : 1) * sizeof(int32_t)));
-  if (!h_hits) return fail(PICO_B200_ERR_OUT_OF_MEMORY, "host allocation of box results failed");
+  const size_t total = on_device ? (size_t)total64 : (size_t)offsets_out[nb];
+  const size_t bytes = (total ? total : 1) * sizeof(int32_t);
+  int32_t* h_hits = nullptr;
+  int32_t* d_hits = nullptr;
+  if (on_device) {
+    PICO_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_hits), bytes));
+  } else {
+    h_hits = static_cast<int32_t*>(malloc(bytes));
+    if (!h_hits) return fail(PICO_B200_ERR_OUT_OF_MEMORY, "host allocation of box results failed");
+  }
+  auto give_up = [&](int rc) {
+    free(h_hits);
+    if (on_device) cudaFree(d_hits);
+    return rc;
+  };
   if (total) {
-    int32_t* d_hits = nullptr;
-    int rc = c.alloc(reinterpret_cast<void**>(&d_hits), total * sizeof(int32_t));
+    int rc = on_device ? 0 : c.alloc(reinterpret_cast<void**>(&d_hits), bytes);
     if (!rc) {
       a.offsets = d_offsets;
       a.hits = d_hits;
       rc = launch();
     }
-    if (rc) {
-      free(h_hits);
-      return rc;
-    }
+    if (rc) return give_up(rc);
     PICO_CUDA(cudaEventRecord(c.ev[3], c.st));
-    PICO_CUDA(cudaMemcpyAsync(h_hits, d_hits, total * sizeof(int32_t), cudaMemcpyDeviceToHost, c.st));
+    if (!on_device) {
+      rc = copy_out(c.st, h_hits, d_hits, total * sizeof(int32_t));
+      if (rc) return give_up(rc);
+    }
   } else {
     PICO_CUDA(cudaEventRecord(c.ev[3], c.st));
   }
   PICO_CUDA(cudaEventRecord(c.ev[4], c.st));
   PICO_CUDA(cudaStreamSynchronize(c.st));
-  *out = h_hits;
+  *out = on_device ? d_hits : h_hits;
   if (stats) {
     stats->h2d_ms = elapsed(c.ev[0], c.ev[1]);
     stats->reorder_ms = 0;

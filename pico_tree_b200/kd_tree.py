@@ -9,6 +9,7 @@ libpico_b200.so. Nothing here computes distances or walks a tree.
 import ctypes as C
 import enum
 import struct
+import weakref
 
 import numpy as np
 
@@ -344,14 +345,15 @@ class KdTree:
 
     @staticmethod
     def _take(p, count, dtype):
+        """Wrap a buffer handed out by the library as an ndarray WITHOUT copying (results can be
+        gigabytes); the buffer is freed when the last view of it dies."""
         if count:
             buf = (C.c_char * (count * dtype.itemsize)).from_address(p.value)
-            out = np.frombuffer(buf, dtype=dtype).copy()
-        else:
-            out = np.empty(0, dtype=dtype)
+            weakref.finalize(buf, _lib.lib().pico_b200_free, C.c_void_p(p.value))
+            return np.frombuffer(buf, dtype=dtype)
         if p.value:
             _lib.lib().pico_b200_free(p)
-        return out
+        return np.empty(0, dtype=dtype)
 
     # ------------------------------------------------------------------ (de)serialisation
     def _saved_stream(self):

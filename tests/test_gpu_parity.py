@@ -373,6 +373,48 @@ def test_deep_tree_uses_global_stack(pt, oracle):
     assert_radius_parity(nns._offsets, nns._flat[:len(flat)], offs, flat, ordered=False)
 
 
+def test_device_resident_ragged_results(pt):
+    """PICO_B200_DEVICE_POINTERS for radius / box: queries, offsets and hits stay in HBM; the bytes must
+    equal what the host-buffer path returns."""
+    import ctypes as C
+    import torch
+    from pico_tree_b200 import _lib, datasets as D
+    L = _lib.lib()
+    pts = D.uniform(80_000, 3, seed=3)
+    q = D.uniform(20_000, 3, seed=4)
+    t = pt.KdTree(pts, pt.Metric.L2Squared, 10)
+    want = t.search_radius(q, 0.0008, True)
+    dev = torch.device("cuda", 0)
+    qd = torch.from_numpy(q).to(dev)
+    offs = torch.empty(len(q) + 1, dtype=torch.int64, device=dev)
+    hits = C.c_void_p()
+    _lib.check(L.pico_b200_radius(t._h, C.c_void_p(qd.data_ptr()), len(q), 3, 0.0008, 0.0, C.c_void_p(offs.data_ptr()),
+                                  C.byref(hits), _lib.FLAG_DEVICE_POINTERS | _lib.FLAG_SORT_RESULTS, None))
+    offs_h = offs.cpu().numpy().astype(np.uint64)
+    assert np.array_equal(offs_h, want._offsets)
+    total = int(offs_h[-1])
+    got = torch.empty(total * 2, dtype=torch.int32, device=dev)
+    C.cdll.LoadLibrary("libcudart.so.12").cudaMemcpy(C.c_void_p(got.data_ptr()), hits, C.c_size_t(total * 8), C.c_int(3))
+    L.pico_b200_free_device(hits)
+    got = got.cpu().numpy().view(t.dtype_neighbor)
+    assert np.array_equal(got["distance"], want._flat["distance"][:total])
+    boxes_min = torch.from_numpy(np.ascontiguousarray(q[:4000] - np.float32(0.02))).to(dev)
+    boxes_max = torch.from_numpy(np.ascontiguousarray(q[:4000] + np.float32(0.02))).to(dev)
+    boffs = torch.empty(4001, dtype=torch.int64, device=dev)
+    bhits = C.c_void_p()
+    _lib.check(L.pico_b200_box(t._h, C.c_void_p(boxes_min.data_ptr()), C.c_void_p(boxes_max.data_ptr()), 4000, 3,
+                               C.c_void_p(boffs.data_ptr()), C.byref(bhits), _lib.FLAG_DEVICE_POINTERS, None))
+    both = np.empty((8000, 3), np.float32)
+    both[0::2], both[1::2] = boxes_min.cpu().numpy(), boxes_max.cpu().numpy()
+    wantb = t.search_box(both)
+    assert np.array_equal(boffs.cpu().numpy().astype(np.uint64), wantb._offsets)
+    nb = int(wantb._offsets[-1])
+    gotb = torch.empty(nb, dtype=torch.int32, device=dev)
+    C.cdll.LoadLibrary("libcudart.so.12").cudaMemcpy(C.c_void_p(gotb.data_ptr()), bhits, C.c_size_t(nb * 4), C.c_int(3))
+    L.pico_b200_free_device(bhits)
+    assert np.array_equal(gotb.cpu().numpy(), wantb._flat[:nb])
+
+
 def test_build_paths_agree(pt, monkeypatch):
     """The three ways a node can be split on the device — one warp, one CTA, grid-wide chunked passes
     (build.cu, PICO_B200_HUGE_MIN is the test hook for the threshold) — must leave the very same
