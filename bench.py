@@ -295,36 +295,36 @@ def run_ours(args, n_tree, n_query):
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except (OSError, ValueError):
         pass
-    if world == 1 and not args.no_cpu_baseline:
+    if not args.no_cpu_baseline:
         from oracle import oracle as O
-        ref_tree, kind = cpu_reference_tree(tree_pts)
-        threads = O.max_threads()
-        t0 = time.perf_counter()
-        ref_all = ref_tree.search_knn(q_host, k, threads=threads)
-        all_s = time.perf_counter() - t0
-        one_n = min(n_query, 500_000)
-        t0 = time.perf_counter()
-        ref_tree.search_knn(np.ascontiguousarray(q_host[:one_n]), k, threads=1)
-        one_s = time.perf_counter() - t0
-        cpu = {"value": n_query / all_s / 1e6, "unit": UNIT, "cores": threads, "kind": kind,
-               "sample": "all %d queries once on %d threads (OpenMP dynamic,128); single thread: first %d queries "
-                         "-> %.3f Mq/s" % (n_query, threads, one_n, one_n / one_s / 1e6),
-               "single_thread_value": one_n / one_s / 1e6}
-        # parity of the benchmarked run itself against the CPU reference (full size)
-        got = res_dev.reshape(n_query, k, 2)
-        same_d = np.array_equal(got[..., 1].view(np.float32), ref_all["distance"])
-        idx_diff = int(np.count_nonzero(got[..., 0] != ref_all["index"]))
-        cpu["parity_vs_this_run"] = {"distances_bit_equal": bool(same_d), "index_mismatches": idx_diff,
-                                     "queries": n_query}
-        # counters from the oracle's instrumented reference traversal (sample)
+        if world == 1:
+            ref_tree, kind = cpu_reference_tree(tree_pts)
+            threads = O.max_threads()
+            t0 = time.perf_counter()
+            ref_all = ref_tree.search_knn(q_host, k, threads=threads)
+            all_s = time.perf_counter() - t0
+            one_n = min(n_query, 500_000)
+            t0 = time.perf_counter()
+            ref_tree.search_knn(np.ascontiguousarray(q_host[:one_n]), k, threads=1)
+            one_s = time.perf_counter() - t0
+            cpu = {"value": n_query / all_s / 1e6, "unit": UNIT, "cores": threads, "kind": kind,
+                   "sample": "all %d queries once on %d threads (OpenMP dynamic,128); single thread: first %d "
+                             "queries -> %.3f Mq/s" % (n_query, threads, one_n, one_n / one_s / 1e6),
+                   "single_thread_value": one_n / one_s / 1e6}
+            # parity of the benchmarked run itself against the CPU reference (full size)
+            got = res_dev.reshape(n_query, k, 2)
+            same_d = np.array_equal(got[..., 1].view(np.float32), ref_all["distance"])
+            idx_diff = int(np.count_nonzero(got[..., 0] != ref_all["index"]))
+            cpu["parity_vs_this_run"] = {"distances_bit_equal": bool(same_d), "index_mismatches": idx_diff,
+                                         "queries": n_query}
+        # algorithmic bytes: counters from the oracle's instrumented reference traversal (sample of
+        # rank 0's queries; every N, the roofline describes the kernel, not the host)
         oc = O.OracleTree(tree_pts, 10)
         cs = min(n_query, 400_000)
         sel = np.ascontiguousarray(q_host[:: max(n_query // cs, 1)][:cs])
-        _, cnt = oc.search_knn(sel, k, counters=True)
+        _, cnt = oc.search_knn(sel, k, counters=True, threads=O.max_threads())
         counters = (cnt / len(sel)).tolist()
         bytes_per_query = 4 * 3 + 8 * k + counters[0] * 16 + counters[2] * 16
-    elif world == 1:
-        bytes_per_query = None
 
     peak = peaks.get("hbm_gbs")
     peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)"

@@ -115,13 +115,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock) knn_thread_kernel(KnnArgs<T>
         LocalStack<T, DIM, kLocalStack> st;
         traverse_packed<T, DIM, FAST, false>(a.nodes, a.pts4, a.outer, q, a.metric, a.approx != 0, a.e_inv, st, vis);
       }
-#pragma unroll
-      for (int i = 0; i < KMAX; ++i) {
-        if (i < a.k) {
-          out[i].index = vis.id[i];
-          out[i].distance = vis.d[i];
-        }
-      }
+      vis.store(out);
     }
   }
 }
@@ -301,11 +295,27 @@ struct ThreadCfg {
 };
 thread_local ThreadCfg g_cfg;
 
+// Streams and events are recycled per host thread: creating a stream plus five events costs tens of
+// microseconds, which is visible next to a 0.1 ms batch.
+struct StreamSet {
+  int device = -1;
+  cudaStream_t st = nullptr;
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+struct StreamCache {
+  std::vector<StreamSet> free_sets;
+  ~StreamCache() {
+    // the CUDA context may already be gone at thread exit; leak instead of calling into it
+  }
+};
+thread_local StreamCache g_stream_cache;
+
 struct CallCtx {
   cudaStream_t st = nullptr;
   bool owns_stream = true;
   bool async = false;
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  int dev = -1;
   std::vector<void*> async_allocs;
   int init(int device, bool want_async = false) {
     PICO_CUDA(cudaSetDevice(device));
@@ -313,11 +323,22 @@ struct CallCtx {
       st = g_cfg.user_stream;
       owns_stream = false;
       async = want_async;
-    } else {
-      PICO_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+      if (!async)
+        for (auto& e : ev) PICO_CUDA(cudaEventCreate(&e));
+      return 0;
     }
-    if (!async)
-      for (auto& e : ev) PICO_CUDA(cudaEventCreate(&e));
+    dev = device;
+    auto& fs = g_stream_cache.free_sets;
+    for (size_t i = 0; i < fs.size(); ++i) {
+      if (fs[i].device == device) {
+        st = fs[i].st;
+        for (int j = 0; j < 5; ++j) ev[j] = fs[i].ev[j];
+        fs.erase(fs.begin() + (long)i);
+        return 0;
+      }
+    }
+    PICO_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    for (auto& e : ev) PICO_CUDA(cudaEventCreate(&e));
     return 0;
   }
   int mark(int i) {
@@ -352,9 +373,16 @@ struct CallCtx {
   ~CallCtx() {
     for (void* p : async_allocs) cudaFreeAsync(p, st);
     if (!async && (st || !owns_stream)) cudaStreamSynchronize(st);
-    if (owns_stream && st) cudaStreamDestroy(st);
-    for (auto& e : ev)
-      if (e) cudaEventDestroy(e);
+    if (owns_stream && st) {
+      StreamSet s;
+      s.device = dev;
+      s.st = st;
+      for (int j = 0; j < 5; ++j) s.ev[j] = ev[j];
+      g_stream_cache.free_sets.push_back(s);
+    } else {
+      for (auto& e : ev)
+        if (e) cudaEventDestroy(e);
+    }
   }
 };
 
@@ -637,7 +665,26 @@ int knn_enqueue(CallCtx& c, const pico_b200_tree* t, const T* q, size_t nq, size
 }
 
 constexpr size_t kHostChunk = (size_t)1 << 20;  // queries per pipelined chunk (host buffers)
-constexpr int kHostStreams = 3;
+constexpr int kHostStreams = 6;  // profiles/r1/e2e_sweep.txt: 1 Mi queries x 6 streams is the best point
+constexpr int kMaxHostStreams = 8;
+
+// tuning hooks (profiles/r1/e2e_sweep.txt): PICO_B200_HOST_CHUNK, PICO_B200_HOST_STREAMS
+size_t host_chunk() {
+  static const size_t v = [] {
+    const char* e = getenv("PICO_B200_HOST_CHUNK");
+    const long long x = e ? atoll(e) : 0;
+    return x >= 65536 ? (size_t)x : kHostChunk;
+  }();
+  return v;
+}
+int host_streams() {
+  static const int v = [] {
+    const char* e = getenv("PICO_B200_HOST_STREAMS");
+    const int x = e ? atoi(e) : 0;
+    return (x >= 1 && x <= kMaxHostStreams) ? x : kHostStreams;
+  }();
+  return v;
+}
 
 }  // namespace
 
@@ -654,21 +701,24 @@ int knn_batch(const pico_b200_tree* t, const T* q, size_t nq, size_t stride, siz
   // Host buffers, big batch, no caller stream: split into chunks that rotate over a few
   // streams so that H2D of chunk i+1, traversal of chunk i and D2H of chunk i-1 overlap
   // (PCIe is full duplex). Each chunk is Z-ordered on its own.
-  if (!on_device && !g_cfg.has_user_stream && nq >= 2 * kHostChunk) {
-    CallCtx ctx[kHostStreams];
-    for (auto& c : ctx) PICO_TRY(c.init(t->device));
+  if (!on_device && !g_cfg.has_user_stream && nq >= 2 * host_chunk()) {
+    const size_t chunk = host_chunk();
+    const int n_streams = host_streams();
+    CallCtx ctx_all[kMaxHostStreams];
+    CallCtx* ctx = ctx_all;
+    for (int i = 0; i < n_streams; ++i) PICO_TRY(ctx[i].init(t->device));
     cudaEvent_t e0, e1;
     PICO_CUDA(cudaEventCreate(&e0));
     PICO_CUDA(cudaEventCreate(&e1));
     PICO_CUDA(cudaEventRecord(e0, ctx[0].st));
     int ci = 0;
-    for (size_t begin = 0; begin < nq; begin += kHostChunk, ++ci) {
-      const size_t cnt = std::min(kHostChunk, nq - begin);
-      CallCtx& c = ctx[ci % kHostStreams];
+    for (size_t begin = 0; begin < nq; begin += chunk, ++ci) {
+      const size_t cnt = std::min(chunk, nq - begin);
+      CallCtx& c = ctx[ci % n_streams];
       c.release();
       PICO_TRY(knn_enqueue<T>(c, t, q + begin * stride, cnt, stride, k, e, out + begin * k, flags, false, &launches));
     }
-    for (auto& c : ctx) PICO_CUDA(cudaStreamSynchronize(c.st));
+    for (int i = 0; i < n_streams; ++i) PICO_CUDA(cudaStreamSynchronize(ctx[i].st));
     PICO_CUDA(cudaEventRecord(e1, ctx[0].st));
     PICO_CUDA(cudaEventSynchronize(e1));
     if (stats) {

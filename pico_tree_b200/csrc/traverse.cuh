@@ -350,27 +350,28 @@ struct VisitNn {
   }
 };
 
-// search_knn + insert_sorted, search_visitor.hpp:20-38,82-123. All KMAX slots start at
-// max(); running the insertion over KMAX >= k slots leaves the first k identical to the
-// k-slot version because acceptance is tested against slot k-1.
+// search_knn + insert_sorted, search_visitor.hpp:20-38,82-123. The k-list lives in the LAST k of
+// KMAX register slots; the slots in front of it hold a negative sentinel that no distance can
+// displace, so the insertion network is the same for every k <= KMAX and max() is always slot
+// KMAX-1 — a compile-time index. (Reading slot k-1 with a run-time k makes the compiler index the
+// array dynamically, which moves it to local memory: 6.4 GB of DRAM writes per launch at k = 16,
+// profiles/r1/knn16_v3_summary.txt.) Equal distances keep the earlier-visited neighbour first.
 template <typename T, int KMAX>
 struct VisitKnn {
   T d[KMAX];
   int id[KMAX];
-  T worst;
   int k;
   __device__ __forceinline__ void init(int k_) {
     k = k_;
-    worst = Limits<T>::max();
 #pragma unroll
     for (int i = 0; i < KMAX; ++i) {
-      d[i] = Limits<T>::max();
+      d[i] = (i < KMAX - k_) ? T(-1) : Limits<T>::max();
       id[i] = -1;
     }
   }
-  __device__ __forceinline__ T max() const { return worst; }
+  __device__ __forceinline__ T max() const { return d[KMAX - 1]; }
   __device__ __forceinline__ void visit(int i_new, T x) {
-    if (!(worst > x)) return;
+    if (!(d[KMAX - 1] > x)) return;
 #pragma unroll
     for (int i = KMAX - 1; i >= 1; --i) {
       const bool shift = d[i - 1] > x;
@@ -384,9 +385,17 @@ struct VisitKnn {
       d[0] = x;
       id[0] = i_new;
     }
+  }
+  // row = k neighbour records, ascending
+  __device__ __forceinline__ void store(Neighbor<T>* row) const {
+    Neighbor<T>* shifted = row - (KMAX - k);
 #pragma unroll
-    for (int i = 0; i < KMAX; ++i)
-      if (i == k - 1) worst = d[i];
+    for (int i = 0; i < KMAX; ++i) {
+      if (i >= KMAX - k) {
+        shifted[i].index = id[i];
+        shifted[i].distance = d[i];
+      }
+    }
   }
 };
 
