@@ -79,7 +79,7 @@ void release(pico_b200_tree* t) {
 // Serialised image: header + root box + nodes + indices + points (device layout).
 struct ImageHeader {
   uint64_t magic;  // "PICOB200"
-  uint32_t version, scalar, metric, reserved;
+  uint32_t version, scalar, metric, max_leaf_points;
   uint64_t n, sdim, n_nodes, n_leaves, height;
   double root_box_host[8];
 };
@@ -288,6 +288,7 @@ int pico_b200_tree_serialize(const pico_b200_tree* t, void* dst, int dst_is_devi
   h.version = PICO_B200_ABI_VERSION;
   h.scalar = (uint32_t)t->scalar;
   h.metric = (uint32_t)t->metric;
+  h.max_leaf_points = (uint32_t)t->max_leaf_points;
   h.n = t->n;
   h.sdim = t->sdim;
   h.n_nodes = t->n_nodes;
@@ -326,6 +327,7 @@ int pico_b200_tree_deserialize(const void* src, uint64_t bytes, int src_is_devic
   t->device = device;
   t->scalar = (int)h.scalar;
   t->metric = (int)h.metric;
+  t->max_leaf_points = h.max_leaf_points;
   t->n = h.n;
   t->sdim = h.sdim;
   t->n_nodes = h.n_nodes;

@@ -88,7 +88,7 @@ struct BuildState {
   int32_t* tmp;        // [n] scratch for the partition
   BNode<T>* nodes;     // BFS table
   T* boxes;            // [cap][2*sdim]: cut box on the way down, tight box on the way up
-  uint32_t* counters;  // [0] n_nodes  [1] n_big_next  [2] n_leaves  [3] n_huge_next  [4] chunks of this level
+  uint32_t* counters;  // [0] n_nodes  [1] n_big_next  [2] n_leaves  [3] n_huge_next  [4] chunks of this level  [5] largest leaf
   uint32_t* big_next;  // ids of next-level nodes that need a CTA
   uint32_t* huge_next; // ids of next-level nodes that need the chunked passes
   HugeNode<T>* huge;   // the current level's huge nodes
@@ -240,6 +240,7 @@ __device__ void finish_leaf(const BuildState<T>& s, BNode<T>& nd, T* box) {
     nd.split_dim = -1;
     nd.subtree = 1;
     atomicAdd(&s.counters[2], 1u);
+    atomicMax(&s.counters[5], (uint32_t)(end - begin));  // largest leaf: sizes the staged leaf tiles
   }
 }
 
@@ -1214,6 +1215,7 @@ int build_tree(pico_b200_tree* t, const T* h_pts, size_t stride, int rule, int s
   const size_t levels = level_start.size() - 1;
   t->n_nodes = n_nodes;
   t->n_leaves = h_counters[2];
+  t->max_leaf_points = h_counters[5];
   t->height = levels - 1;
 
   // --- bottom-up (tight boxes, bounds, subtree sizes), then pre-order numbers
@@ -1251,7 +1253,7 @@ int upload_tree(pico_b200_tree* t, const T* h_pts, size_t stride, const void* h_
   const int sdim = (int)t->sdim;
   const NodeT* nodes = static_cast<const NodeT*>(h_nodes);
   // validate links and measure height / leaves on the host (cheap, once)
-  size_t leaves = 0, height = 0;
+  size_t leaves = 0, height = 0, max_leaf = 0;
   {
     std::vector<std::pair<uint32_t, uint32_t>> stack;
     if (n_nodes == 0) return fail(PICO_B200_ERR_INVALID_ARGUMENT, "tree has no nodes");
@@ -1265,6 +1267,7 @@ int upload_tree(pico_b200_tree* t, const T* h_pts, size_t stride, const void* h_
       if (nodes[i].split_dim == PICO_B200_LEAF) {
         ++leaves;
         const int64_t b = nodes[i].a.begin_idx, e = nodes[i].b.end_idx;
+        if (e > b) max_leaf = std::max<size_t>(max_leaf, (size_t)(e - b));
         if (b < 0 || e < b || (size_t)e > n) return fail(PICO_B200_ERR_INVALID_ARGUMENT, "leaf range out of bounds");
       } else {
         if (nodes[i].split_dim >= (uint32_t)sdim) return fail(PICO_B200_ERR_INVALID_ARGUMENT, "split_dim >= sdim");
@@ -1277,6 +1280,7 @@ int upload_tree(pico_b200_tree* t, const T* h_pts, size_t stride, const void* h_
     if (indices[i] < 0 || (size_t)indices[i] >= n) return fail(PICO_B200_ERR_INVALID_ARGUMENT, "index out of range");
   t->n_nodes = n_nodes;
   t->n_leaves = leaves;
+  t->max_leaf_points = max_leaf;
   t->height = height;
 
   cudaStream_t st;

@@ -90,7 +90,7 @@ struct pico_b200_tree {
   int device = 0;
   int scalar = PICO_B200_F32;
   int metric = PICO_B200_METRIC_L2_SQUARED;
-  size_t n = 0, sdim = 0, n_nodes = 0, n_leaves = 0, height = 0;
+  size_t n = 0, sdim = 0, n_nodes = 0, n_leaves = 0, height = 0, max_leaf_points = 0;
   void* d_nodes = nullptr;
   void* d_pts = nullptr;       // pts4 or ptsN (see above)
   int32_t* d_indices = nullptr;

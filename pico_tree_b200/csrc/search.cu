@@ -71,6 +71,9 @@ struct KnnArgs {
   // deep-tree workspace (GlobalStack) or warp stacks
   void* ws;
   size_t ws_stride, ws_depth;
+  // warp kernels: shared memory per warp in scalars (query + offsets [+ leaf tile]) and the rows
+  // of the staged leaf tile (0 = points are read straight from global memory)
+  int warp_smem, tile_rows;
 };
 
 template <typename T, int DIM, int KMAX, bool FAST, bool DEEP>
@@ -176,8 +179,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) knn_warp_kernel(KnnArgs<T
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* smem = reinterpret_cast<T*>(smem_raw);
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  T* sq = smem + (size_t)w * 2 * a.sdim;
+  T* sq = smem + (size_t)w * a.warp_smem;
   T* so = sq + a.sdim;
+  T* tile = so + a.sdim;
+  WarpFrame<T>* win = reinterpret_cast<WarpFrame<T>*>(sq + a.warp_smem) - kStackWindow;  // tail of the warp's slice
   const size_t warp_global = (size_t)blockIdx.x * kWarpsPerBlock + w;
   const size_t total_warps = (size_t)gridDim.x * kWarpsPerBlock;
   WarpFrame<T>* stack = static_cast<WarpFrame<T>*>(a.ws) + warp_global * a.ws_depth;
@@ -195,12 +200,14 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) knn_warp_kernel(KnnArgs<T
     if (REGLIST) {
       WarpVisitKnn<T, WarpKnnReg<T>> vis;
       vis.list.init(a.k);
-      traverse_warp<T, PACKED>(a.nodes, a.outer, ps, sq, so, stack, a.metric, a.approx != 0, a.e_inv, vis);
+      traverse_warp<T, PACKED>(a.nodes, a.outer, ps, sq, so, stack, win, a.metric, a.approx != 0, a.e_inv, vis,
+                               tile, a.tile_rows);
       vis.list.store(row);
     } else {
       WarpVisitKnn<T, WarpKnnMem<T>> vis;
       vis.list.init(row, a.k);
-      traverse_warp<T, PACKED>(a.nodes, a.outer, ps, sq, so, stack, a.metric, a.approx != 0, a.e_inv, vis);
+      traverse_warp<T, PACKED>(a.nodes, a.outer, ps, sq, so, stack, win, a.metric, a.approx != 0, a.e_inv, vis,
+                               tile, a.tile_rows);
     }
   }
 }
@@ -211,8 +218,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) radius_warp_kernel(Radius
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* smem = reinterpret_cast<T*>(smem_raw);
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  T* sq = smem + (size_t)w * 2 * a.sdim;
+  T* sq = smem + (size_t)w * a.warp_smem;
   T* so = sq + a.sdim;
+  T* tile = so + a.sdim;
+  WarpFrame<T>* win = reinterpret_cast<WarpFrame<T>*>(sq + a.warp_smem) - kStackWindow;  // tail of the warp's slice
   const size_t warp_global = (size_t)blockIdx.x * kWarpsPerBlock + w;
   const size_t total_warps = (size_t)gridDim.x * kWarpsPerBlock;
   WarpFrame<T>* stack = static_cast<WarpFrame<T>*>(a.ws) + warp_global * a.ws_depth;
@@ -229,7 +238,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) radius_warp_kernel(Radius
     WarpVisitRadius<T> vis;
     vis.radius = r.radius;
     vis.out = r.hits ? r.hits + r.offsets[qi] : nullptr;
-    traverse_warp<T, PACKED>(a.nodes, a.outer, ps, sq, so, stack, a.metric, a.approx != 0, a.e_inv, vis);
+    traverse_warp<T, PACKED>(a.nodes, a.outer, ps, sq, so, stack, win, a.metric, a.approx != 0, a.e_inv, vis, tile,
+                             a.tile_rows);
     if (!r.hits && lane == 0) r.counts[qi] = vis.count;
   }
 }
@@ -471,6 +481,17 @@ int stage_queries(CallCtx& c, const T* q, size_t nq, size_t stride, size_t sdim,
   return 0;
 }
 
+// The batch is sorted on the top morton_bits() bits of the 30-bit code (stable radix sort, 8 bits per
+// pass): 24 bits = 3 passes with 8 bits per dimension. PICO_B200_MORTON_BITS is a tuning hook.
+int morton_bits() {
+  static const int v = [] {
+    const char* e = getenv("PICO_B200_MORTON_BITS");
+    const int x = e ? atoi(e) : 0;
+    return (x >= 3 && x <= 30) ? x : 24;  // profiles/r1/morton_sweep.txt
+  }();
+  return v;
+}
+
 // Z-order permutation of the batch (device). Returns nullptr in *perm for tiny batches.
 template <typename T>
 int make_perm(CallCtx& c, const pico_b200_tree* t, const T* d_q, size_t stride, size_t nq, unsigned flags,
@@ -494,10 +515,10 @@ int make_perm(CallCtx& c, const pico_b200_tree* t, const T* d_q, size_t stride, 
                                                                     make_double3(inv[0], inv[1], inv[2]), codes, ids);
   PICO_CUDA(cudaGetLastError());
   size_t tmp_bytes = 0;
-  PICO_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, codes, codes2, ids, ids2, (int)nq, 0, 30, c.st));
+  PICO_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, codes, codes2, ids, ids2, (int)nq, 30 - morton_bits(), 30, c.st));
   void* tmp = nullptr;
   PICO_TRY(c.alloc(&tmp, tmp_bytes));
-  PICO_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, codes, codes2, ids, ids2, (int)nq, 0, 30, c.st));
+  PICO_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, codes, codes2, ids, ids2, (int)nq, 30 - morton_bits(), 30, c.st));
   *perm = ids2;
   return 0;
 }
@@ -522,6 +543,31 @@ void fill_base(KnnArgs<T>& a, const pico_b200_tree* t, const T* d_q, size_t d_st
   a.e_inv = e > 0 ? T(1.0) / T(e) : T(1.0);  // search_visitor.hpp:173,216,265
   a.ws = nullptr;
   a.ws_stride = a.ws_depth = 0;
+  a.warp_smem = 2 * (int)t->sdim + (int)(kStackWindow * sizeof(WarpFrame<T>) / sizeof(T));
+  a.tile_rows = 0;
+}
+
+// Shared memory per warp of the warp-per-query kernels, in bytes; decides whether leaves are
+// staged through shared memory (row storage, 16-byte rows, the tile fits next to 8 warps' state).
+template <typename T>
+size_t plan_warp_smem(const pico_b200_tree* t, KnnArgs<T>& a) {
+  const size_t sdim = t->sdim;
+  const size_t vec = 16 / sizeof(T);
+  const size_t window = kStackWindow * sizeof(WarpFrame<T>) / sizeof(T);  // scalars; a multiple of 16 bytes
+  a.warp_smem = (int)(2 * sdim + window);
+  a.tile_rows = 0;
+  if (!t->packed() && sdim % vec == 0 && t->max_leaf_points > 0) {
+    size_t rows = std::min<size_t>(32, t->max_leaf_points);
+    // keep at least two blocks of 8 warps resident per SM (227 KB of shared memory)
+    while (rows > 4 && (2 * sdim + rows * (sdim + vec) + window) * sizeof(T) * kWarpsPerBlock > 100 * 1024)
+      rows = (rows + 1) / 2;
+    const size_t bytes = (2 * sdim + rows * (sdim + vec) + window) * sizeof(T);
+    if (bytes * kWarpsPerBlock <= 100 * 1024) {
+      a.tile_rows = (int)rows;
+      a.warp_smem = (int)(2 * sdim + rows * (sdim + vec) + window);
+    }
+  }
+  return (size_t)a.warp_smem * sizeof(T);
 }
 
 // thread-per-query launch geometry + optional deep-tree workspace
@@ -631,7 +677,7 @@ int knn_enqueue(CallCtx& c, const pico_b200_tree* t, const T* q, size_t nq, size
   } else {
     unsigned blocks;
     size_t smem;
-    PICO_TRY(warp_geometry<T>(c, t, nq, sizeof(WarpFrame<T>), 2 * t->sdim * sizeof(T), &a.ws, &a.ws_depth, &blocks,
+    PICO_TRY(warp_geometry<T>(c, t, nq, sizeof(WarpFrame<T>), plan_warp_smem<T>(t, a), &a.ws, &a.ws_depth, &blocks,
                               &smem));
     const bool reg = k <= 32;
 #define PICO_LAUNCH_WARP(P, R)                                                                                  \
@@ -866,7 +912,7 @@ int launch_radius(CallCtx& c, const pico_b200_tree* t, RadiusArgs<T>& r, unsigne
   } else {
     unsigned blocks;
     size_t smem;
-    PICO_TRY(warp_geometry<T>(c, t, a.nq, sizeof(WarpFrame<T>), 2 * t->sdim * sizeof(T), &a.ws, &a.ws_depth, &blocks,
+    PICO_TRY(warp_geometry<T>(c, t, a.nq, sizeof(WarpFrame<T>), plan_warp_smem<T>(t, a), &a.ws, &a.ws_depth, &blocks,
                               &smem));
     if (t->packed()) {
       radius_warp_kernel<T, true><<<blocks, kWarpsPerBlock * 32, smem, c.st>>>(r);

@@ -16,6 +16,10 @@
 
 namespace pico {
 
+constexpr int kStackWindow = 16;  // frames mirrored in shared memory (power of two)
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 template <typename T>
 struct WarpFrame {
   uint32_t far;
@@ -70,6 +74,109 @@ struct PointSet {
     return ok;
   }
 };
+
+// ---------------------------------------------------------------- staged leaf scan (row storage)
+// sdim > 3: a leaf is `rows x sdim` contiguous scalars. With one lane per point reading its own
+// row, every load instruction touches as many sectors as there are points and only ~10 of 32
+// lanes issue loads at all (profiles/r1/configs_v3.jsonl: 128-D exact search ran at 350 GB/s).
+// Instead the whole warp copies the leaf tile to shared memory with 16-byte cp.async (fully
+// coalesced, no registers), then lane p folds row p in dimension order — the summation order, and
+// with it every distance bit, stays that of metric.hpp:36-51.
+template <typename T>
+struct Vec16;
+template <>
+struct Vec16<float> {
+  using type = float4;
+  static constexpr int n = 4;
+};
+template <>
+struct Vec16<double> {
+  using type = double2;
+  static constexpr int n = 2;
+};
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+__device__ __forceinline__ float fold_vec(int metric, float d, const float4& q, const float4& p, int j) {
+  d = metric_fold(metric, d, q.x, p.x, j);
+  d = metric_fold(metric, d, q.y, p.y, j + 1);
+  d = metric_fold(metric, d, q.z, p.z, j + 2);
+  return metric_fold(metric, d, q.w, p.w, j + 3);
+}
+__device__ __forceinline__ double fold_vec(int metric, double d, const double2& q, const double2& p, int j) {
+  d = metric_fold(metric, d, q.x, p.x, j);
+  return metric_fold(metric, d, q.y, p.y, j + 1);
+}
+
+// One row against the query, dimension order, with the metric resolved OUTSIDE the loop (a
+// run-time switch per coordinate costs more than the arithmetic).
+template <int METRIC, typename T, typename VT>
+__device__ __forceinline__ T fold_row(const VT* __restrict__ qv, const VT* __restrict__ row, int sdimv) {
+  constexpr int V = Vec16<T>::n;
+  T d = metric_init<T>(METRIC);
+#pragma unroll 8
+  for (int c = 0; c < sdimv; ++c) d = fold_vec(METRIC, d, qv[c], row[c], c * V);
+  return d;
+}
+
+// tile: tile_rows x (sdim + Vec16::n) scalars of warp-private shared memory, 16-byte aligned;
+// sq: the query, same alignment. Requires sdim % Vec16::n == 0.
+template <typename T, typename Visitor>
+__device__ __forceinline__ void scan_leaf_staged(const T* __restrict__ rows, const int32_t* __restrict__ indices,
+                                                 int sdim, int lb, int le, const T* sq, T* tile, int tile_rows,
+                                                 int metric, bool approx, T e_inv, Visitor& vis) {
+  using VT = typename Vec16<T>::type;
+  constexpr int V = Vec16<T>::n;
+  const int lane = threadIdx.x & 31;
+  const int sdimv = sdim / V;
+  const int pitch = sdimv + 1;  // one 16-byte pad per row: rows start in different banks
+  VT* tile_v = reinterpret_cast<VT*>(tile);
+  const VT* qv = reinterpret_cast<const VT*>(sq);
+  for (int base = lb; base < le; base += tile_rows) {
+    const int rows_here = min(tile_rows, le - base);
+    const VT* src = reinterpret_cast<const VT*>(rows + (size_t)base * sdim);
+    if ((sdimv & 31) == 0) {
+      for (int r = 0; r < rows_here; ++r)
+        for (int c = lane; c < sdimv; c += 32) cp_async16(tile_v + r * pitch + c, src + (size_t)r * sdimv + c);
+    } else {
+      const int total = rows_here * sdimv;
+      for (int t = lane; t < total; t += 32) {
+        const int r = t / sdimv, c = t - r * sdimv;
+        cp_async16(tile_v + r * pitch + c, src + t);
+      }
+    }
+    const bool valid = lane < rows_here;
+    int idx = -1;
+    if (valid) idx = __ldg(indices + base + lane);  // in flight together with the tile
+    cp_async_wait_all();
+    __syncwarp();
+    T d = Limits<T>::max();
+    if (valid) {
+      const VT* row = tile_v + lane * pitch;
+      switch (metric) {
+        case PICO_B200_METRIC_L2_SQUARED:
+          d = fold_row<PICO_B200_METRIC_L2_SQUARED, T>(qv, row, sdimv);
+          break;
+        case PICO_B200_METRIC_L1:
+          d = fold_row<PICO_B200_METRIC_L1, T>(qv, row, sdimv);
+          break;
+        case PICO_B200_METRIC_LPINF:
+          d = fold_row<PICO_B200_METRIC_LPINF, T>(qv, row, sdimv);
+          break;
+        default:
+          d = fold_row<PICO_B200_METRIC_LNINF, T>(qv, row, sdimv);
+          break;
+      }
+      if (approx) d = mul_rn(d, e_inv);
+    }
+    __syncwarp();  // the tile is overwritten by the next round
+    vis.visit_batch(valid, idx, d);
+  }
+}
 
 // ---------------------------------------------------------------- warp visitors
 // k <= 32: the sorted list lives in registers, slot i in lane i ("register k-heap").
@@ -196,12 +303,17 @@ struct WarpVisitRadius {
 // `sq` = query, `so` = node_box_offset_ (both shared, sdim entries, warp-private).
 template <typename T, bool PACKED, typename Visitor>
 __device__ void traverse_warp(const typename NodeOf<T>::type* __restrict__ nodes, const T* __restrict__ outer,
-                              const PointSet<T, PACKED>& ps, const T* sq, T* so, WarpFrame<T>* stack, int metric,
-                              bool approx, T e_inv, Visitor& vis) {
+                              const PointSet<T, PACKED>& ps, const T* sq, T* so, WarpFrame<T>* stack,
+                              WarpFrame<T>* win, int metric, bool approx, T e_inv, Visitor& vis, T* tile = nullptr,
+                              int tile_rows = 0) {
+  // `stack` (global, one slot per tree level) is the backing store; `win` (shared, kStackWindow
+  // frames) mirrors the most recently pushed ones, so the pop that follows a push — every leaf
+  // visit — does not wait for a global-memory round trip. Frames [win_lo, sp) are valid in `win`.
   const int lane = threadIdx.x & 31;
   uint32_t node = 0;
   T node_dist = T(0);
   int sp = 0;
+  int win_lo = 0;
   for (;;) {
     T a, b;
     uint32_t right, sd;
@@ -212,35 +324,53 @@ __device__ void traverse_warp(const typename NodeOf<T>::type* __restrict__ nodes
       bool go_left;
       T new_off;
       branch_choice(metric, outer, node, a, b, v, sd, go_left, new_off);
+      const uint32_t far = go_left ? right : node + 1;
       if (lane == 0) {
         WarpFrame<T> f;
-        f.far = go_left ? right : node + 1;
+        f.far = far;
         f.sd_state = sd;
         f.dist = node_dist;
         f.new_off = new_off;
         f.old_off = T(0);
+        win[sp & (kStackWindow - 1)] = f;
         stack[sp] = f;
+        prefetch_l2(nodes + far);  // it is (most likely) visited after the near subtree
       }
+      win_lo = max(win_lo, sp + 1 - kStackWindow);
       ++sp;
       node = go_left ? node + 1 : right;
       load_node(nodes, node, a, b, right, sd, lb, le);
     }
-    for (int base = lb; base < le; base += 32) {
-      const int i = base + lane;
-      const bool valid = i < le;
-      int idx = -1;
-      T d = Limits<T>::max();
-      if (valid) {
-        d = ps.distance(i, sq, metric, idx);
-        if (approx) d = mul_rn(d, e_inv);
+    if (!PACKED && tile_rows > 0) {
+      scan_leaf_staged<T>(ps.rows, ps.indices, ps.sdim, lb, le, sq, tile, tile_rows, metric, approx, e_inv, vis);
+    } else {
+      for (int base = lb; base < le; base += 32) {
+        const int i = base + lane;
+        const bool valid = i < le;
+        int idx = -1;
+        T d = Limits<T>::max();
+        if (valid) {
+          d = ps.distance(i, sq, metric, idx);
+          if (approx) d = mul_rn(d, e_inv);
+        }
+        vis.visit_batch(valid, idx, d);
       }
-      vis.visit_batch(valid, idx, d);
     }
     // unwind (kd_tree_search.hpp:93-103)
     bool found = false;
     __syncwarp();
     while (sp > 0) {
-      const WarpFrame<T> f = stack[sp - 1];
+      const int top = sp - 1;
+      WarpFrame<T> f;
+      if (top >= win_lo) {
+        f = win[top & (kStackWindow - 1)];
+      } else {
+        f = stack[top];
+        __syncwarp();
+        if (lane == 0) win[top & (kStackWindow - 1)] = f;
+        win_lo = top;
+        __syncwarp();
+      }
       const uint32_t fsd = f.sd_state & 0x7fffffffu;
       if (!(f.sd_state >> 31)) {
         const T old = so[fsd];
@@ -248,8 +378,11 @@ __device__ void traverse_warp(const typename NodeOf<T>::type* __restrict__ nodes
         if (vis.max() >= d2) {
           __syncwarp();
           if (lane == 0) {
-            stack[sp - 1].sd_state = fsd | 0x80000000u;
-            stack[sp - 1].old_off = old;
+            WarpFrame<T>& wf = win[top & (kStackWindow - 1)];
+            wf.sd_state = fsd | 0x80000000u;
+            wf.old_off = old;
+            stack[top].sd_state = fsd | 0x80000000u;
+            stack[top].old_off = old;
             so[fsd] = f.new_off;
           }
           __syncwarp();
