@@ -253,9 +253,73 @@ class KdTree:
             f |= _lib.FLAG_WARP_PER_QUERY
         return f
 
+    # -- device-resident batches (skip the H2D / D2H copies) ---------------------
+    @staticmethod
+    def _cuda_view(obj, what):
+        """(pointer, shape, typestr) of an object exposing __cuda_array_interface__ (torch.Tensor,
+        cupy.ndarray, numba device array); it must be C-contiguous."""
+        cai = obj.__cuda_array_interface__
+        if cai.get("strides") is not None:
+            itemsize = int(cai["typestr"][2:])
+            expect = []
+            acc = itemsize
+            for n in reversed(cai["shape"]):
+                expect.insert(0, acc)
+                acc *= n
+            if tuple(cai["strides"]) != tuple(expect):
+                raise ValueError(f"{what} not contiguous")
+        return int(cai["data"][0]), tuple(cai["shape"]), cai["typestr"]
+
+    def search_knn_device(self, pts, k, e=None, nns=None, stream=None):
+        """knn for queries that already live on the tree's GPU. `pts`: (n, sdim) device array of the
+        tree's dtype. Returns (or fills) `nns`: a device array of n*k neighbour records seen as int32
+        words — shape (n, k, 2) for float32 trees: [..., 0] = index, [..., 1] = bits of the float32
+        distance (``nns[..., 1].view(torch.float32)``); (n, k, 4) for float64: word 0 = index, words
+        2..3 = the float64 distance. The call is enqueued on `stream` (a CUDA stream handle; default:
+        torch's current stream) and does not synchronise."""
+        ptr, shape, typestr = self._cuda_view(pts, "pts")
+        want = "<f4" if self._dtype == np.float32 else "<f8"
+        if typestr != want:
+            raise ValueError("array dtype not " + ("float32" if want == "<f4" else "float64"))
+        if len(shape) != 2:
+            raise ValueError("array ndim not 2")
+        if shape[1] != self.sdim:
+            raise ValueError("incompatible kd_tree sdim and array inner stride")
+        k = int(k)
+        if k <= 0:
+            raise ValueError("k must be > 0")
+        words = 2 if self._dtype == np.float32 else 4
+        if nns is None:
+            import torch
+            nns = torch.empty((shape[0], k, words), dtype=torch.int32, device=torch.device("cuda", self._device))
+        optr, oshape, otypestr = self._cuda_view(nns, "nns")
+        if otypestr != "<i4" or int(np.prod(oshape)) != shape[0] * k * words:
+            raise ValueError("array dtype not neighbor")
+        if stream is None:
+            import torch
+            stream = torch.cuda.current_stream(self._device).cuda_stream
+        L = _lib.lib()
+        _lib.check(L.pico_b200_set_stream(C.c_void_p(stream)))
+        try:
+            _lib.check(L.pico_b200_knn(self._h, C.c_void_p(ptr), shape[0], self.sdim, k, float(e or 0.0),
+                                       C.c_void_p(optr), _lib.FLAG_DEVICE_POINTERS | _lib.FLAG_ASYNC, None))
+        finally:
+            _lib.check(L.pico_b200_set_stream(None))
+        return nns
+
     def search_knn(self, pts, k, *args, **kw):
         """search_knn(pts, k[, e][, nns]) — def_kd_tree.cpp:59-110. Returns / fills an array
-        of shape (npts, k) (or (k, npts) for column-major input, kd_tree.hpp:362-378)."""
+        of shape (npts, k) (or (k, npts) for column-major input, kd_tree.hpp:362-378). Device arrays
+        (anything with __cuda_array_interface__) are routed to search_knn_device."""
+        if hasattr(pts, "__cuda_array_interface__") and not isinstance(pts, np.ndarray):
+            e = kw.pop("e", None)
+            nns = kw.pop("nns", None)
+            for a in args:
+                if isinstance(a, (int, float, np.floating, np.integer)):
+                    e = float(a)
+                else:
+                    nns = a
+            return self.search_knn_device(pts, k, e, nns)
         e, nns = self._split_args(args, kw, np.ndarray)
         view, row_major = self._queries(pts)
         k = int(k)

@@ -373,6 +373,33 @@ def test_deep_tree_uses_global_stack(pt, oracle):
     assert_radius_parity(nns._offsets, nns._flat[:len(flat)], offs, flat, ordered=False)
 
 
+def test_python_device_arrays(pt):
+    """KdTree.search_knn with torch CUDA tensors: no host copies, enqueued on torch's current stream."""
+    import torch
+    from pico_tree_b200 import datasets as D
+    pts = D.uniform(50_000, 3, seed=1)
+    q = D.uniform(30_000, 3, seed=2)
+    t = pt.KdTree(pts, pt.Metric.L2Squared, 10)
+    want = t.search_knn(q, 5)
+    qd = torch.from_numpy(q).cuda()
+    got = t.search_knn(qd, 5)
+    assert isinstance(got, torch.Tensor) and got.shape == (30_000, 5, 2) and got.dtype == torch.int32
+    torch.cuda.synchronize()
+    assert np.array_equal(got[..., 0].cpu().numpy(), want["index"])
+    assert np.array_equal(got[..., 1].contiguous().view(torch.float32).cpu().numpy(), want["distance"])
+    out = torch.empty((30_000, 1, 2), dtype=torch.int32, device="cuda")
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        r = t.search_knn(qd, 1, 1.5, out)
+    s.synchronize()
+    assert r is out
+    assert np.array_equal(out[..., 0].cpu().numpy(), t.search_knn(q, 1, 1.5)["index"])
+    with pytest.raises(ValueError):
+        t.search_knn(qd.double(), 1)
+    with pytest.raises(ValueError):
+        t.search_knn(qd[:, :2], 1)
+
+
 def test_device_resident_ragged_results(pt):
     """PICO_B200_DEVICE_POINTERS for radius / box: queries, offsets and hits stay in HBM; the bytes must
     equal what the host-buffer path returns."""
