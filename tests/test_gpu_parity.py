@@ -510,3 +510,46 @@ def test_full_size_properties(pt):
     rad = t.search_radius(part, 0.01)
     counts = np.diff(rad._offsets.astype(np.int64))
     assert np.array_equal(counts > 0, nn["distance"][:500_000, 0] < np.float32(0.01))
+
+
+def test_nccl_tree_broadcast_two_gpus(pt):
+    """pico_b200_tree_broadcast with raw ncclComm_t handles (ncclCommInitAll, one host thread per GPU):
+    the replica on GPU 1 must answer exactly like the tree built on GPU 0. Needs two visible GPUs."""
+    import ctypes as C
+    import glob
+    import threading
+    import torch
+    from pico_tree_b200 import _lib, datasets as D
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (run with gpurun --gpus 2)")
+    libs = glob.glob(os.path.join(os.path.dirname(torch.__file__), "..", "nvidia", "nccl", "lib", "libnccl.so*"))
+    nccl = C.CDLL(libs[0] if libs else "libnccl.so.2", mode=C.RTLD_GLOBAL)
+    comms = (C.c_void_p * 2)()
+    devs = (C.c_int * 2)(0, 1)
+    assert nccl.ncclCommInitAll(comms, 2, devs) == 0
+    L = _lib.lib()
+    pts = D.lidar_shape(200_000, seed=1)
+    q = D.lidar_shape(50_000, seed=2, pose_shift=0.35)
+    tree0 = pt.KdTree(pts, pt.Metric.L2Squared, 10, device=0)
+    handles = [C.c_void_p(tree0._h.value), C.c_void_p()]
+    rcs = [None, None]
+
+    def run(rank):
+        rcs[rank] = L.pico_b200_tree_broadcast(C.byref(handles[rank]), comms[rank], rank, 0, rank)
+
+    threads = [threading.Thread(target=run, args=(r,)) for r in range(2)]
+    [t.start() for t in threads]
+    [t.join(timeout=120) for t in threads]
+    assert rcs == [0, 0], (rcs, L.pico_b200_last_error())
+    assert handles[1].value and handles[1].value != handles[0].value
+    inf = _lib.TreeInfo()
+    _lib.check(L.pico_b200_tree_info_get(handles[1], C.byref(inf)))
+    assert inf.device == 1 and inf.n_points == len(pts) and inf.n_nodes == tree0.info()["n_nodes"]
+    want = tree0.search_knn(q, 4)
+    got = np.empty_like(want)
+    _lib.check(L.pico_b200_knn(handles[1], C.c_void_p(q.ctypes.data), len(q), 3, 4, 0.0, C.c_void_p(got.ctypes.data), 0,
+                               None))
+    assert np.array_equal(got["index"], want["index"]) and np.array_equal(got["distance"], want["distance"])
+    L.pico_b200_tree_destroy(handles[1])
+    for c in comms:
+        nccl.ncclCommDestroy(C.c_void_p(c))
