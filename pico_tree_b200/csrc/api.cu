@@ -73,6 +73,7 @@ void release(pico_b200_tree* t) {
   cudaFree(t->d_indices);
   cudaFree(t->d_root_box);
   cudaFree(t->d_outer);
+  cudaFree(t->d_spans);
   delete t;
 }
 
@@ -89,7 +90,7 @@ size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
 size_t image_bytes(const pico_b200_tree* t) {
   return align16(sizeof(ImageHeader)) + align16(2 * t->sdim * t->scalar_size()) + align16(t->n_nodes * t->node_size()) +
-         align16(t->n * 4) + align16(t->pts_bytes()) + align16(t->outer_bytes());
+         align16(t->n * 4) + align16(t->pts_bytes()) + align16(t->outer_bytes()) + align16(t->spans_bytes());
 }
 
 }  // namespace
@@ -309,6 +310,8 @@ int pico_b200_tree_serialize(const pico_b200_tree* t, void* dst, int dst_is_devi
   PICO_CUDA(cudaMemcpy(p, t->d_pts, t->pts_bytes(), kd));
   p += align16(t->pts_bytes());
   if (t->topological()) PICO_CUDA(cudaMemcpy(p, t->d_outer, t->outer_bytes(), kd));
+  p += align16(t->outer_bytes());
+  if (!t->packed()) PICO_CUDA(cudaMemcpy(p, t->d_spans, t->spans_bytes(), kd));
   return 0;
 }
 
@@ -352,12 +355,15 @@ int pico_b200_tree_deserialize(const void* src, uint64_t bytes, int src_is_devic
   if (!rc) rc = up(reinterpret_cast<void**>(&t->d_indices), t->n * 4);
   if (!rc) rc = up(&t->d_pts, t->pts_bytes());
   if (!rc && t->topological()) rc = up(&t->d_outer, t->outer_bytes());
+  if (!rc && !t->topological()) p += align16(t->outer_bytes());
+  if (!rc && !t->packed()) rc = up(reinterpret_cast<void**>(&t->d_spans), t->spans_bytes());
   if (rc) {
     release(t);
     return rc;
   }
   t->device_bytes =
-      t->pts_bytes() + t->n_nodes * t->node_size() + t->n * 4 + 2 * t->sdim * t->scalar_size() + t->outer_bytes();
+      t->pts_bytes() + t->n_nodes * t->node_size() + t->n * 4 + 2 * t->sdim * t->scalar_size() + t->outer_bytes() +
+      t->spans_bytes();
   *out = t;
   return 0;
 }

@@ -927,7 +927,8 @@ __global__ void number_level(BNode<T>* nodes, uint32_t level_begin, uint32_t lev
 }
 
 template <typename T>
-__global__ void emit_nodes(const BNode<T>* nodes, uint32_t n_nodes, typename NodeOf<T>::type* out, T* outer) {
+__global__ void emit_nodes(const BNode<T>* nodes, uint32_t n_nodes, typename NodeOf<T>::type* out, T* outer,
+                           uint2* spans) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_nodes) return;
   const BNode<T>& nd = nodes[i];
@@ -945,6 +946,7 @@ __global__ void emit_nodes(const BNode<T>* nodes, uint32_t n_nodes, typename Nod
     o.split_dim = (uint32_t)nd.split_dim;
   }
   out[nd.preorder] = o;
+  if (spans) spans[nd.preorder] = make_uint2((uint32_t)nd.begin, (uint32_t)(nd.end - nd.begin));
   if (outer) {
     const bool leaf = nd.split_dim < 0;
     outer[2 * (size_t)nd.preorder] = leaf ? T(0) : nd.left_min;
@@ -1018,7 +1020,8 @@ int finalize_storage(pico_b200_tree* t, const T* d_raw, cudaStream_t st) {
                                                                       static_cast<T*>(t->d_pts));
   }
   PICO_CUDA(cudaGetLastError());
-  t->device_bytes = t->pts_bytes() + t->n_nodes * t->node_size() + n * 4 + 2 * t->sdim * sizeof(T) + t->outer_bytes();
+  t->device_bytes = t->pts_bytes() + t->n_nodes * t->node_size() + n * 4 + 2 * t->sdim * sizeof(T) + t->outer_bytes() +
+                    t->spans_bytes();
   return 0;
 }
 
@@ -1229,9 +1232,10 @@ int build_tree(pico_b200_tree* t, const T* h_pts, size_t stride, int rule, int s
   }
   PICO_CUDA(cudaMalloc(&t->d_nodes, (size_t)n_nodes * t->node_size()));
   if (t->topological()) PICO_CUDA(cudaMalloc(&t->d_outer, t->outer_bytes()));
+  if (!t->packed()) PICO_CUDA(cudaMalloc(reinterpret_cast<void**>(&t->d_spans), t->spans_bytes()));
   emit_nodes<T><<<(n_nodes + 255) / 256, 256, 0, st>>>(s.nodes, n_nodes,
                                                         static_cast<typename NodeOf<T>::type*>(t->d_nodes),
-                                                        static_cast<T*>(t->d_outer));
+                                                        static_cast<T*>(t->d_outer), t->d_spans);
   PICO_CUDA(cudaGetLastError());
   PICO_TRY(finalize_storage<T>(t, raw.as<T>(), st));
   PICO_CUDA(cudaEventRecord(ev1, st));
@@ -1298,6 +1302,21 @@ int upload_tree(pico_b200_tree* t, const T* h_pts, size_t stride, const void* h_
   PICO_CUDA(cudaMemcpyAsync(t->d_indices, indices, n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   PICO_CUDA(cudaMemcpyAsync(t->d_root_box, root_box, 2 * sdim * sizeof(T), cudaMemcpyHostToDevice, st));
   PICO_CUDA(cudaMemcpyAsync(t->d_nodes, nodes, n_nodes * sizeof(NodeT), cudaMemcpyHostToDevice, st));
+  if (!t->packed()) {
+    // pre-order: children have larger ids than their parent, so one backward sweep suffices
+    std::vector<uint2> spans(n_nodes);
+    for (size_t i = n_nodes; i-- > 0;) {
+      if (nodes[i].split_dim == PICO_B200_LEAF) {
+        spans[i] = make_uint2((uint32_t)nodes[i].a.begin_idx, (uint32_t)(nodes[i].b.end_idx - nodes[i].a.begin_idx));
+      } else {
+        const uint2 l = spans[i + 1], r = spans[nodes[i].right];
+        spans[i] = make_uint2(l.x, l.y + r.y);
+      }
+    }
+    PICO_CUDA(cudaMalloc(reinterpret_cast<void**>(&t->d_spans), t->spans_bytes()));
+    PICO_CUDA(cudaMemcpyAsync(t->d_spans, spans.data(), t->spans_bytes(), cudaMemcpyHostToDevice, st));
+    PICO_CUDA(cudaStreamSynchronize(st));
+  }
   if (t->topological()) {
     if (!outer_bounds) return fail(PICO_B200_ERR_INVALID_ARGUMENT, "topological metric needs the outer bounds");
     PICO_CUDA(cudaMalloc(&t->d_outer, t->outer_bytes()));

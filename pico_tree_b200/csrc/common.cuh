@@ -6,6 +6,8 @@
 //   ptsN    : T[n * sdim] row-major for sdim > 3, LEAF ORDER
 //   indices : int32[n], leaf position -> original index (kd_tree_data::indices)
 //   outer   : T[n_nodes][2] = {left_min, right_max}, topological metrics only
+//   spans   : uint2[n_nodes] = {first point, number of points} below each node, sdim > 3 only
+//             (leaf order makes every subtree one contiguous run; feeds the subtree distance cache)
 #pragma once
 
 #include <cuda_runtime.h>
@@ -96,6 +98,7 @@ struct pico_b200_tree {
   int32_t* d_indices = nullptr;
   void* d_root_box = nullptr;  // min[sdim] then max[sdim], device copy
   void* d_outer = nullptr;     // topological metrics: {left_min, right_max}[n_nodes] (kd_tree_node.hpp:52-59)
+  uint2* d_spans = nullptr;    // row storage (sdim > 3): {first point, point count} below every node
   double root_box_host[2 * 4] = {0};  // first min(sdim,4) dims, as double, for query ordering
   double build_ms = 0.0;
   size_t device_bytes = 0;
@@ -105,6 +108,7 @@ struct pico_b200_tree {
   bool packed() const { return sdim <= (size_t)pico::kMaxPackedDim; }
   bool topological() const { return metric >= PICO_B200_METRIC_SO2; }
   size_t outer_bytes() const { return topological() ? n_nodes * 2 * scalar_size() : 0; }
+  size_t spans_bytes() const { return packed() ? 0 : n_nodes * sizeof(uint2); }
   size_t pts_bytes() const { return packed() ? n * 4 * scalar_size() : n * sdim * scalar_size(); }
 };
 

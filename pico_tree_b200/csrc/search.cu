@@ -58,6 +58,7 @@ template <typename T>
 struct KnnArgs {
   const typename NodeOf<T>::type* nodes;
   const T* outer;  // {left_min, right_max} per node, topological metrics only
+  const uint2* spans;  // {first point, count} below each node (row storage), or nullptr
   const typename Vec4Of<T>::type* pts4;
   const T* rows;
   const int32_t* indices;
@@ -201,13 +202,13 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) knn_warp_kernel(KnnArgs<T
       WarpVisitKnn<T, WarpKnnReg<T>> vis;
       vis.list.init(a.k);
       traverse_warp<T, PACKED>(a.nodes, a.outer, ps, sq, so, stack, win, a.metric, a.approx != 0, a.e_inv, vis,
-                               tile, a.tile_rows);
+                               tile, a.tile_rows, a.spans);
       vis.list.store(row);
     } else {
       WarpVisitKnn<T, WarpKnnMem<T>> vis;
       vis.list.init(row, a.k);
       traverse_warp<T, PACKED>(a.nodes, a.outer, ps, sq, so, stack, win, a.metric, a.approx != 0, a.e_inv, vis,
-                               tile, a.tile_rows);
+                               tile, a.tile_rows, a.spans);
     }
   }
 }
@@ -239,7 +240,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) radius_warp_kernel(Radius
     vis.radius = r.radius;
     vis.out = r.hits ? r.hits + r.offsets[qi] : nullptr;
     traverse_warp<T, PACKED>(a.nodes, a.outer, ps, sq, so, stack, win, a.metric, a.approx != 0, a.e_inv, vis, tile,
-                             a.tile_rows);
+                             a.tile_rows, a.spans);
     if (!r.hits && lane == 0) r.counts[qi] = vis.count;
   }
 }
@@ -528,6 +529,7 @@ void fill_base(KnnArgs<T>& a, const pico_b200_tree* t, const T* d_q, size_t d_st
                double e) {
   a.nodes = static_cast<const typename NodeOf<T>::type*>(t->d_nodes);
   a.outer = static_cast<const T*>(t->d_outer);
+  a.spans = nullptr;
   a.pts4 = t->packed() ? static_cast<const typename Vec4Of<T>::type*>(t->d_pts) : nullptr;
   a.rows = t->packed() ? nullptr : static_cast<const T*>(t->d_pts);
   a.indices = t->d_indices;
@@ -556,15 +558,28 @@ size_t plan_warp_smem(const pico_b200_tree* t, KnnArgs<T>& a) {
   const size_t window = kStackWindow * sizeof(WarpFrame<T>) / sizeof(T);  // scalars; a multiple of 16 bytes
   a.warp_smem = (int)(2 * sdim + window);
   a.tile_rows = 0;
+  a.spans = nullptr;
   if (!t->packed() && sdim % vec == 0 && t->max_leaf_points > 0) {
-    size_t rows = std::min<size_t>(32, t->max_leaf_points);
-    // keep at least two blocks of 8 warps resident per SM (227 KB of shared memory)
-    while (rows > 4 && (2 * sdim + rows * (sdim + vec) + window) * sizeof(T) * kWarpsPerBlock > 100 * 1024)
-      rows = (rows + 1) / 2;
-    const size_t bytes = (2 * sdim + rows * (sdim + vec) + window) * sizeof(T);
-    if (bytes * kWarpsPerBlock <= 100 * 1024) {
+    // per warp: query + offsets, the tile (rows x (sdim + pad)), the distance / index cache of the tile's
+    // rows, the stack window. The tile holds a whole subtree when it can (subtree distance cache): as many
+    // rows as fit while FOUR blocks of 8 warps stay resident per SM (the kernel's 64 registers allow no
+    // more; a bigger tile costs occupancy and was slower, profiles/r1/hd_tile_rows.txt), at most 32.
+    static const size_t cap = [] {
+      const char* e = getenv("PICO_B200_TILE_ROWS");  // tuning hook
+      const int x = e ? atoi(e) : 0;
+      return (size_t)((x >= 1 && x <= 32) ? x : 32);
+    }();
+    auto slice = [&](size_t rows) {
+      const size_t cache = (2 * rows + vec - 1) / vec * vec;
+      return 2 * sdim + rows * (sdim + vec) + cache + window;
+    };
+    size_t rows = cap;
+    constexpr size_t kBlockBudget = 56 * 1024;
+    while (rows > 1 && slice(rows) * sizeof(T) * kWarpsPerBlock > kBlockBudget) --rows;
+    if (slice(rows) * sizeof(T) * kWarpsPerBlock <= kBlockBudget) {
       a.tile_rows = (int)rows;
-      a.warp_smem = (int)(2 * sdim + rows * (sdim + vec) + window);
+      a.warp_smem = (int)slice(rows);
+      a.spans = t->d_spans;
     }
   }
   return (size_t)a.warp_smem * sizeof(T);

@@ -75,13 +75,7 @@ struct PointSet {
   }
 };
 
-// ---------------------------------------------------------------- staged leaf scan (row storage)
-// sdim > 3: a leaf is `rows x sdim` contiguous scalars. With one lane per point reading its own
-// row, every load instruction touches as many sectors as there are points and only ~10 of 32
-// lanes issue loads at all (profiles/r1/configs_v3.jsonl: 128-D exact search ran at 350 GB/s).
-// Instead the whole warp copies the leaf tile to shared memory with 16-byte cp.async (fully
-// coalesced, no registers), then lane p folds row p in dimension order — the summation order, and
-// with it every distance bit, stays that of metric.hpp:36-51.
+// ---------------------------------------------------------------- leaf scan for row storage (sdim > 3)
 template <typename T>
 struct Vec16;
 template <>
@@ -95,40 +89,58 @@ struct Vec16<double> {
   static constexpr int n = 2;
 };
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc));
+// The distance of a row is a fold over per-coordinate TERMS: term_j = (q_j - p_j)^2 or |q_j - p_j|,
+// folded with +, max or min in dimension order (metric.hpp:36-51,131-145,158-174). The terms are
+// independent of each other, the fold is a serial chain. Leaves are small, so a lane-per-point
+// loop doing both leaves most lanes idle while the warp still pays every instruction: measured
+// 364 M warp instructions per 128-D query, 70 % of them in that loop, issue slots 79 % busy.
+// Split instead: ALL lanes compute terms (coalesced 16-byte loads straight from global memory, one
+// chunk of a row per lane) into a shared-memory tile; then lane p folds the terms of row p in
+// dimension order. Same operations on the same operands in the same order — bit-identical.
+template <int METRIC>
+__device__ __forceinline__ float term1(float q, float p) {
+  const float t = sub_rn(q, p);
+  return METRIC == PICO_B200_METRIC_L2_SQUARED ? mul_rn(t, t) : fabsf(t);
 }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+template <int METRIC>
+__device__ __forceinline__ double term1(double q, double p) {
+  const double t = sub_rn(q, p);
+  return METRIC == PICO_B200_METRIC_L2_SQUARED ? mul_rn(t, t) : fabs(t);
+}
+template <int METRIC, typename T>
+__device__ __forceinline__ T acc1(T d, T a) {
+  if (METRIC == PICO_B200_METRIC_L2_SQUARED || METRIC == PICO_B200_METRIC_L1) return add_rn(d, a);
+  if (METRIC == PICO_B200_METRIC_LPINF) return d < a ? a : d;
+  return a < d ? a : d;
+}
+template <int METRIC>
+__device__ __forceinline__ float4 term_vec(const float4& q, const float4& p) {
+  return make_float4(term1<METRIC>(q.x, p.x), term1<METRIC>(q.y, p.y), term1<METRIC>(q.z, p.z),
+                     term1<METRIC>(q.w, p.w));
+}
+template <int METRIC>
+__device__ __forceinline__ double2 term_vec(const double2& q, const double2& p) {
+  return make_double2(term1<METRIC>(q.x, p.x), term1<METRIC>(q.y, p.y));
+}
+template <int METRIC>
+__device__ __forceinline__ float acc_vec(float d, const float4& s) {
+  d = acc1<METRIC>(d, s.x);
+  d = acc1<METRIC>(d, s.y);
+  d = acc1<METRIC>(d, s.z);
+  return acc1<METRIC>(d, s.w);
+}
+template <int METRIC>
+__device__ __forceinline__ double acc_vec(double d, const double2& s) {
+  d = acc1<METRIC>(d, s.x);
+  return acc1<METRIC>(d, s.y);
+}
+__device__ __forceinline__ float4 ldg16(const float4* p) { return __ldg(p); }
+__device__ __forceinline__ double2 ldg16(const double2* p) { return __ldg(p); }
 
-__device__ __forceinline__ float fold_vec(int metric, float d, const float4& q, const float4& p, int j) {
-  d = metric_fold(metric, d, q.x, p.x, j);
-  d = metric_fold(metric, d, q.y, p.y, j + 1);
-  d = metric_fold(metric, d, q.z, p.z, j + 2);
-  return metric_fold(metric, d, q.w, p.w, j + 3);
-}
-__device__ __forceinline__ double fold_vec(int metric, double d, const double2& q, const double2& p, int j) {
-  d = metric_fold(metric, d, q.x, p.x, j);
-  return metric_fold(metric, d, q.y, p.y, j + 1);
-}
-
-// One row against the query, dimension order, with the metric resolved OUTSIDE the loop (a
-// run-time switch per coordinate costs more than the arithmetic).
-template <int METRIC, typename T, typename VT>
-__device__ __forceinline__ T fold_row(const VT* __restrict__ qv, const VT* __restrict__ row, int sdimv) {
-  constexpr int V = Vec16<T>::n;
-  T d = metric_init<T>(METRIC);
-#pragma unroll 8
-  for (int c = 0; c < sdimv; ++c) d = fold_vec(METRIC, d, qv[c], row[c], c * V);
-  return d;
-}
-
-// tile: tile_rows x (sdim + Vec16::n) scalars of warp-private shared memory, 16-byte aligned;
-// sq: the query, same alignment. Requires sdim % Vec16::n == 0.
-template <typename T, typename Visitor>
-__device__ __forceinline__ void scan_leaf_staged(const T* __restrict__ rows, const int32_t* __restrict__ indices,
-                                                 int sdim, int lb, int le, const T* sq, T* tile, int tile_rows,
-                                                 int metric, bool approx, T e_inv, Visitor& vis) {
+// rows [base, base + rows_here) -> terms in the tile -> lane p < rows_here returns the fold of row p
+template <int METRIC, typename T>
+__device__ __forceinline__ T terms_then_fold(const T* __restrict__ rows, int sdim, int base, int rows_here,
+                                             const T* sq, T* tile) {
   using VT = typename Vec16<T>::type;
   constexpr int V = Vec16<T>::n;
   const int lane = threadIdx.x & 31;
@@ -136,47 +148,94 @@ __device__ __forceinline__ void scan_leaf_staged(const T* __restrict__ rows, con
   const int pitch = sdimv + 1;  // one 16-byte pad per row: rows start in different banks
   VT* tile_v = reinterpret_cast<VT*>(tile);
   const VT* qv = reinterpret_cast<const VT*>(sq);
+  const VT* src = reinterpret_cast<const VT*>(rows + (size_t)base * sdim);
+  if ((sdimv & 31) == 0) {
+    // every lane always handles the same chunks of the query
+    for (int c = lane; c < sdimv; c += 32) {
+      const VT qc = qv[c];
+#pragma unroll 4
+      for (int r = 0; r < rows_here; ++r)
+        tile_v[r * pitch + c] = term_vec<METRIC>(qc, ldg16(src + (size_t)r * sdimv + c));
+    }
+  } else {
+    const int total = rows_here * sdimv;
+#pragma unroll 2
+    for (int t = lane; t < total; t += 32) {
+      const int r = t / sdimv, c = t - r * sdimv;
+      tile_v[r * pitch + c] = term_vec<METRIC>(qv[c], ldg16(src + t));
+    }
+  }
+  __syncwarp();
+  T d = metric_init<T>(METRIC);
+  if (lane < rows_here) {
+    const VT* row = tile_v + lane * pitch;
+#pragma unroll 8
+    for (int c = 0; c < sdimv; ++c) d = acc_vec<METRIC>(d, row[c]);
+  }
+  __syncwarp();  // the tile is overwritten by the next round
+  return d;
+}
+
+// Returns, in lane p < rows_here (rows_here <= tile_rows), the distance of row base + p to the query
+// (scaled for the approximate visitors) and its original index.
+template <typename T>
+__device__ __forceinline__ void stage_and_fold(const T* __restrict__ rows, const int32_t* __restrict__ indices, int sdim,
+                                               int base, int rows_here, const T* sq, T* tile, int metric, bool approx,
+                                               T e_inv, T& d, int& idx) {
+  const int lane = threadIdx.x & 31;
+  const bool valid = lane < rows_here;
+  idx = -1;
+  if (valid) idx = __ldg(indices + base + lane);
+  switch (metric) {
+    case PICO_B200_METRIC_L2_SQUARED:
+      d = terms_then_fold<PICO_B200_METRIC_L2_SQUARED, T>(rows, sdim, base, rows_here, sq, tile);
+      break;
+    case PICO_B200_METRIC_L1:
+      d = terms_then_fold<PICO_B200_METRIC_L1, T>(rows, sdim, base, rows_here, sq, tile);
+      break;
+    case PICO_B200_METRIC_LPINF:
+      d = terms_then_fold<PICO_B200_METRIC_LPINF, T>(rows, sdim, base, rows_here, sq, tile);
+      break;
+    default:
+      d = terms_then_fold<PICO_B200_METRIC_LNINF, T>(rows, sdim, base, rows_here, sq, tile);
+      break;
+  }
+  if (!valid)
+    d = Limits<T>::max();
+  else if (approx)
+    d = mul_rn(d, e_inv);
+}
+
+template <typename T, typename Visitor>
+__device__ __forceinline__ void scan_leaf_staged(const T* __restrict__ rows, const int32_t* __restrict__ indices,
+                                                 int sdim, int lb, int le, const T* sq, T* tile, int tile_rows,
+                                                 int metric, bool approx, T e_inv, Visitor& vis) {
+  const int lane = threadIdx.x & 31;
   for (int base = lb; base < le; base += tile_rows) {
     const int rows_here = min(tile_rows, le - base);
-    const VT* src = reinterpret_cast<const VT*>(rows + (size_t)base * sdim);
-    if ((sdimv & 31) == 0) {
-      for (int r = 0; r < rows_here; ++r)
-        for (int c = lane; c < sdimv; c += 32) cp_async16(tile_v + r * pitch + c, src + (size_t)r * sdimv + c);
-    } else {
-      const int total = rows_here * sdimv;
-      for (int t = lane; t < total; t += 32) {
-        const int r = t / sdimv, c = t - r * sdimv;
-        cp_async16(tile_v + r * pitch + c, src + t);
-      }
-    }
-    const bool valid = lane < rows_here;
-    int idx = -1;
-    if (valid) idx = __ldg(indices + base + lane);  // in flight together with the tile
-    cp_async_wait_all();
-    __syncwarp();
-    T d = Limits<T>::max();
-    if (valid) {
-      const VT* row = tile_v + lane * pitch;
-      switch (metric) {
-        case PICO_B200_METRIC_L2_SQUARED:
-          d = fold_row<PICO_B200_METRIC_L2_SQUARED, T>(qv, row, sdimv);
-          break;
-        case PICO_B200_METRIC_L1:
-          d = fold_row<PICO_B200_METRIC_L1, T>(qv, row, sdimv);
-          break;
-        case PICO_B200_METRIC_LPINF:
-          d = fold_row<PICO_B200_METRIC_LPINF, T>(qv, row, sdimv);
-          break;
-        default:
-          d = fold_row<PICO_B200_METRIC_LNINF, T>(qv, row, sdimv);
-          break;
-      }
-      if (approx) d = mul_rn(d, e_inv);
-    }
-    __syncwarp();  // the tile is overwritten by the next round
-    vis.visit_batch(valid, idx, d);
+    T d;
+    int idx;
+    stage_and_fold<T>(rows, indices, sdim, base, rows_here, sq, tile, metric, approx, e_inv, d, idx);
+    vis.visit_batch(lane < rows_here, idx, d);
   }
 }
+
+// Subtree distance cache (row storage). Leaves of a high-dimensional tree are small (2-3 points on
+// average under the sliding midpoint rule with max_leaf_size 10), so a lane-per-point leaf scan
+// keeps 2 of 32 lanes busy and the kernel is bound by instruction issue. Points are stored in
+// leaf order, i.e. the points below ANY node form one contiguous run: when the descent reaches a
+// node with at most tile_rows points below it, the distances of all of them are computed in one
+// staged pass (one lane per point) and kept in shared memory; the traversal below that node —
+// its order, its prune tests, what is offered to the visitor — runs unchanged and takes the
+// distances from the cache. Distances of leaves that end up pruned were computed for nothing; the
+// lanes would have idled anyway.
+template <typename T>
+struct SpanCache {
+  T* dist;        // [tile_rows] shared
+  int* index;     // [tile_rows] shared
+  int lo, hi;     // cached point range
+  int base_sp;    // stack height when it was filled; frames below it belong to ancestors
+};
 
 // ---------------------------------------------------------------- warp visitors
 // k <= 32: the sorted list lives in registers, slot i in lane i ("register k-heap").
@@ -305,7 +364,7 @@ template <typename T, bool PACKED, typename Visitor>
 __device__ void traverse_warp(const typename NodeOf<T>::type* __restrict__ nodes, const T* __restrict__ outer,
                               const PointSet<T, PACKED>& ps, const T* sq, T* so, WarpFrame<T>* stack,
                               WarpFrame<T>* win, int metric, bool approx, T e_inv, Visitor& vis, T* tile = nullptr,
-                              int tile_rows = 0) {
+                              int tile_rows = 0, const uint2* __restrict__ spans = nullptr) {
   // `stack` (global, one slot per tree level) is the backing store; `win` (shared, kStackWindow
   // frames) mirrors the most recently pushed ones, so the pop that follows a push — every leaf
   // visit — does not wait for a global-memory round trip. Frames [win_lo, sp) are valid in `win`.
@@ -314,12 +373,38 @@ __device__ void traverse_warp(const typename NodeOf<T>::type* __restrict__ nodes
   T node_dist = T(0);
   int sp = 0;
   int win_lo = 0;
+  SpanCache<T> cache;
+  cache.lo = cache.hi = 0;
+  cache.base_sp = 0x7fffffff;  // nothing cached
+  if (!PACKED && tile_rows > 0) {
+    // behind the tile: tile_rows distances, then tile_rows indices
+    cache.dist = tile + (size_t)tile_rows * (ps.sdim + Vec16<T>::n);
+    cache.index = reinterpret_cast<int*>(cache.dist + tile_rows);
+  }
   for (;;) {
     T a, b;
     uint32_t right, sd;
     int lb, le;
     load_node(nodes, node, a, b, right, sd, lb, le);
     while (sd != PICO_B200_LEAF) {
+      if (!PACKED && spans != nullptr && sp < cache.base_sp) {
+        // outside any cached subtree: does everything below this node fit into one tile?
+        const uint2 span = __ldg(spans + node);
+        if ((int)span.y <= tile_rows) {
+          T d;
+          int idx;
+          stage_and_fold<T>(ps.rows, ps.indices, ps.sdim, (int)span.x, (int)span.y, sq, tile, metric, approx, e_inv,
+                            d, idx);
+          if (lane < (int)span.y) {
+            cache.dist[lane] = d;
+            cache.index[lane] = idx;
+          }
+          __syncwarp();
+          cache.lo = (int)span.x;
+          cache.hi = (int)(span.x + span.y);
+          cache.base_sp = sp;
+        }
+      }
       const T v = sq[sd];
       bool go_left;
       T new_off;
@@ -341,7 +426,15 @@ __device__ void traverse_warp(const typename NodeOf<T>::type* __restrict__ nodes
       node = go_left ? node + 1 : right;
       load_node(nodes, node, a, b, right, sd, lb, le);
     }
-    if (!PACKED && tile_rows > 0) {
+    if (!PACKED && tile_rows > 0 && sp >= cache.base_sp && lb >= cache.lo && le <= cache.hi) {
+      for (int base = lb; base < le; base += 32) {
+        const int i = base + lane;
+        const bool valid = i < le;
+        const T d = valid ? cache.dist[i - cache.lo] : Limits<T>::max();
+        const int idx = valid ? cache.index[i - cache.lo] : -1;
+        vis.visit_batch(valid, idx, d);
+      }
+    } else if (!PACKED && tile_rows > 0) {
       scan_leaf_staged<T>(ps.rows, ps.indices, ps.sdim, lb, le, sq, tile, tile_rows, metric, approx, e_inv, vis);
     } else {
       for (int base = lb; base < le; base += 32) {
@@ -389,6 +482,7 @@ __device__ void traverse_warp(const typename NodeOf<T>::type* __restrict__ nodes
           node = f.far;
           node_dist = d2;
           found = true;
+          if (top < cache.base_sp) cache.base_sp = 0x7fffffff;  // left the cached subtree
           break;
         }
         --sp;
