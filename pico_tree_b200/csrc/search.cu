@@ -75,6 +75,8 @@ struct KnnArgs {
   // warp kernels: shared memory per warp in scalars (query + offsets [+ leaf tile]) and the rows
   // of the staged leaf tile (0 = points are read straight from global memory)
   int warp_smem, tile_rows;
+  // warp kernels are persistent (one wave of resident blocks): every warp draws its next query here
+  unsigned long long* counter;
 };
 
 template <typename T, int DIM, int KMAX, bool FAST, bool DEEP>
@@ -185,10 +187,14 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) knn_warp_kernel(KnnArgs<T
   T* tile = so + a.sdim;
   WarpFrame<T>* win = reinterpret_cast<WarpFrame<T>*>(sq + a.warp_smem) - kStackWindow;  // tail of the warp's slice
   const size_t warp_global = (size_t)blockIdx.x * kWarpsPerBlock + w;
-  const size_t total_warps = (size_t)gridDim.x * kWarpsPerBlock;
   WarpFrame<T>* stack = static_cast<WarpFrame<T>*>(a.ws) + warp_global * a.ws_depth;
   PointSet<T, PACKED> ps{a.pts4, a.rows, a.indices, a.sdim};
-  for (size_t slot = warp_global; slot < a.nq; slot += total_warps) {
+  for (;;) {
+    // queries differ a lot in cost (pruning): draw them one at a time instead of striding
+    unsigned long long slot = 0;
+    if (lane == 0) slot = atomicAdd(a.counter, 1ull);
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+    if (slot >= a.nq) break;
     const uint32_t qi = a.perm ? a.perm[slot] : (uint32_t)slot;
     const T* qp = a.q + (size_t)qi * a.q_stride;
     __syncwarp();
@@ -224,10 +230,14 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) radius_warp_kernel(Radius
   T* tile = so + a.sdim;
   WarpFrame<T>* win = reinterpret_cast<WarpFrame<T>*>(sq + a.warp_smem) - kStackWindow;  // tail of the warp's slice
   const size_t warp_global = (size_t)blockIdx.x * kWarpsPerBlock + w;
-  const size_t total_warps = (size_t)gridDim.x * kWarpsPerBlock;
   WarpFrame<T>* stack = static_cast<WarpFrame<T>*>(a.ws) + warp_global * a.ws_depth;
   PointSet<T, PACKED> ps{a.pts4, a.rows, a.indices, a.sdim};
-  for (size_t slot = warp_global; slot < a.nq; slot += total_warps) {
+  for (;;) {
+    // queries differ a lot in cost (pruning): draw them one at a time instead of striding
+    unsigned long long slot = 0;
+    if (lane == 0) slot = atomicAdd(a.counter, 1ull);
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+    if (slot >= a.nq) break;
     const uint32_t qi = a.perm ? a.perm[slot] : (uint32_t)slot;
     const T* qp = a.q + (size_t)qi * a.q_stride;
     __syncwarp();
@@ -547,6 +557,7 @@ void fill_base(KnnArgs<T>& a, const pico_b200_tree* t, const T* d_q, size_t d_st
   a.ws_stride = a.ws_depth = 0;
   a.warp_smem = 2 * (int)t->sdim + (int)(kStackWindow * sizeof(WarpFrame<T>) / sizeof(T));
   a.tile_rows = 0;
+  a.counter = nullptr;
 }
 
 // Shared memory per warp of the warp-per-query kernels, in bytes; decides whether leaves are
@@ -615,6 +626,22 @@ int warp_geometry(CallCtx& c, const pico_b200_tree* t, size_t items, size_t fram
   if (*smem > 200 * 1024) return fail(PICO_B200_ERR_UNSUPPORTED, "spatial dimension too large for shared memory");
   *blocks = (unsigned)nblocks;
   PICO_TRY(c.alloc(ws, nblocks * kWarpsPerBlock * *depth * frame_bytes));
+  return 0;
+}
+
+// Persistent launch: no more blocks than are resident at once (occupancy x SMs); the warps draw
+// queries from `counter`, which is zeroed here.
+template <typename Kernel>
+int persistent_grid(CallCtx& c, const pico_b200_tree* t, Kernel kernel, size_t smem, unsigned long long** counter,
+                    unsigned* blocks) {
+  if (smem > 48 * 1024)
+    PICO_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  PICO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kWarpsPerBlock * 32, smem));
+  if (per_sm < 1) return fail(PICO_B200_ERR_UNSUPPORTED, "warp kernel does not fit on an SM");
+  *blocks = std::min<unsigned>(*blocks, (unsigned)per_sm * (unsigned)t->sm_count);
+  if (!*counter) PICO_TRY(c.alloc(reinterpret_cast<void**>(counter), sizeof(unsigned long long)));
+  PICO_CUDA(cudaMemsetAsync(*counter, 0, sizeof(unsigned long long), c.st));
   return 0;
 }
 
@@ -695,12 +722,10 @@ int knn_enqueue(CallCtx& c, const pico_b200_tree* t, const T* q, size_t nq, size
     PICO_TRY(warp_geometry<T>(c, t, nq, sizeof(WarpFrame<T>), plan_warp_smem<T>(t, a), &a.ws, &a.ws_depth, &blocks,
                               &smem));
     const bool reg = k <= 32;
-#define PICO_LAUNCH_WARP(P, R)                                                                                  \
-  do {                                                                                                          \
-    if (smem > 48 * 1024)                                                                                       \
-      PICO_CUDA(cudaFuncSetAttribute(knn_warp_kernel<T, P, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
-                                     (int)smem));                                                               \
-    knn_warp_kernel<T, P, R><<<blocks, kWarpsPerBlock * 32, smem, c.st>>>(a);                                   \
+#define PICO_LAUNCH_WARP(P, R)                                                                \
+  do {                                                                                        \
+    PICO_TRY(persistent_grid(c, t, knn_warp_kernel<T, P, R>, smem, &a.counter, &blocks));     \
+    knn_warp_kernel<T, P, R><<<blocks, kWarpsPerBlock * 32, smem, c.st>>>(a);                 \
   } while (0)
     if (t->packed()) {
       if (reg)
@@ -930,11 +955,10 @@ int launch_radius(CallCtx& c, const pico_b200_tree* t, RadiusArgs<T>& r, unsigne
     PICO_TRY(warp_geometry<T>(c, t, a.nq, sizeof(WarpFrame<T>), plan_warp_smem<T>(t, a), &a.ws, &a.ws_depth, &blocks,
                               &smem));
     if (t->packed()) {
+      PICO_TRY(persistent_grid(c, t, radius_warp_kernel<T, true>, smem, &a.counter, &blocks));
       radius_warp_kernel<T, true><<<blocks, kWarpsPerBlock * 32, smem, c.st>>>(r);
     } else {
-      if (smem > 48 * 1024)
-        PICO_CUDA(cudaFuncSetAttribute(radius_warp_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem));
+      PICO_TRY(persistent_grid(c, t, radius_warp_kernel<T, false>, smem, &a.counter, &blocks));
       radius_warp_kernel<T, false><<<blocks, kWarpsPerBlock * 32, smem, c.st>>>(r);
     }
   }

@@ -325,6 +325,39 @@ def test_edge_cases(pt, oracle):
     assert np.array_equal(got_f.T["index"], t.search_knn(q, 2)["index"])
 
 
+def test_empty_and_degenerate_batches(pt, oracle):
+    """Empty and ragged inputs: no queries, no hits at all, k beyond the point count, boxes that hold
+    nothing / everything, one-point leaves."""
+    rng = np.random.default_rng(4)
+    pts = rng.random((300, 3), dtype=np.float32)
+    t = pt.KdTree(pts, pt.Metric.L2Squared, 1)          # every leaf holds exactly one point
+    assert t.info()["n_leaves"] == 300
+    none = np.empty((0, 3), np.float32)
+    assert len(t.search_radius(none, 1.0)) == 0
+    assert len(t.search_box(none)) == 0
+    far = np.full((5, 3), 100.0, np.float32)
+    rad = t.search_radius(far, 1e-3)
+    assert len(rad) == 5 and all(len(r) == 0 for r in rad)  # ragged result with zero total hits
+    everything = np.array([[-1, -1, -1], [2, 2, 2], [5, 5, 5], [6, 6, 6]], np.float32)
+    res = t.search_box(everything)
+    assert sorted(res[0].tolist()) == list(range(300)) and len(res[1]) == 0
+    # k beyond the point count through the C-ABI: the first n slots are the sorted answer, the rest stay
+    # {-1, max} (the reference's iterator overload leaves them unspecified, search_visitor.hpp:98-103)
+    q = rng.random((40, 3), dtype=np.float32)
+    for kw in ({}, {"warp_per_query": True}):
+        got = t.search_knn(q, 320, **kw)
+        want = oracle.OracleTree(pts, 1).search_knn(q, 300)
+        assert np.array_equal(got["distance"][:, :300], want["distance"])
+        assert np.all(got["index"][:, 300:] == -1) and np.all(got["distance"][:, 300:] == np.finfo(np.float32).max)
+    # all queries identical, all points identical in one coordinate
+    pts2 = rng.random((5000, 2), dtype=np.float32)
+    pts2[:, 1] = 0.5
+    t2 = pt.KdTree(pts2, pt.Metric.L2Squared, 10)
+    o2 = oracle.OracleTree(pts2, 10)
+    q2 = np.tile(np.array([[0.3, 0.5]], np.float32), (3000, 1))
+    assert_knn_parity(t2.search_knn(q2, 3), o2.search_knn(q2, 3), pts2, q2)
+
+
 def test_python_api_three_point_cases(pt):
     # test/pyco_tree/kd_tree_test.py:53-69,90-118,151-192
     a = np.array([[2, 1], [4, 3], [8, 7]], np.float32)
