@@ -68,6 +68,7 @@ struct KnnArgs {
   const uint32_t* perm;  // nullptr = identity
   Neighbor<T>* out;
   int k, sdim, metric, approx;
+  uint32_t n_points;
   T e_inv;
   // deep-tree workspace (GlobalStack) or warp stacks
   void* ws;
@@ -99,10 +100,12 @@ __global__ void __launch_bounds__(kThreadsPerBlock) knn_thread_kernel(KnnArgs<T>
         st.node = static_cast<uint32_t*>(a.ws) + tid;
         st.dist = reinterpret_cast<T*>(static_cast<uint32_t*>(a.ws) + a.ws_stride * a.ws_depth) + tid;
         st.off = st.dist + a.ws_stride * a.ws_depth;
-        traverse_packed<T, DIM, FAST, true>(a.nodes, a.pts4, a.outer, q, a.metric, a.approx != 0, a.e_inv, st, vis);
+        traverse_packed<T, DIM, FAST, kPrimeFirstLeaf>(a.nodes, a.pts4, a.outer, q, a.metric, a.approx != 0, a.e_inv, st,
+                                                       vis);
       } else {
         LocalStack<T, DIM, kLocalStack> st;
-        traverse_packed<T, DIM, FAST, true>(a.nodes, a.pts4, a.outer, q, a.metric, a.approx != 0, a.e_inv, st, vis);
+        traverse_packed<T, DIM, FAST, kPrimeFirstLeaf>(a.nodes, a.pts4, a.outer, q, a.metric, a.approx != 0, a.e_inv, st,
+                                                       vis);
       }
       out->index = vis.idx;
       out->distance = vis.best;
@@ -116,10 +119,11 @@ __global__ void __launch_bounds__(kThreadsPerBlock) knn_thread_kernel(KnnArgs<T>
         st.node = static_cast<uint32_t*>(a.ws) + tid;
         st.dist = reinterpret_cast<T*>(static_cast<uint32_t*>(a.ws) + a.ws_stride * a.ws_depth) + tid;
         st.off = st.dist + a.ws_stride * a.ws_depth;
-        traverse_packed<T, DIM, FAST, false>(a.nodes, a.pts4, a.outer, q, a.metric, a.approx != 0, a.e_inv, st, vis);
+        traverse_packed<T, DIM, FAST, kPrimeNone>(a.nodes, a.pts4, a.outer, q, a.metric, a.approx != 0, a.e_inv, st, vis);
       } else {
         LocalStack<T, DIM, kLocalStack> st;
-        traverse_packed<T, DIM, FAST, false>(a.nodes, a.pts4, a.outer, q, a.metric, a.approx != 0, a.e_inv, st, vis);
+        traverse_packed<T, DIM, FAST, kPrimeBound>(a.nodes, a.pts4, a.outer, q, a.metric, a.approx != 0, a.e_inv, st, vis,
+                                                   (int)a.n_points, a.k);
       }
       vis.store(out);
     }
@@ -160,16 +164,16 @@ __global__ void __launch_bounds__(kThreadsPerBlock) radius_thread_kernel(RadiusA
       vis.radius = r.radius;
       vis.out = r.hits + r.offsets[qi];
       if (DEEP)
-        traverse_packed<T, DIM, false, false>(a.nodes, a.pts4, a.outer, q, a.metric, a.approx != 0, a.e_inv, gst, vis);
+        traverse_packed<T, DIM, false, kPrimeNone>(a.nodes, a.pts4, a.outer, q, a.metric, a.approx != 0, a.e_inv, gst, vis);
       else
-        traverse_packed<T, DIM, false, false>(a.nodes, a.pts4, a.outer, q, a.metric, a.approx != 0, a.e_inv, lst, vis);
+        traverse_packed<T, DIM, false, kPrimeNone>(a.nodes, a.pts4, a.outer, q, a.metric, a.approx != 0, a.e_inv, lst, vis);
     } else {
       VisitRadiusCount<T> vis;
       vis.radius = r.radius;
       if (DEEP)
-        traverse_packed<T, DIM, false, false>(a.nodes, a.pts4, a.outer, q, a.metric, a.approx != 0, a.e_inv, gst, vis);
+        traverse_packed<T, DIM, false, kPrimeNone>(a.nodes, a.pts4, a.outer, q, a.metric, a.approx != 0, a.e_inv, gst, vis);
       else
-        traverse_packed<T, DIM, false, false>(a.nodes, a.pts4, a.outer, q, a.metric, a.approx != 0, a.e_inv, lst, vis);
+        traverse_packed<T, DIM, false, kPrimeNone>(a.nodes, a.pts4, a.outer, q, a.metric, a.approx != 0, a.e_inv, lst, vis);
       r.counts[qi] = vis.count;
     }
   }
@@ -550,6 +554,7 @@ void fill_base(KnnArgs<T>& a, const pico_b200_tree* t, const T* d_q, size_t d_st
   a.out = nullptr;
   a.k = 0;
   a.sdim = (int)t->sdim;
+  a.n_points = (uint32_t)t->n;
   a.metric = t->metric;
   a.approx = e > 0;
   a.e_inv = e > 0 ? T(1.0) / T(e) : T(1.0);  // search_visitor.hpp:173,216,265

@@ -228,13 +228,30 @@ struct GlobalStack {
 // Equivalence: the second walk makes the same near/far choices, visits the far children in
 // the same (deepest-first) order, tests them against a max() that is never larger than
 // the one the reference sees, and skips the already scanned first leaf.
-template <typename T, int DIM, bool FAST, bool PRIME, typename Stack, typename Visitor>
+//
+// PRIME == 2 (exact search, k > 1): a k-list stays "infinite" until k points were seen, i.e. for
+// the whole first descent and the first leaf or two — the same ~25 unconditional frames per
+// query (3.9 GB of stack traffic per launch at k = 16, a third of the kernel's stall samples).
+// Here the first descent (again without frames) only locates the first leaf; the largest
+// distance among k consecutive stored points around it (leaf order keeps them spatially close)
+// is an upper bound B of the final k-th distance, and the real traversal starts from the root
+// pruning with min(max(), B). Nothing is inserted out of order. A node dropped by B but visited
+// by the reference holds only points farther than B >= the final k-th distance: none of them
+// survives in the reference's list, and removing such points from the visit sequence changes
+// neither the final members nor their order (insert_sorted is stable). Not used for the
+// approximate visitors, whose lists are not the true k nearest, nor for metric_lpinf / metric_lninf,
+// nor for trees deeper than the local stack (the rounding margin of the bound assumes depth < 64).
+constexpr int kPrimeNone = 0, kPrimeFirstLeaf = 1, kPrimeBound = 2;
+
+template <typename T, int DIM, bool FAST, int PRIME, typename Stack, typename Visitor>
 __device__ __forceinline__ void traverse_packed(const typename NodeOf<T>::type* __restrict__ nodes,
                                                 const typename Vec4Of<T>::type* __restrict__ pts4,
                                                 const T* __restrict__ outer, const T (&q)[DIM], int metric_rt,
-                                                bool approx_rt, T e_inv, Stack& stack, Visitor& vis) {
+                                                bool approx_rt, T e_inv, Stack& stack, Visitor& vis,
+                                                int n_points = 0, int k = 0) {
   const int metric = FAST ? (int)PICO_B200_METRIC_L2_SQUARED : metric_rt;
   const bool approx = FAST ? false : approx_rt;
+  T bound = Limits<T>::max();
   T off[DIM];
 #pragma unroll
   for (int j = 0; j < DIM; ++j) off[j] = T(0);
@@ -242,7 +259,11 @@ __device__ __forceinline__ void traverse_packed(const typename NodeOf<T>::type* 
   T node_dist = T(0);
   int sp = 0;
   uint32_t primed_leaf = 0xFFFFFFFEu;
-  if (PRIME) {
+  // (the bound needs box distances that are true lower bounds of the point distances: the reference sums
+  // per-dimension offsets for every metric, which over-estimates under metric_lpinf / metric_lninf — there
+  // its pruning is part of the result and must be reproduced exactly)
+  const bool bound_ok = metric != PICO_B200_METRIC_LPINF && metric != PICO_B200_METRIC_LNINF;
+  if (PRIME == kPrimeFirstLeaf || (PRIME == kPrimeBound && bound_ok && !approx && k > 1 && n_points >= k)) {
     T a, b;
     uint32_t right, sd;
     int lb, le;
@@ -258,18 +279,42 @@ __device__ __forceinline__ void traverse_packed(const typename NodeOf<T>::type* 
       node = go_left ? node + 1 : right;
       load_node(nodes, node, a, b, right, sd, lb, le);
     }
-    for (int i = lb; i < le; ++i) {
-      const typename Vec4Of<T>::type p = ldg4(pts4 + i);
-      T d = metric_init<T>(metric);
-      d = metric_fold(metric, d, q[0], p.x, 0);
-      if (DIM > 1) d = metric_fold(metric, d, q[DIM > 1 ? 1 : 0], p.y, 1);
-      if (DIM > 2) d = metric_fold(metric, d, q[DIM > 2 ? 2 : 0], p.z, 2);
-      if (approx) d = mul_rn(d, e_inv);
-      vis.visit(index_of(p), d);
+    if (PRIME == kPrimeFirstLeaf) {
+      for (int i = lb; i < le; ++i) {
+        const typename Vec4Of<T>::type p = ldg4(pts4 + i);
+        T d = metric_init<T>(metric);
+        d = metric_fold(metric, d, q[0], p.x, 0);
+        if (DIM > 1) d = metric_fold(metric, d, q[DIM > 1 ? 1 : 0], p.y, 1);
+        if (DIM > 2) d = metric_fold(metric, d, q[DIM > 2 ? 2 : 0], p.z, 2);
+        if (approx) d = mul_rn(d, e_inv);
+        vis.visit(index_of(p), d);
+      }
+      primed_leaf = node;
+    } else {
+      // k consecutive stored points centred on the first leaf
+      int s = lb - (k - (le - lb)) / 2;
+      s = s < 0 ? 0 : (s > n_points - k ? n_points - k : s);
+      T far = T(0);
+      for (int i = s; i < s + k; ++i) {
+        const typename Vec4Of<T>::type p = ldg4(pts4 + i);
+        T d = metric_init<T>(metric);
+        d = metric_fold(metric, d, q[0], p.x, 0);
+        if (DIM > 1) d = metric_fold(metric, d, q[DIM > 1 ? 1 : 0], p.y, 1);
+        if (DIM > 2) d = metric_fold(metric, d, q[DIM > 2 ? 2 : 0], p.z, 2);
+        far = d > far ? d : far;
+      }
+      // far_dist values are sums built with one rounding per tree level and can exceed the exact
+      // box distance by a few ulps; a point that IS the bound (the window may reach into the far
+      // node) must not lose its own node to that: widen by 1024 eps >> 2 * depth * eps (depth < 64)
+      bound = add_rn(far, mul_rn(far, sizeof(T) == 4 ? T(1.2207031e-4) : T(2.2737368e-13)));
     }
-    primed_leaf = node;
     node = 0;
   }
+  // max() of the visitor, capped by the primed bound
+  auto reach = [&]() -> T {
+    const T m = vis.max();
+    return (PRIME == kPrimeBound && bound < m) ? bound : m;
+  };
   for (;;) {
     // ---- descend to a leaf (kd_tree_search.hpp:60-88)
     T a, b;
@@ -294,7 +339,7 @@ __device__ __forceinline__ void traverse_packed(const typename NodeOf<T>::type* 
       const T far_dist = add_rn(sub_rn(node_dist, old), new_off);
       // The reference tests `visitor.max() >= dist` after the near subtree; max() never
       // grows, so a far child that already fails now can be dropped without a push.
-      if (vis.max() >= far_dist) {
+      if (reach() >= far_dist) {
         T snap[DIM];
 #pragma unroll
         for (int j = 0; j < DIM; ++j) snap[j] = (sd == (uint32_t)j) ? new_off : off[j];
@@ -304,7 +349,7 @@ __device__ __forceinline__ void traverse_packed(const typename NodeOf<T>::type* 
       load_node(nodes, node, a, b, right, sd, lb, le);
     }
     // ---- leaf scan (kd_tree_search.hpp:54-59): contiguous Vec4 records, index in .w
-    if (PRIME && node == primed_leaf) le = lb;
+    if (PRIME == kPrimeFirstLeaf && node == primed_leaf) le = lb;
     for (int i = lb; i < le; ++i) {
       const typename Vec4Of<T>::type p = ldg4(pts4 + i);
       T d = metric_init<T>(metric);
@@ -322,7 +367,7 @@ __device__ __forceinline__ void traverse_packed(const typename NodeOf<T>::type* 
       uint32_t n;
       T snap[DIM];
       stack.pop(sp, n, d, snap);
-      if (vis.max() >= d) {
+      if (reach() >= d) {
         node = n;
         node_dist = d;
 #pragma unroll
