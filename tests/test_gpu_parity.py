@@ -178,6 +178,32 @@ def test_uniform_vs_oracle(pt, oracle, n, sdim, leaf):
         assert np.array_equal(np.sort(a), np.sort(b))
 
 
+@pytest.mark.parametrize("leaf", [1, 2, 10])
+def test_exact_knn_bound_priming_stress(pt, oracle, leaf):
+    """k > 1 exact search prunes with an upper bound taken from stored points next to the first leaf
+    (traverse.cuh, kPrimeBound). Worst cases for it: one-point leaves (the bound point's own node is a
+    far child), queries that coincide with tree points, duplicated points, planes of equal coordinates,
+    k from 2 to 16 — answers must still be those of the reference traversal."""
+    rng = np.random.default_rng(100 + leaf)
+    for sdim in (2, 3):
+        pts = rng.random((60_000, sdim)).astype(np.float32)
+        pts[:5_000, 0] = 0.25                      # a plane
+        pts[5_000:7_000] = pts[7_000:9_000]        # exact duplicates
+        pts[9_000:12_000] = np.round(pts[9_000:12_000] * 64) / 64   # lattice: many equal distances
+        q = np.concatenate([pts[rng.integers(0, len(pts), 15_000)],            # on tree points
+                            rng.random((15_000, sdim), dtype=np.float32),
+                            (np.round(rng.random((5_000, sdim)) * 64) / 64).astype(np.float32)])
+        q = np.ascontiguousarray(q.astype(np.float32))
+        o = oracle.OracleTree(pts, leaf)
+        t = pt.KdTree(pts, pt.Metric.L2Squared, leaf)
+        for k in (2, 3, 7, 16):
+            want = o.search_knn(q, k, threads=oracle.max_threads())
+            assert_knn_parity(t.search_knn(q, k), want, pts, q)
+        t1 = pt.KdTree(pts, pt.Metric.L1, leaf)
+        o1 = oracle.OracleTree(pts, leaf, metric="l1")
+        assert_knn_parity(t1.search_knn(q, 5), o1.search_knn(q, 5, threads=oracle.max_threads()), pts, q, "l1")
+
+
 def test_lidar_shape_vs_oracle(pt, oracle):
     """cfg2's cloud at a size the oracle finishes in seconds: slides in both directions, deep tree."""
     from pico_tree_b200 import datasets as D
