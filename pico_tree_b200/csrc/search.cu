@@ -367,8 +367,9 @@ struct CallCtx {
     for (auto& e : ev) PICO_CUDA(cudaEventCreate(&e));
     return 0;
   }
+  bool timed = true;  // record the five stage events (search stats)
   int mark(int i) {
-    if (!async) PICO_CUDA(cudaEventRecord(ev[i], st));
+    if (!async && timed) PICO_CUDA(cudaEventRecord(ev[i], st));
     return 0;
   }
   // brackets a traversal kernel when the thread is profiling
@@ -487,6 +488,19 @@ struct PinnedMirror {
   }
 };
 thread_local PinnedMirror g_pin_in, g_pin_out;
+
+// Small batches from host memory (the reference's one-query-per-call loops end up here): the
+// queries are written into a pinned, device-mapped buffer that the kernel reads and writes over
+// PCIe directly — no allocation, no copy calls, no events; one launch and one synchronisation.
+constexpr size_t kSmallQueryBytes = 16 * 1024, kSmallResultBytes = 48 * 1024;
+struct SmallBuffer {
+  void* p = nullptr;  // kSmallQueryBytes of queries, then kSmallResultBytes of results
+  int ensure() {
+    if (!p) PICO_CUDA(cudaHostAlloc(&p, kSmallQueryBytes + kSmallResultBytes, cudaHostAllocMapped));
+    return 0;
+  }
+};
+thread_local SmallBuffer g_small;
 
 int copy_out(cudaStream_t st, void* h_dst, const void* d_src, size_t bytes) {
   if (bytes <= ((size_t)8 << 20)) {
@@ -928,6 +942,26 @@ int knn_batch(const pico_b200_tree* t, const T* q, size_t nq, size_t stride, siz
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
+    return 0;
+  }
+  // (k <= 32: larger lists use the output row as working memory, which must not sit across PCIe)
+  if (!on_device && !g_cfg.has_user_stream && !g_cfg.profiling && k <= 32 &&
+      nq * t->sdim * sizeof(T) <= kSmallQueryBytes && nq * k * sizeof(Neighbor<T>) <= kSmallResultBytes) {
+    PICO_TRY(g_small.ensure());
+    T* mq = static_cast<T*>(g_small.p);
+    Neighbor<T>* mout = reinterpret_cast<Neighbor<T>*>(static_cast<char*>(g_small.p) + kSmallQueryBytes);
+    for (size_t i = 0; i < nq; ++i) memcpy(mq + i * t->sdim, q + i * stride, t->sdim * sizeof(T));
+    CallCtx c;
+    PICO_TRY(c.init(t->device));
+    c.timed = stats != nullptr;
+    PICO_TRY(knn_enqueue<T>(c, t, mq, nq, t->sdim, k, e, mout, flags | PICO_B200_NO_REORDER, true, &launches));
+    PICO_CUDA(cudaStreamSynchronize(c.st));
+    memcpy(out, mout, nq * k * sizeof(Neighbor<T>));
+    if (stats) {
+      stats->h2d_ms = stats->d2h_ms = stats->reorder_ms = 0;
+      stats->kernel_ms = elapsed(c.ev[2], c.ev[3]);
+      stats->kernel_launches = launches;
+    }
     return 0;
   }
   CallCtx c;
