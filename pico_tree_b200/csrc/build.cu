@@ -753,26 +753,56 @@ __device__ void median_node(const BuildState<T>& s, uint32_t node_id) {
   const T* col = s.raw + sd;
   int32_t* idx = s.idx;
   const int kth = cnt / 2;  // rank of the split element inside [begin, end)
-  // bitwise radix select on the order-preserving key, MSB first
+  // radix select on the order-preserving key, 8 bits per pass, MSB first: a 256-bin histogram of
+  // the keys that still match the prefix, then the bin that holds rank `rank`
   constexpr int kBits = sizeof(T) * 8;
+  __shared__ int s_hist_all[(G == 32 ? 8 : 1) * 256];
+  __shared__ unsigned s_pick_all[(G == 32 ? 8 : 1) * 2];
+  int* hist = s_hist_all + (G == 32 ? (threadIdx.x >> 5) * 256 : 0);
+  unsigned* pick = s_pick_all + (G == 32 ? (threadIdx.x >> 5) * 2 : 0);
   unsigned long long prefix = 0, mask = 0;
   int rank = kth;
-  for (int b = kBits - 1; b >= 0; --b) {
-    const unsigned long long bit = 1ull << b;
-    int zeros = 0;
+  for (int shift = kBits - 8; shift >= 0; shift -= 8) {
+    for (int b = tid; b < 256; b += G) hist[b] = 0;
+    Grp<G>::sync();
     for (int base = begin; base < end; base += G) {
       const int i = base + tid;
       if (i < end) {
         const unsigned long long key = order_bits<T>(col[(size_t)idx[i] * sdim]);
-        zeros += ((key & mask) == prefix) && !(key & bit);
+        if ((key & mask) == prefix) atomicAdd(&hist[(unsigned)(key >> shift) & 255u], 1);
       }
     }
-    zeros = Grp<G>::sum(zeros);
-    if (rank >= zeros) {
-      rank -= zeros;
-      prefix |= bit;
+    Grp<G>::sync();
+    if (tid < 32) {
+      // lane l owns bins [8l, 8l + 8)
+      int local[8], sum = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        local[j] = hist[tid * 8 + j];
+        sum += local[j];
+      }
+      int incl = sum;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (tid >= o) incl += v;
+      }
+      int before = incl - sum;
+      if (rank >= before && rank < incl) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (rank >= before && rank < before + local[j]) {
+            pick[0] = (unsigned)(tid * 8 + j);
+            pick[1] = (unsigned)(rank - before);
+          }
+          before += local[j];
+        }
+      }
     }
-    mask |= bit;
+    Grp<G>::sync();
+    prefix |= (unsigned long long)pick[0] << shift;
+    mask |= 255ull << shift;
+    rank = (int)pick[1];
+    Grp<G>::sync();
   }
   // prefix is now the key of the kth element; `rank` = how many equal keys belong left of it
   // stable three-way arrangement into tmp, then copy back
