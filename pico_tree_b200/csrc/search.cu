@@ -1231,8 +1231,19 @@ int box_batch(const pico_b200_tree* t, const T* mins, const T* maxs, size_t nb, 
   PICO_CUDA(cudaEventRecord(c.ev[0], c.st));
   const T *d_min = nullptr, *d_max = nullptr;
   size_t d_stride = 0;
-  PICO_TRY(stage_queries(c, mins, nb, stride, t->sdim, on_device, &d_min, &d_stride));
-  PICO_TRY(stage_queries(c, maxs, nb, stride, t->sdim, on_device, &d_max, &d_stride));
+  if (!on_device && maxs == mins + t->sdim && stride == 2 * t->sdim) {
+    // (min, max) row pairs of one array — the layout of the reference's binding
+    // (_pyco_tree/kd_tree.hpp:240-268): one contiguous copy instead of two strided ones
+    T* buf = nullptr;
+    PICO_TRY(c.alloc(reinterpret_cast<void**>(&buf), nb * stride * sizeof(T)));
+    PICO_CUDA(cudaMemcpyAsync(buf, mins, nb * stride * sizeof(T), cudaMemcpyHostToDevice, c.st));
+    d_min = buf;
+    d_max = buf + t->sdim;
+    d_stride = stride;
+  } else {
+    PICO_TRY(stage_queries(c, mins, nb, stride, t->sdim, on_device, &d_min, &d_stride));
+    PICO_TRY(stage_queries(c, maxs, nb, stride, t->sdim, on_device, &d_max, &d_stride));
+  }
   PICO_CUDA(cudaEventRecord(c.ev[1], c.st));
   PICO_CUDA(cudaEventRecord(c.ev[2], c.st));
 

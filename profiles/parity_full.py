@@ -1,0 +1,36 @@
+"""Full-size parity of knn=16 / knn=4 on cfg2 with the REFERENCE'S OWN TREE uploaded (kd_tree::save stream ->
+pico_b200_tree_load): node-for-node and leaf-order identical trees, so every index must match, ties included.
+Separates traversal equivalence (this script must report 0 mismatches) from the tie-class differences a
+device-built tree may show after slides."""
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import pico_tree_b200 as pt  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+from pico_tree_b200 import datasets as D  # noqa: E402
+
+tree_pts, q = D.bench_clouds()
+ref = O.RefTree(tree_pts, 10)
+with tempfile.TemporaryDirectory() as d:
+    f = os.path.join(d, "ref.pkd")
+    name = b"L2Squared"
+    open(f, "wb").write(b"\x89PKD" + (1).to_bytes(4, "little") + len(name).to_bytes(8, "little") + name + ref.saved())
+    loaded = pt.load_kd_tree(tree_pts, f)
+built = pt.KdTree(tree_pts, pt.Metric.L2Squared, 10)
+for k in (16, 4, 1):
+    want = ref.search_knn(q, k, threads=O.max_threads())
+    for label, tree in (("reference tree uploaded", loaded), ("device-built tree", built)):
+        got = tree.search_knn(q, k)
+        same_d = bool(np.array_equal(got["distance"], want["distance"]))
+        diff = got["index"] != want["index"]
+        rows = np.unique(np.nonzero(diff)[0])
+        # a mismatch is a tie iff the row holds the same multiset of (distance) and the differing slots carry equal distances
+        tie_like = all(np.array_equal(np.sort(got["index"][r]), np.sort(want["index"][r])) or
+                       got["distance"][r][-1] == want["distance"][r][-1] for r in rows[:1000])
+        print(f"k={k:2d} {label:26s}: distances bit-equal {same_d}, index mismatches {int(diff.sum())} in {len(rows)} rows"
+              f"{' (all tie-class)' if len(rows) and tie_like else ''}", flush=True)

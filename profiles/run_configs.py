@@ -122,7 +122,7 @@ def cfg2s():
 
 def cfg3a():
     tree_pts, q = D.bench_clouds()
-    return knn_line("cfg3 knn=16", tree_pts, q, 16, cpu_sample=500_000, reps=10)
+    return knn_line("cfg3 knn=16", tree_pts, q, 16, cpu_sample=len(q), reps=10)
 
 
 def cfg3b():
@@ -140,7 +140,7 @@ def cfg3b():
     hits = int(nns._offsets[-1])
     ref, kind = cpu_tree(tree_pts)
     threads = O.max_threads()
-    ns = 300_000
+    ns = 1_000_000
     qs = np.ascontiguousarray(q[:ns])
     t0 = time.perf_counter()
     offs, flat = ref.search_radius(qs, r2)
@@ -156,6 +156,35 @@ def cfg3b():
             "cpu": {"kind": kind, "threads": 1, "sample": ns, "mqs_one_thread": ns / cpu_s / 1e6,
                     "note": "the reference's radius loop is serial in oracle/ref_driver.cpp"},
             "parity": {"queries": ns, "hit_counts_equal": same_counts, "sorted_distances_equal": same_dist}}
+
+
+def cfgbox():
+    """search_box on the cfg2 cloud: 1M axis-aligned boxes of 0.4 m edge centred on query points."""
+    tree_pts, q = D.bench_clouds()
+    tree = pt.KdTree(tree_pts, pt.Metric.L2Squared, 10)
+    nb = 1_000_000
+    boxes = np.empty((2 * nb, 3), np.float32)
+    boxes[0::2] = q[:nb] - np.float32(0.2)
+    boxes[1::2] = q[:nb] + np.float32(0.2)
+    box = {}
+
+    def run():
+        box["r"] = tree.search_box(boxes)
+    e2e_s = timed(run, 3)
+    res = box["r"]
+    st = tree.last_stats
+    ref, kind = cpu_tree(tree_pts)
+    ns = 100_000
+    t0 = time.perf_counter()
+    offs, flat = ref.search_box(np.ascontiguousarray(boxes[0:2 * ns:2]), np.ascontiguousarray(boxes[1:2 * ns:2]))
+    cpu_s = time.perf_counter() - t0
+    same_counts = bool(np.array_equal(res._offsets[:ns + 1], offs))
+    same_order = bool(same_counts and np.array_equal(res._flat[:int(offs[-1])], flat))
+    return {"config": "search_box, 1M boxes of 0.4 m edge on the cfg2 cloud", "n_tree": len(tree_pts), "n_boxes": nb,
+            "mean_hits_per_box": int(res._offsets[-1]) / nb, "e2e_mboxes_s": nb / e2e_s / 1e6, "e2e_ms": e2e_s * 1e3,
+            "device_ms": {"h2d": st.h2d_ms, "count+scan+fill": st.kernel_ms, "d2h": st.d2h_ms},
+            "cpu": {"kind": kind, "threads": 1, "sample": ns, "mboxes_s_one_thread": ns / cpu_s / 1e6},
+            "parity": {"boxes": ns, "hit_counts_equal": same_counts, "indices_equal_in_dfs_order": same_order}}
 
 
 def cfg4():
@@ -214,8 +243,8 @@ def build():
 
 
 def main():
-    want = sys.argv[1:] or ["cfg1", "cfg2s", "cfg3a", "cfg3b", "cfg4", "build"]
-    fns = {"cfg1": cfg1, "cfg2s": cfg2s, "cfg3a": cfg3a, "cfg3b": cfg3b, "cfg4": cfg4, "build": build}
+    want = sys.argv[1:] or ["cfg1", "cfg2s", "cfg3a", "cfg3b", "cfgbox", "cfg4", "build"]
+    fns = {"cfg1": cfg1, "cfg2s": cfg2s, "cfg3a": cfg3a, "cfg3b": cfg3b, "cfgbox": cfgbox, "cfg4": cfg4, "build": build}
     for w in want:
         r = fns[w]()
         for line in (r if isinstance(r, list) else [r]):
