@@ -19,10 +19,9 @@
 // The index array is partitioned in place exactly like libstdc++'s std::partition would
 // leave it (the j-th misplaced element from the left is exchanged with the j-th misplaced
 // element from the right), so the order inside a leaf — which decides which of two
-// equidistant points a query reports — matches the reference wherever no slide happened.
-// A slide moves the extreme element next to the split by a single exchange; libstdc++'s
-// nth_element would additionally shuffle the remainder (tie-class difference only,
-// DESIGN.md §6).
+// equidistant points a query reports — matches the reference. Slides and the median rule call
+// std::nth_element in the reference; group_nth_element emulates libstdc++'s introselect exactly,
+// so the index permutation (and with it the saved stream) is identical to the reference's.
 #include <cub/cub.cuh>
 
 #include <algorithm>
@@ -86,6 +85,7 @@ struct BuildState {
   int32_t sdim;
   int32_t* idx;        // [n]
   int32_t* tmp;        // [n] scratch for the partition
+  int32_t* tmp2;       // [n] second scratch list (nth_element emulation)
   BNode<T>* nodes;     // BFS table
   T* boxes;            // [cap][2*sdim]: cut box on the way down, tight box on the way up
   uint32_t* counters;  // [0] n_nodes  [1] n_big_next  [2] n_leaves  [3] n_huge_next  [4] chunks of this level  [5] largest leaf
@@ -294,6 +294,176 @@ __device__ void emit_children(const BuildState<T>& s, uint32_t node_id, int sd, 
   }
 }
 
+// ------------------------------------------------------------------ std::nth_element, exactly
+// The reference calls std::nth_element in the slide cases of the sliding midpoint rule
+// (kd_tree_builder.hpp:255-275) and for every node of the median rule (:167-173). Which index ends
+// up where — beyond the n-th position itself — is decided by libstdc++'s introselect (GCC 13
+// bits/stl_algo.h: median-of-three pivot, unguarded Hoare partition, insertion sort below four
+// elements, heap select when the depth limit runs out), and the order of the indices inside a leaf
+// decides which of two equidistant points a query reports. The emulation below leaves the index
+// range in exactly that state. The Hoare partition is the only O(n) step and is data-parallel: the
+// j-th element from the left that is >= pivot is exchanged with the j-th element from the right
+// that is <= pivot for all j < m, where m counts the pairs whose left position is still smaller
+// than the right one; the cut follows from the two position lists (tests/test_oracle_golden.py
+// holds the sequential restatement this was checked against; tests/test_gpu_parity.py compares the
+// resulting permutations with the reference's fixtures).
+template <typename T>
+struct NthCtx {
+  const T* col;  // coordinate `split_dim` of point p is col[p * sdim]
+  int32_t* idx;
+  int sdim;
+  __device__ __forceinline__ T at(int pos) const { return col[(size_t)idx[pos] * sdim]; }
+  __device__ __forceinline__ bool less(int a, int b) const { return at(a) < at(b); }  // positions
+  __device__ __forceinline__ void swap(int a, int b) const {
+    const int32_t t = idx[a];
+    idx[a] = idx[b];
+    idx[b] = t;
+  }
+};
+
+// sequential pieces (one thread): std::__move_median_to_first, std::__insertion_sort, std::__heap_select
+template <typename T>
+__device__ void seq_move_median_to_first(const NthCtx<T>& c, int result, int a, int b, int cc) {
+  int pick;
+  if (c.less(a, b)) {
+    if (c.less(b, cc))
+      pick = b;
+    else if (c.less(a, cc))
+      pick = cc;
+    else
+      pick = a;
+  } else if (c.less(a, cc)) {
+    pick = a;
+  } else if (c.less(b, cc)) {
+    pick = cc;
+  } else {
+    pick = b;
+  }
+  c.swap(result, pick);
+}
+
+template <typename T>
+__device__ void seq_insertion_sort(const NthCtx<T>& c, int first, int last) {
+  for (int i = first + 1; i < last; ++i) {
+    const int32_t val = c.idx[i];
+    const T v = c.col[(size_t)val * c.sdim];
+    int j = i;
+    if (v < c.at(first)) {
+      for (; j > first; --j) c.idx[j] = c.idx[j - 1];
+    } else {
+      while (v < c.at(j - 1)) {
+        c.idx[j] = c.idx[j - 1];
+        --j;
+      }
+    }
+    c.idx[j] = val;
+  }
+}
+
+template <typename T>
+__device__ void seq_adjust_heap(const NthCtx<T>& c, int first, int hole, int len, int32_t value) {
+  const int top = hole;
+  int child = hole;
+  auto key = [&](int32_t id) { return c.col[(size_t)id * c.sdim]; };
+  while (child < (len - 1) / 2) {
+    child = 2 * (child + 1);
+    if (c.less(first + child, first + child - 1)) child--;
+    c.idx[first + hole] = c.idx[first + child];
+    hole = child;
+  }
+  if ((len & 1) == 0 && child == (len - 2) / 2) {
+    child = 2 * (child + 1);
+    c.idx[first + hole] = c.idx[first + child - 1];
+    hole = child - 1;
+  }
+  int parent = (hole - 1) / 2;  // std::__push_heap
+  while (hole > top && key(c.idx[first + parent]) < key(value)) {
+    c.idx[first + hole] = c.idx[first + parent];
+    hole = parent;
+    parent = (hole - 1) / 2;
+  }
+  c.idx[first + hole] = value;
+}
+
+template <typename T>
+__device__ void seq_heap_select(const NthCtx<T>& c, int first, int middle, int last) {
+  const int len = middle - first;
+  if (len >= 2) {  // std::__make_heap
+    for (int parent = (len - 2) / 2;; --parent) {
+      seq_adjust_heap(c, first, parent, len, c.idx[first + parent]);
+      if (parent == 0) break;
+    }
+  }
+  for (int i = middle; i < last; ++i) {
+    if (c.less(i, first)) {  // std::__pop_heap(first, middle, i)
+      const int32_t value = c.idx[i];
+      c.idx[i] = c.idx[first];
+      seq_adjust_heap(c, first, 0, len, value);
+    }
+  }
+}
+
+// std::nth_element(first, nth, last) on positions of s.idx, by the whole group
+template <typename T, int G>
+__device__ void group_nth_element(const BuildState<T>& s, int sd, int first, int nth, int last) {
+  if (first == last || nth == last) return;
+  const int tid = Grp<G>::tid();
+  NthCtx<T> c{s.raw + sd, s.idx, s.sdim};
+  int32_t* lst_l = s.tmp;   // positions of elements >= pivot, ascending, at [lo, lo + n_l)
+  int32_t* lst_r = s.tmp2;  // positions of elements <= pivot, descending, at (hi - 1 - n_r, hi - 1]
+  int depth_limit = 2 * (31 - __clz(last - first));
+  while (last - first > 3) {
+    if (depth_limit == 0) {
+      if (tid == 0) {
+        seq_heap_select(c, first, nth + 1, last);
+        c.swap(first, nth);
+      }
+      Grp<G>::sync();
+      return;
+    }
+    --depth_limit;
+    if (tid == 0) seq_move_median_to_first(c, first, first + 1, first + (last - first) / 2, last - 1);
+    Grp<G>::sync();
+    const T pv = c.at(first);
+    const int lo = first + 1, hi = last;
+    int n_l = 0, n_r = 0;
+    for (int base = lo; base < hi; base += G) {
+      const int i = base + tid;
+      const int f = (i < hi) && !(c.at(i) < pv);
+      int tot;
+      const int ex = Grp<G>::excl(f, tot);
+      if (f) lst_l[lo + n_l + ex] = i;
+      n_l += tot;
+    }
+    for (int base = 0; base < hi - lo; base += G) {
+      const int i = hi - 1 - (base + tid);
+      const int f = (i >= lo) && !(pv < c.at(i));
+      int tot;
+      const int ex = Grp<G>::excl(f, tot);
+      if (f) lst_r[hi - 1 - (n_r + ex)] = i;
+      n_r += tot;
+    }
+    Grp<G>::sync();
+    const int pairs = n_l < n_r ? n_l : n_r;
+    int cnt = 0;
+    for (int j = tid; j < pairs; j += G) cnt += lst_l[lo + j] < lst_r[hi - 1 - j];
+    const int m = Grp<G>::sum(cnt);
+    for (int j = tid; j < m; j += G) c.swap(lst_l[lo + j], lst_r[hi - 1 - j]);
+    int cut;
+    if (m < n_l && (m == 0 || lst_l[lo + m] < lst_r[hi - 1 - (m - 1)]))
+      cut = lst_l[lo + m];
+    else
+      cut = lst_r[hi - 1 - (m - 1)];
+    Grp<G>::sync();
+    if (cut <= nth)
+      first = cut;
+    else
+      last = cut;
+  }
+  if (tid == 0) seq_insertion_sort(c, first, last);
+  Grp<G>::sync();
+}
+
 template <typename T, int G>
 __device__ void process_node(const BuildState<T>& s, uint32_t node_id) {
   BNode<T>& nd = s.nodes[node_id];
@@ -339,61 +509,13 @@ __device__ void process_node(const BuildState<T>& s, uint32_t node_id) {
     nl = Grp<G>::sum(nl);
     split = begin + nl;
 
-    if (s.rule == PICO_B200_RULE_SLIDING_MIDPOINT_MAX_SIDE && nl == cnt) {
-      // all left: the largest coordinate slides right (kd_tree_builder.hpp:255-264)
-      // among equal maxima the LAST one moves (what a stable insertion of the tail gives,
-      // i.e. libstdc++'s nth_element on short ranges); positions are negated so that the
-      // "lower position wins" tie rule of arg_extreme picks the highest index
-      T v = -Limits<T>::max();
-      int p = 0x7fffffff;
-      for (int i = begin + tid; i < end; i += G) {
-        const T x = col[(size_t)idx[i] * sdim];
-        if (x >= v) {
-          v = x;
-          p = -i;
-        }
-      }
-      Grp<G>::template arg_extreme<T, true>(v, p);
-      p = -p;
-      if (tid == 0) {
-        const int32_t a = idx[p];
-        idx[p] = idx[end - 1];
-        idx[end - 1] = a;
-      }
-      split = end - 1;
-      split_val = v;
-      Grp<G>::sync();
-    } else if (s.rule == PICO_B200_RULE_SLIDING_MIDPOINT_MAX_SIDE && nl == 0) {
-      // all right: the smallest coordinate slides left; split_val becomes the second
-      // smallest coordinate (kd_tree_builder.hpp:265-275)
-      T v = Limits<T>::max();
-      int p = 0x7fffffff;
-      for (int i = begin + tid; i < end; i += G) {
-        const T x = col[(size_t)idx[i] * sdim];
-        if (x < v) {
-          v = x;
-          p = i;
-        }
-      }
-      Grp<G>::template arg_extreme<T, false>(v, p);
-      if (tid == 0) {
-        const int32_t a = idx[p];
-        idx[p] = idx[begin];
-        idx[begin] = a;
-      }
-      Grp<G>::sync();
-      T v2 = Limits<T>::max();
-      int p2 = 0x7fffffff;
-      for (int i = begin + 1 + tid; i < end; i += G) {
-        const T x = col[(size_t)idx[i] * sdim];
-        if (x < v2) {
-          v2 = x;
-          p2 = i;
-        }
-      }
-      Grp<G>::template arg_extreme<T, false>(v2, p2);
-      split = begin + 1;
-      split_val = v2;
+    if (s.rule == PICO_B200_RULE_SLIDING_MIDPOINT_MAX_SIDE && (nl == cnt || nl == 0)) {
+      // Nothing has moved (std::partition found every point on one side). One point slides to the
+      // empty side: nth_element at the last / the second position, and the split value becomes the
+      // coordinate found there (kd_tree_builder.hpp:255-275).
+      split = (nl == cnt) ? end - 1 : begin + 1;
+      group_nth_element<T, G>(s, sd, begin, split, end);
+      split_val = col[(size_t)idx[split] * sdim];
     } else if (nl > 0 && nl < cnt) {
       // std::partition order: j-th misplaced from the left <-> j-th misplaced from the right
       int32_t* tmp = s.tmp;
@@ -617,26 +739,11 @@ __global__ void __launch_bounds__(32) huge_resolve(BuildState<T> s, int n_huge) 
   int split = hn.begin + nl;
   T split_val = hn.split_val;
   int mode = 0;
-  if (s.rule == PICO_B200_RULE_SLIDING_MIDPOINT_MAX_SIDE && nl == cnt) {
-    // all left: the largest coordinate slides right (kd_tree_builder.hpp:255-264)
-    if (lane == 0) {
-      const int32_t a = s.idx[ex.mx_pos];
-      s.idx[ex.mx_pos] = s.idx[hn.end - 1];
-      s.idx[hn.end - 1] = a;
-    }
-    split = hn.end - 1;
-    split_val = ex.mx;
-    mode = 1;
-  } else if (s.rule == PICO_B200_RULE_SLIDING_MIDPOINT_MAX_SIDE && nl == 0) {
-    // all right: the smallest slides left, split_val = second smallest (:265-275)
-    if (lane == 0) {
-      const int32_t a = s.idx[ex.mn_pos];
-      s.idx[ex.mn_pos] = s.idx[hn.begin];
-      s.idx[hn.begin] = a;
-    }
-    split = hn.begin + 1;
-    split_val = ex.mn2;
-    mode = 1;
+  if (s.rule == PICO_B200_RULE_SLIDING_MIDPOINT_MAX_SIDE && (nl == cnt || nl == 0)) {
+    // slide (kd_tree_builder.hpp:255-275): std::nth_element at the last / second position, done by a
+    // whole CTA in huge_slide
+    split = (nl == cnt) ? hn.end - 1 : hn.begin + 1;
+    mode = 2;
   } else if (nl == 0 || nl == cnt) {
     mode = 1;  // midpoint rule: one child is empty, nothing moves
   }
@@ -647,7 +754,18 @@ __global__ void __launch_bounds__(32) huge_resolve(BuildState<T> s, int n_huge) 
     hn.m = 0;
   }
   __syncwarp();
-  emit_children<T, 32>(s, hn.node, hn.sd, split, split_val);
+  if (mode != 2) emit_children<T, 32>(s, hn.node, hn.sd, split, split_val);
+}
+
+// one CTA per huge node that slides: exact nth_element, then the children
+template <typename T>
+__global__ void __launch_bounds__(kBigThreads) huge_slide(BuildState<T> s, int n_huge) {
+  const HugeNode<T>& hn = s.huge[blockIdx.x];
+  if (hn.mode != 2) return;
+  group_nth_element<T, kBigThreads>(s, hn.sd, hn.begin, hn.split, hn.end);
+  const T split_val = s.raw[(size_t)s.idx[hn.split] * s.sdim + hn.sd];
+  __syncthreads();
+  emit_children<T, kBigThreads>(s, hn.node, hn.sd, hn.split, split_val);
 }
 
 // grid = chunks: the two lists of misplaced positions (left list at tmp[begin + j], right list,
@@ -708,26 +826,9 @@ __global__ void __launch_bounds__(kChunkThreads) huge_swap(BuildState<T> s, int 
 }
 
 // ------------------------------------------------------------------ median rule
-// nth_element at the middle (kd_tree_builder.hpp:153-176): the split position is fixed, the
-// value is the (cnt/2)-th order statistic on split_dim. One warp per node: repeated
-// three-way narrowing on the value range (exact, works on the bit pattern order).
-// Membership among equal coordinates is libstdc++-defined in the reference; here elements
-// equal to split_val fill the left side in index-array order.
-template <typename T>
-__device__ __forceinline__ unsigned long long order_bits(T x);
-template <>
-__device__ __forceinline__ unsigned long long order_bits<float>(float x) {
-  unsigned u = __float_as_uint(x);
-  u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-  return u;
-}
-template <>
-__device__ __forceinline__ unsigned long long order_bits<double>(double x) {
-  unsigned long long u = (unsigned long long)__double_as_longlong(x);
-  u = (u & 0x8000000000000000ull) ? ~u : (u | 0x8000000000000000ull);
-  return u;
-}
-
+// nth_element at the middle (kd_tree_builder.hpp:153-176): the split position is fixed by the rule,
+// the value is the coordinate that ends up there; group_nth_element leaves the indices exactly
+// where libstdc++ would.
 template <typename T, int G>
 __device__ void median_node(const BuildState<T>& s, uint32_t node_id) {
   BNode<T>& nd = s.nodes[node_id];
@@ -752,106 +853,10 @@ __device__ void median_node(const BuildState<T>& s, uint32_t node_id) {
   }
   const T* col = s.raw + sd;
   int32_t* idx = s.idx;
-  const int kth = cnt / 2;  // rank of the split element inside [begin, end)
-  // radix select on the order-preserving key, 8 bits per pass, MSB first: a 256-bin histogram of
-  // the keys that still match the prefix, then the bin that holds rank `rank`
-  constexpr int kBits = sizeof(T) * 8;
-  __shared__ int s_hist_all[(G == 32 ? 8 : 1) * 256];
-  __shared__ unsigned s_pick_all[(G == 32 ? 8 : 1) * 2];
-  int* hist = s_hist_all + (G == 32 ? (threadIdx.x >> 5) * 256 : 0);
-  unsigned* pick = s_pick_all + (G == 32 ? (threadIdx.x >> 5) * 2 : 0);
-  unsigned long long prefix = 0, mask = 0;
-  int rank = kth;
-  for (int shift = kBits - 8; shift >= 0; shift -= 8) {
-    for (int b = tid; b < 256; b += G) hist[b] = 0;
-    Grp<G>::sync();
-    for (int base = begin; base < end; base += G) {
-      const int i = base + tid;
-      if (i < end) {
-        const unsigned long long key = order_bits<T>(col[(size_t)idx[i] * sdim]);
-        if ((key & mask) == prefix) atomicAdd(&hist[(unsigned)(key >> shift) & 255u], 1);
-      }
-    }
-    Grp<G>::sync();
-    if (tid < 32) {
-      // lane l owns bins [8l, 8l + 8)
-      int local[8], sum = 0;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        local[j] = hist[tid * 8 + j];
-        sum += local[j];
-      }
-      int incl = sum;
-      for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (tid >= o) incl += v;
-      }
-      int before = incl - sum;
-      if (rank >= before && rank < incl) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (rank >= before && rank < before + local[j]) {
-            pick[0] = (unsigned)(tid * 8 + j);
-            pick[1] = (unsigned)(rank - before);
-          }
-          before += local[j];
-        }
-      }
-    }
-    Grp<G>::sync();
-    prefix |= (unsigned long long)pick[0] << shift;
-    mask |= 255ull << shift;
-    rank = (int)pick[1];
-    Grp<G>::sync();
-  }
-  // prefix is now the key of the kth element; `rank` = how many equal keys belong left of it
-  // stable three-way arrangement into tmp, then copy back
-  int32_t* tmp = s.tmp;
-  int n_less = 0, n_eq = 0;
-  for (int base = begin; base < end; base += G) {
-    const int i = base + tid;
-    int lt = 0, eq = 0;
-    if (i < end) {
-      const unsigned long long key = order_bits<T>(col[(size_t)idx[i] * sdim]);
-      lt = key < prefix;
-      eq = key == prefix;
-    }
-    n_less += lt;
-    n_eq += eq;
-  }
-  n_less = Grp<G>::sum(n_less);
-  n_eq = Grp<G>::sum(n_eq);
-  int o_lt = 0, o_eq = 0, o_gt = 0;
-  T split_val = 0;
-  for (int base = begin; base < end; base += G) {
-    const int i = base + tid;
-    int lt = 0, eq = 0, gt = 0;
-    int32_t v = 0;
-    if (i < end) {
-      v = idx[i];
-      const T x = col[(size_t)v * sdim];
-      const unsigned long long key = order_bits<T>(x);
-      lt = key < prefix;
-      eq = key == prefix;
-      gt = key > prefix;
-      if (eq) split_val = x;
-    }
-    int t0, t1, t2;
-    const int e0 = Grp<G>::excl(lt, t0);
-    const int e1 = Grp<G>::excl(eq, t1);
-    const int e2 = Grp<G>::excl(gt, t2);
-    if (lt) tmp[begin + o_lt + e0] = v;
-    if (eq) tmp[begin + n_less + o_eq + e1] = v;
-    if (gt) tmp[begin + n_less + n_eq + o_gt + e2] = v;
-    o_lt += t0;
-    o_eq += t1;
-    o_gt += t2;
-  }
-  Grp<G>::sync();
-  for (int i = begin + tid; i < end; i += G) idx[i] = tmp[i];
-  Grp<G>::sync();
-  const int split = begin + kth;
-  split_val = col[(size_t)idx[split] * sdim];
+  // std::nth_element at the middle (kd_tree_builder.hpp:165-175), emulated exactly
+  const int split = begin + cnt / 2;
+  group_nth_element<T, G>(s, sd, begin, split, end);
+  const T split_val = col[(size_t)idx[split] * sdim];
   Grp<G>::sync();
   emit_children<T, G>(s, node_id, sd, split, split_val);
 }
@@ -1071,12 +1076,13 @@ int build_tree(pico_b200_tree* t, const T* h_pts, size_t stride, int rule, int s
     ~StreamGuard() { cudaStreamDestroy(s); }
   } guard{st};
 
-  DevBuf raw, tmp, nodes, boxes, counters, big_a, big_b, partial, huge_a, huge_b, huge_nodes, chunk_stats;
+  DevBuf raw, tmp, tmp2, nodes, boxes, counters, big_a, big_b, partial, huge_a, huge_b, huge_nodes, chunk_stats;
   PICO_TRY(alloc(raw, n * sdim * sizeof(T)));
   PICO_TRY(stage_points(h_pts, n, sdim, stride, raw.as<T>(), st));
   PICO_CUDA(cudaMalloc(&t->d_indices, n * sizeof(int32_t)));
   PICO_CUDA(cudaMalloc(&t->d_root_box, 2 * sdim * sizeof(T)));
   PICO_TRY(alloc(tmp, n * sizeof(int32_t)));
+  PICO_TRY(alloc(tmp2, n * sizeof(int32_t)));
 
   cudaEvent_t ev0, ev1;
   PICO_CUDA(cudaEventCreate(&ev0));
@@ -1137,6 +1143,7 @@ int build_tree(pico_b200_tree* t, const T* h_pts, size_t stride, int rule, int s
   s.sdim = sdim;
   s.idx = t->d_indices;
   s.tmp = tmp.as<int32_t>();
+  s.tmp2 = tmp2.as<int32_t>();
   s.nodes = nodes.as<BNode<T>>();
   s.boxes = boxes.as<T>();
   s.counters = counters.as<uint32_t>();
@@ -1218,6 +1225,7 @@ int build_tree(pico_b200_tree* t, const T* h_pts, size_t stride, int rule, int s
       huge_plan<T><<<1, 256, 0, st>>>(s, huge_cur, (int)n_huge);
       huge_count<T><<<chunk_grid, kChunkThreads, 0, st>>>(s, (int)n_huge);
       huge_resolve<T><<<n_huge, 32, 0, st>>>(s, (int)n_huge);
+      if (rule == PICO_B200_RULE_SLIDING_MIDPOINT_MAX_SIDE) huge_slide<T><<<n_huge, kBigThreads, 0, st>>>(s, (int)n_huge);
       huge_scatter<T><<<chunk_grid, kChunkThreads, 0, st>>>(s, (int)n_huge);
       huge_swap<T><<<chunk_grid, kChunkThreads, 0, st>>>(s, (int)n_huge);
     }
