@@ -492,6 +492,20 @@ def test_device_resident_ragged_results(pt):
     assert np.array_equal(gotb.cpu().numpy(), wantb._flat[:nb])
 
 
+def test_nth_element_heap_select_fallback(pt, oracle):
+    """Adversarial inputs (oracle/make_killers.py) push libstdc++'s introselect past its depth limit into
+    std::__heap_select; the device build's emulation must follow it there (warp and CTA flavours)."""
+    data = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "introselect_killers.npz"))
+    for key in data.files:
+        v = data[key]
+        pts = np.ascontiguousarray(np.stack([v, np.zeros_like(v)], axis=1))
+        o = oracle.OracleTree(pts, 10, rule="median")
+        t = pt.KdTree(pts, pt.Metric.L2Squared, 10, rule=pt.kd_tree.Rule.MedianMaxSide)
+        nodes, indices, _ = t.export()
+        assert np.array_equal(indices, o.indices), key
+        assert_same_structure(nodes_from_export(nodes, pts.dtype), o.nodes)
+
+
 def test_build_paths_agree(pt, monkeypatch):
     """The three ways a node can be split on the device — one warp, one CTA, grid-wide chunked passes
     (build.cu, PICO_B200_HUGE_MIN is the test hook for the threshold) — must leave the very same

@@ -164,3 +164,21 @@ def test_oracle_matches_live_reference(oracle, seed):
     for k, e in ((1, 0.0), (16, 0.0), (4, 2.0)):
         a, b = o.search_knn(q, k, e=e), r.search_knn(q, k, e=e)
         assert a.tobytes() == b.tobytes()
+
+
+def test_introselect_heap_select_fallback_matches_reference(oracle):
+    """std::nth_element falls back to std::__heap_select when its depth limit runs out. The adversarial value
+    sequences of oracle/make_killers.py drive the median rule's root split into that branch; the C oracle's
+    restatement must still leave the index array exactly like the reference does."""
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref/libpico_ref.so not built here")
+    data = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "introselect_killers.npz"))
+    for key in data.files:
+        v = data[key]
+        pts = np.ascontiguousarray(np.stack([v, np.zeros_like(v)], axis=1))
+        o = oracle.OracleTree(pts, 10, rule="median")
+        r = oracle.RefTree(pts, 10, rule="median")
+        _, idx, box, nodes = r.structure()
+        assert np.array_equal(idx, o.indices), key
+        for f in GOLDEN_NODE_FIELDS:
+            assert np.array_equal(o.nodes[f], nodes[f]), (key, f)
