@@ -36,7 +36,7 @@ constexpr int kWarpNodeMax = 1024;  // nodes up to this many points are split by
 constexpr int kBigThreads = 1024;   // CTA size for bigger nodes
 // Nodes above kHugeMin points (the first ~8 levels of a multi-million point tree) are not given
 // to a single CTA: all such nodes of a level are cut into chunks of kChunk index positions and
-// split by five grid-wide passes (plan, count, resolve, scatter, swap) so that every SM works
+// split by grid-wide passes (plan, count, resolve, [slide], scatter, swap) so that every SM works
 // on them. profiles/r1/launches_knn1_v2.csv: one CTA per node spent 38 of 45 ms there.
 constexpr int kHugeMin = 32768;
 constexpr int kChunkThreads = 256;
@@ -74,9 +74,6 @@ template <typename T>
 struct ChunkStat {
   int32_t lt;         // points with coord < split_val
   int32_t lt_prefix;  // exclusive prefix of lt inside the node (huge_resolve)
-  T mn, mn2, mx;      // smallest, second smallest (may equal mn), largest coordinate
-  int32_t mn_pos;     // first position of mn
-  int32_t mx_pos;     // last position of mx
 };
 
 template <typename T>
@@ -629,42 +626,7 @@ __global__ void huge_plan(BuildState<T> s, const uint32_t* list, int n_huge) {
   }
 }
 
-template <typename T>
-struct Extremes {
-  T mn, mn2, mx;
-  int mn_pos, mx_pos;
-  __device__ __forceinline__ void init() {
-    mn = mn2 = Limits<T>::max();
-    mx = -Limits<T>::max();
-    mn_pos = 0x7fffffff;
-    mx_pos = -1;
-  }
-  __device__ __forceinline__ void add(T x, int pos) { merge(x, Limits<T>::max(), pos, x, pos); }
-  // smallest: first position wins ties; largest: last position wins ties
-  __device__ __forceinline__ void merge(T omn, T omn2, int omn_pos, T omx, int omx_pos) {
-    if (omn < mn || (omn == mn && omn_pos < mn_pos)) {
-      const T second = omn2 < mn ? omn2 : mn;
-      mn2 = second;
-      mn = omn;
-      mn_pos = omn_pos;
-    } else {
-      const T second = omn < mn2 ? omn : mn2;
-      mn2 = omn2 < second ? omn2 : second;
-    }
-    if (omx > mx || (omx == mx && omx_pos > mx_pos)) {
-      mx = omx;
-      mx_pos = omx_pos;
-    }
-  }
-  __device__ __forceinline__ void merge_lane(int o) {
-    const T a = __shfl_xor_sync(0xffffffffu, mn, o), b = __shfl_xor_sync(0xffffffffu, mn2, o),
-            c = __shfl_xor_sync(0xffffffffu, mx, o);
-    const int pa = __shfl_xor_sync(0xffffffffu, mn_pos, o), pc = __shfl_xor_sync(0xffffffffu, mx_pos, o);
-    merge(a, b, pa, c, pc);
-  }
-};
-
-// grid = chunks of the level: flags counted, extremes kept for the slide cases
+// grid = chunks of the level: points left of the split value, per chunk
 template <typename T>
 __global__ void __launch_bounds__(kChunkThreads) huge_count(BuildState<T> s, int n_huge) {
   const uint32_t c = blockIdx.x;
@@ -675,37 +637,15 @@ __global__ void __launch_bounds__(kChunkThreads) huge_count(BuildState<T> s, int
   const T* col = s.raw + hn.sd;
   const T sv = hn.split_val;
   int lt = 0;
-  Extremes<T> ex;
-  ex.init();
-  for (int i = lo + threadIdx.x; i < hi; i += kChunkThreads) {
-    const T x = col[(size_t)s.idx[i] * s.sdim];
-    lt += x < sv;
-    ex.add(x, i);
-  }
-  for (int o = 16; o > 0; o >>= 1) {
-    lt += __shfl_xor_sync(0xffffffffu, lt, o);
-    ex.merge_lane(o);
-  }
+  for (int i = lo + threadIdx.x; i < hi; i += kChunkThreads) lt += col[(size_t)s.idx[i] * s.sdim] < sv;
+  for (int o = 16; o > 0; o >>= 1) lt += __shfl_xor_sync(0xffffffffu, lt, o);
   __shared__ int s_lt[kChunkThreads / 32];
-  __shared__ Extremes<T> s_ex[kChunkThreads / 32];
-  if ((threadIdx.x & 31) == 0) {
-    s_lt[threadIdx.x >> 5] = lt;
-    s_ex[threadIdx.x >> 5] = ex;
-  }
+  if ((threadIdx.x & 31) == 0) s_lt[threadIdx.x >> 5] = lt;
   __syncthreads();
   if (threadIdx.x == 0) {
-    for (int w = 1; w < kChunkThreads / 32; ++w) {
-      lt += s_lt[w];
-      ex.merge(s_ex[w].mn, s_ex[w].mn2, s_ex[w].mn_pos, s_ex[w].mx, s_ex[w].mx_pos);
-    }
-    ChunkStat<T>& cs = s.chunks[c];
-    cs.lt = lt;
-    cs.lt_prefix = 0;
-    cs.mn = ex.mn;
-    cs.mn2 = ex.mn2;
-    cs.mx = ex.mx;
-    cs.mn_pos = ex.mn_pos;
-    cs.mx_pos = ex.mx_pos;
+    for (int w = 1; w < kChunkThreads / 32; ++w) lt += s_lt[w];
+    s.chunks[c].lt = lt;
+    s.chunks[c].lt_prefix = 0;
   }
 }
 
@@ -720,12 +660,9 @@ __global__ void __launch_bounds__(32) huge_resolve(BuildState<T> s, int n_huge) 
   const int n_chunks = (cnt + kChunk - 1) / kChunk;
   ChunkStat<T>* cs = s.chunks + hn.first_chunk;
   int carry = 0;
-  Extremes<T> ex;
-  ex.init();
   for (int base = 0; base < n_chunks; base += 32) {
     const int c = base + lane;
     int v = c < n_chunks ? cs[c].lt : 0;
-    if (c < n_chunks) ex.merge(cs[c].mn, cs[c].mn2, cs[c].mn_pos, cs[c].mx, cs[c].mx_pos);
     int incl = v;
     for (int o = 1; o < 32; o <<= 1) {
       const int t = __shfl_up_sync(0xffffffffu, incl, o);
@@ -734,7 +671,6 @@ __global__ void __launch_bounds__(32) huge_resolve(BuildState<T> s, int n_huge) 
     if (c < n_chunks) cs[c].lt_prefix = carry + incl - v;
     carry += __shfl_sync(0xffffffffu, incl, 31);
   }
-  for (int o = 16; o > 0; o >>= 1) ex.merge_lane(o);
   const int nl = carry;
   int split = hn.begin + nl;
   T split_val = hn.split_val;
