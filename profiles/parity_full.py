@@ -1,7 +1,8 @@
 """Full-size parity of knn=16 / knn=4 on cfg2 with the REFERENCE'S OWN TREE uploaded (kd_tree::save stream ->
 pico_b200_tree_load): node-for-node and leaf-order identical trees, so every index must match, ties included.
-Separates traversal equivalence (this script must report 0 mismatches) from the tie-class differences a
-device-built tree may show after slides."""
+Both lines must report 0 mismatches: the first proves the traversals equivalent, the second that the device build
+leaves the same index permutation as the reference (std::partition and std::nth_element orders).
+(Before the nth_element emulation the device-built tree showed 30 equal-distance swaps in 115 M slots at k = 16.)"""
 import os
 import sys
 import tempfile
