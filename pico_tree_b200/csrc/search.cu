@@ -3,7 +3,7 @@
 // Batch entry points replace the per-query loops of the reference
 // (src/pyco_tree/pico_tree/_pyco_tree/kd_tree.hpp:117-268, examples/benchmark/bm_pico_kd_tree.cpp:63-78).
 // Two traversal families (traverse.cuh / traverse_warp.cuh):
-//   * thread-per-query for sdim <= 3 and k <= 16: queries are Z-ordered first, so the 32
+//   * thread-per-query for sdim <= 3 and k <= 32: queries are Z-ordered first, so the 32
 //     threads of a warp walk almost the same root-to-leaf path — node and leaf loads become
 //     warp-wide broadcasts served by L1/L2;
 //   * warp-per-query for everything else (any sdim, any k), also selectable with
@@ -24,6 +24,7 @@ namespace {
 
 constexpr int kThreadsPerBlock = 128;
 constexpr int kWarpsPerBlock = 8;
+constexpr size_t kThreadKMax = 32;  // largest k of the thread-per-query kernels (register k-list)
 
 // ------------------------------------------------------------------ query ordering
 // 30-bit (3 x 10) Morton code of the query inside the tree's root box; queries outside are
@@ -722,8 +723,10 @@ void launch_knn_thread_k(const KnnArgs<T>& a, unsigned blocks, cudaStream_t st) 
     knn_thread_kernel<T, DIM, 4, FAST, DEEP><<<blocks, kThreadsPerBlock, 0, st>>>(a);
   else if (a.k <= 8)
     knn_thread_kernel<T, DIM, 8, FAST, DEEP><<<blocks, kThreadsPerBlock, 0, st>>>(a);
-  else
+  else if (a.k <= 16)
     knn_thread_kernel<T, DIM, 16, FAST, DEEP><<<blocks, kThreadsPerBlock, 0, st>>>(a);
+  else
+    knn_thread_kernel<T, DIM, 32, FAST, DEEP><<<blocks, kThreadsPerBlock, 0, st>>>(a);
 }
 
 template <typename T, int DIM>
@@ -768,7 +771,7 @@ int knn_enqueue(CallCtx& c, const pico_b200_tree* t, const T* q, size_t nq, size
   a.out = d_out;
   a.k = (int)k;
   *launches += perm ? 3 : 0;
-  const bool use_thread = t->packed() && k <= 16 && !(flags & PICO_B200_WARP_PER_QUERY);
+  const bool use_thread = t->packed() && k <= kThreadKMax && !(flags & PICO_B200_WARP_PER_QUERY);
   if (use_thread) {
     bool deep;
     unsigned blocks;
