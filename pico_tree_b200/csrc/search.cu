@@ -77,7 +77,7 @@ struct KnnArgs {
   size_t ws_stride, ws_depth;
   // warp kernels: shared memory per warp in scalars (query + offsets [+ leaf tile]) and the rows
   // of the staged leaf tile (0 = points are read straight from global memory)
-  int warp_smem, tile_rows;
+  int warp_smem, tile_rows, cache_rows;
   // warp kernels are persistent (one wave of resident blocks): every warp draws its next query here
   unsigned long long* counter;
 };
@@ -214,13 +214,13 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) knn_warp_kernel(KnnArgs<T
       WarpVisitKnn<T, WarpKnnReg<T>> vis;
       vis.list.init(a.k);
       traverse_warp<T, PACKED>(a.nodes, a.outer, ps, sq, so, stack, win, a.metric, a.approx != 0, a.e_inv, vis,
-                               tile, a.tile_rows, a.spans);
+                               tile, a.tile_rows, a.spans, a.cache_rows);
       vis.list.store(row);
     } else {
       WarpVisitKnn<T, WarpKnnMem<T>> vis;
       vis.list.init(row, a.k);
       traverse_warp<T, PACKED>(a.nodes, a.outer, ps, sq, so, stack, win, a.metric, a.approx != 0, a.e_inv, vis,
-                               tile, a.tile_rows, a.spans);
+                               tile, a.tile_rows, a.spans, a.cache_rows);
     }
   }
 }
@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) radius_warp_kernel(Radius
     vis.radius = r.radius;
     vis.out = r.hits ? r.hits + r.offsets[qi] : nullptr;
     traverse_warp<T, PACKED>(a.nodes, a.outer, ps, sq, so, stack, win, a.metric, a.approx != 0, a.e_inv, vis, tile,
-                             a.tile_rows, a.spans);
+                             a.tile_rows, a.spans, a.cache_rows);
     if (!r.hits && lane == 0) r.counts[qi] = vis.count;
   }
 }
@@ -627,6 +627,7 @@ void fill_base(KnnArgs<T>& a, const pico_b200_tree* t, const T* d_q, size_t d_st
   a.ws_stride = a.ws_depth = 0;
   a.warp_smem = 2 * (int)t->sdim + (int)(kStackWindow * sizeof(WarpFrame<T>) / sizeof(T));
   a.tile_rows = 0;
+  a.cache_rows = 0;
   a.counter = nullptr;
 }
 
@@ -639,6 +640,7 @@ size_t plan_warp_smem(const pico_b200_tree* t, KnnArgs<T>& a) {
   const size_t window = kStackWindow * sizeof(WarpFrame<T>) / sizeof(T);  // scalars; a multiple of 16 bytes
   a.warp_smem = (int)(2 * sdim + window);
   a.tile_rows = 0;
+  a.cache_rows = 0;
   a.spans = nullptr;
   if (!t->packed() && sdim % vec == 0 && t->max_leaf_points > 0) {
     // per warp: query + offsets, the tile (rows x (sdim + pad)), the distance / index cache of the tile's
@@ -650,8 +652,16 @@ size_t plan_warp_smem(const pico_b200_tree* t, KnnArgs<T>& a) {
       const int x = e ? atoi(e) : 0;
       return (size_t)((x >= 1 && x <= 32) ? x : 32);
     }();
+    // distances of up to cache_factor tiles are kept: in high dimensions nothing gets pruned, and a span
+    // of several small leaves then costs one full-tile round per tile_rows points instead of one per leaf
+    static const size_t cache_factor = [] {
+      const char* e = getenv("PICO_B200_CACHE_TILES");  // tuning hook
+      const int x = e ? atoi(e) : 0;
+      return (size_t)((x >= 1 && x <= 64) ? x : 16);  // profiles/r1/hd_tile_rows.txt
+    }();
+    const size_t factor = sdim >= 64 ? cache_factor : 1;
     auto slice = [&](size_t rows) {
-      const size_t cache = (2 * rows + vec - 1) / vec * vec;
+      const size_t cache = (2 * rows * factor + vec - 1) / vec * vec;
       return 2 * sdim + rows * (sdim + vec) + cache + window;
     };
     size_t rows = cap;
@@ -659,6 +669,7 @@ size_t plan_warp_smem(const pico_b200_tree* t, KnnArgs<T>& a) {
     while (rows > 1 && slice(rows) * sizeof(T) * kWarpsPerBlock > kBlockBudget) --rows;
     if (slice(rows) * sizeof(T) * kWarpsPerBlock <= kBlockBudget) {
       a.tile_rows = (int)rows;
+      a.cache_rows = (int)(rows * factor);
       a.warp_smem = (int)slice(rows);
       a.spans = t->d_spans;
     }

@@ -224,15 +224,15 @@ __device__ __forceinline__ void scan_leaf_staged(const T* __restrict__ rows, con
 // average under the sliding midpoint rule with max_leaf_size 10), so a lane-per-point leaf scan
 // keeps 2 of 32 lanes busy and the kernel is bound by instruction issue. Points are stored in
 // leaf order, i.e. the points below ANY node form one contiguous run: when the descent reaches a
-// node with at most tile_rows points below it, the distances of all of them are computed in one
-// staged pass (one lane per point) and kept in shared memory; the traversal below that node —
+// node with at most cache_rows points below it, the distances of all of them are computed in
+// full-tile rounds (one lane per point) and kept in shared memory; the traversal below that node —
 // its order, its prune tests, what is offered to the visitor — runs unchanged and takes the
 // distances from the cache. Distances of leaves that end up pruned were computed for nothing; the
 // lanes would have idled anyway.
 template <typename T>
 struct SpanCache {
-  T* dist;        // [tile_rows] shared
-  int* index;     // [tile_rows] shared
+  T* dist;        // [cache_rows] shared
+  int* index;     // [cache_rows] shared
   int lo, hi;     // cached point range
   int base_sp;    // stack height when it was filled; frames below it belong to ancestors
 };
@@ -364,7 +364,7 @@ template <typename T, bool PACKED, typename Visitor>
 __device__ void traverse_warp(const typename NodeOf<T>::type* __restrict__ nodes, const T* __restrict__ outer,
                               const PointSet<T, PACKED>& ps, const T* sq, T* so, WarpFrame<T>* stack,
                               WarpFrame<T>* win, int metric, bool approx, T e_inv, Visitor& vis, T* tile = nullptr,
-                              int tile_rows = 0, const uint2* __restrict__ spans = nullptr) {
+                              int tile_rows = 0, const uint2* __restrict__ spans = nullptr, int cache_rows = 0) {
   // `stack` (global, one slot per tree level) is the backing store; `win` (shared, kStackWindow
   // frames) mirrors the most recently pushed ones, so the pop that follows a push — every leaf
   // visit — does not wait for a global-memory round trip. Frames [win_lo, sp) are valid in `win`.
@@ -377,9 +377,9 @@ __device__ void traverse_warp(const typename NodeOf<T>::type* __restrict__ nodes
   cache.lo = cache.hi = 0;
   cache.base_sp = 0x7fffffff;  // nothing cached
   if (!PACKED && tile_rows > 0) {
-    // behind the tile: tile_rows distances, then tile_rows indices
+    // behind the tile: cache_rows distances, then cache_rows indices
     cache.dist = tile + (size_t)tile_rows * (ps.sdim + Vec16<T>::n);
-    cache.index = reinterpret_cast<int*>(cache.dist + tile_rows);
+    cache.index = reinterpret_cast<int*>(cache.dist + cache_rows);
   }
   for (;;) {
     T a, b;
@@ -390,14 +390,18 @@ __device__ void traverse_warp(const typename NodeOf<T>::type* __restrict__ nodes
       if (!PACKED && spans != nullptr && sp < cache.base_sp) {
         // outside any cached subtree: does everything below this node fit into one tile?
         const uint2 span = __ldg(spans + node);
-        if ((int)span.y <= tile_rows) {
-          T d;
-          int idx;
-          stage_and_fold<T>(ps.rows, ps.indices, ps.sdim, (int)span.x, (int)span.y, sq, tile, metric, approx, e_inv,
-                            d, idx);
-          if (lane < (int)span.y) {
-            cache.dist[lane] = d;
-            cache.index[lane] = idx;
+        if ((int)span.y <= cache_rows) {
+          // rounds of tile_rows rows: every round is a full tile although the leaves are small
+          for (int done = 0; done < (int)span.y; done += tile_rows) {
+            const int rows_here = min(tile_rows, (int)span.y - done);
+            T d;
+            int idx;
+            stage_and_fold<T>(ps.rows, ps.indices, ps.sdim, (int)span.x + done, rows_here, sq, tile, metric, approx,
+                              e_inv, d, idx);
+            if (lane < rows_here) {
+              cache.dist[done + lane] = d;
+              cache.index[done + lane] = idx;
+            }
           }
           __syncwarp();
           cache.lo = (int)span.x;
