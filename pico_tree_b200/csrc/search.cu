@@ -1130,6 +1130,63 @@ int launch_radius(CallCtx& c, const pico_b200_tree* t, RadiusArgs<T>& r, unsigne
 
 }  // namespace
 
+// Small host batches (the reference's one-query-per-call pattern): queries, counts, offsets and hits
+// live in the pinned device-mapped buffer; the prefix sum of at most 256 counts is host bookkeeping.
+// *served tells whether the call was answered here; if not, the regular path takes it.
+template <typename T>
+int radius_small(const pico_b200_tree* t, const T* q, size_t nq, size_t stride, double radius, double e,
+                 uint64_t* offsets_out, void** out, unsigned flags, bool* served) {
+  *served = false;
+  const size_t sdim = t->sdim;
+  if (nq > 256 || nq * sdim * sizeof(T) > 8 * 1024 || (flags & PICO_B200_SORT_RESULTS) || g_cfg.has_user_stream ||
+      g_cfg.profiling)
+    return 0;
+  PICO_TRY(g_small.ensure());
+  char* base = static_cast<char*>(g_small.p);
+  T* mq = reinterpret_cast<T*>(base);
+  uint32_t* counts = reinterpret_cast<uint32_t*>(base + 8 * 1024);
+  uint64_t* offs = reinterpret_cast<uint64_t*>(base + 10 * 1024);
+  Neighbor<T>* hits = reinterpret_cast<Neighbor<T>*>(base + kSmallQueryBytes);
+  for (size_t i = 0; i < nq; ++i) memcpy(mq + i * sdim, q + i * stride, sdim * sizeof(T));
+  CallCtx c;
+  PICO_TRY(c.init(t->device));
+  c.timed = false;
+  RadiusArgs<T> r;
+  fill_base(r.base, t, mq, sdim, nq, nullptr, e);
+  r.radius = e > 0 ? T(radius) * r.base.e_inv : T(radius);
+  r.counts = counts;
+  r.offsets = nullptr;
+  r.hits = nullptr;
+  PICO_TRY((launch_radius<T, false>(c, t, r, flags)));
+  PICO_CUDA(cudaStreamSynchronize(c.st));
+  uint64_t total = 0;
+  for (size_t i = 0; i < nq; ++i) {
+    offs[i] = total;
+    total += counts[i];
+  }
+  offs[nq] = total;
+  if (total * sizeof(Neighbor<T>) > kSmallResultBytes) return 0;
+  Neighbor<T>* h = static_cast<Neighbor<T>*>(malloc((total ? total : 1) * sizeof(Neighbor<T>)));
+  if (!h) return fail(PICO_B200_ERR_OUT_OF_MEMORY, "host allocation of radius results failed");
+  if (total) {
+    if (sizeof(T) == 8) memset(hits, 0, total * sizeof(Neighbor<T>));  // defined padding
+    r.offsets = offs;
+    r.hits = hits;
+    r.base.ws = nullptr;
+    int rc = launch_radius<T, true>(c, t, r, flags);
+    if (!rc && cudaStreamSynchronize(c.st) != cudaSuccess) rc = fail(PICO_B200_ERR_CUDA, "small radius batch failed");
+    if (rc) {
+      free(h);
+      return rc;
+    }
+    memcpy(h, hits, total * sizeof(Neighbor<T>));
+  }
+  memcpy(offsets_out, offs, (nq + 1) * sizeof(uint64_t));
+  *out = h;
+  *served = true;
+  return 0;
+}
+
 template <typename T>
 int radius_batch(const pico_b200_tree* t, const T* q, size_t nq, size_t stride, double radius, double e,
                  uint64_t* offsets_out, void** out, unsigned flags, pico_b200_search_stats* stats) {
@@ -1138,6 +1195,11 @@ int radius_batch(const pico_b200_tree* t, const T* q, size_t nq, size_t stride, 
   // PICO_B200_DEVICE_POINTERS: queries and offsets_out are device pointers and *out receives a device
   // buffer (pico_b200_free_device); the call still synchronises once to learn the total.
   const bool on_device = flags & PICO_B200_DEVICE_POINTERS;
+  if (!on_device && nq > 0 && !stats) {
+    bool served = false;
+    PICO_TRY(radius_small<T>(t, q, nq, stride, radius, e, offsets_out, out, flags, &served));
+    if (served) return 0;
+  }
   CallCtx c;
   PICO_TRY(c.init(t->device));
   if (nq == 0) {
@@ -1227,12 +1289,97 @@ int radius_batch(const pico_b200_tree* t, const T* q, size_t nq, size_t stride, 
 }
 
 // ------------------------------------------------------------------ box
+// Small host batches of boxes, like radius_small.
+template <typename T>
+int box_small(const pico_b200_tree* t, const T* mins, const T* maxs, size_t nb, size_t stride, uint64_t* offsets_out,
+              int32_t** out, bool* served) {
+  *served = false;
+  const size_t sdim = t->sdim;
+  if (nb > 256 || nb * sdim * sizeof(T) > 4 * 1024 || g_cfg.has_user_stream || g_cfg.profiling) return 0;
+  PICO_TRY(g_small.ensure());
+  char* base = static_cast<char*>(g_small.p);
+  T* mmin = reinterpret_cast<T*>(base);
+  T* mmax = reinterpret_cast<T*>(base + 4 * 1024);
+  uint32_t* counts = reinterpret_cast<uint32_t*>(base + 8 * 1024);
+  uint64_t* offs = reinterpret_cast<uint64_t*>(base + 10 * 1024);
+  int32_t* hits = reinterpret_cast<int32_t*>(base + kSmallQueryBytes);
+  for (size_t i = 0; i < nb; ++i) {
+    memcpy(mmin + i * sdim, mins + i * stride, sdim * sizeof(T));
+    memcpy(mmax + i * sdim, maxs + i * stride, sdim * sizeof(T));
+  }
+  CallCtx c;
+  PICO_TRY(c.init(t->device));
+  c.timed = false;
+  BoxArgs<T> a;
+  a.nodes = static_cast<const typename NodeOf<T>::type*>(t->d_nodes);
+  a.outer = static_cast<const T*>(t->d_outer);
+  a.metric = t->metric;
+  a.pts4 = t->packed() ? static_cast<const typename Vec4Of<T>::type*>(t->d_pts) : nullptr;
+  a.rows = t->packed() ? nullptr : static_cast<const T*>(t->d_pts);
+  a.indices = t->d_indices;
+  a.root_box = static_cast<const T*>(t->d_root_box);
+  a.mins = mmin;
+  a.maxs = mmax;
+  a.stride = sdim;
+  a.nb = (uint32_t)nb;
+  a.sdim = (int)sdim;
+  a.counts = counts;
+  a.offsets = nullptr;
+  a.hits = nullptr;
+  unsigned blocks;
+  size_t smem;
+  PICO_TRY(warp_geometry<T>(c, t, nb, sizeof(BoxFrame) + sizeof(T), 4 * sdim * sizeof(T), &a.ws, &a.ws_depth, &blocks,
+                            &smem));
+  auto launch = [&]() -> int {
+    if (t->packed()) {
+      box_warp_kernel<T, true><<<blocks, kWarpsPerBlock * 32, smem, c.st>>>(a);
+    } else {
+      if (smem > 48 * 1024)
+        PICO_CUDA(cudaFuncSetAttribute(box_warp_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+      box_warp_kernel<T, false><<<blocks, kWarpsPerBlock * 32, smem, c.st>>>(a);
+    }
+    PICO_CUDA(cudaGetLastError());
+    PICO_CUDA(cudaStreamSynchronize(c.st));
+    return 0;
+  };
+  PICO_TRY(launch());
+  uint64_t total = 0;
+  for (size_t i = 0; i < nb; ++i) {
+    offs[i] = total;
+    total += counts[i];
+  }
+  offs[nb] = total;
+  if (total * sizeof(int32_t) > kSmallResultBytes) return 0;
+  int32_t* h = static_cast<int32_t*>(malloc((total ? total : 1) * sizeof(int32_t)));
+  if (!h) return fail(PICO_B200_ERR_OUT_OF_MEMORY, "host allocation of box results failed");
+  if (total) {
+    a.offsets = offs;
+    a.hits = hits;
+    const int rc = launch();
+    if (rc) {
+      free(h);
+      return rc;
+    }
+    memcpy(h, hits, total * sizeof(int32_t));
+  }
+  memcpy(offsets_out, offs, (nb + 1) * sizeof(uint64_t));
+  *out = h;
+  *served = true;
+  return 0;
+}
+
 template <typename T>
 int box_batch(const pico_b200_tree* t, const T* mins, const T* maxs, size_t nb, size_t stride, uint64_t* offsets_out,
               int32_t** out, unsigned flags, pico_b200_search_stats* stats) {
   *out = nullptr;
   if (nb > 0xfffffff0u) return fail(PICO_B200_ERR_UNSUPPORTED, "more than 2^32-16 boxes in one call");
   const bool on_device = flags & PICO_B200_DEVICE_POINTERS;  // same convention as radius_batch
+  if (!on_device && nb > 0 && !stats) {
+    bool served = false;
+    PICO_TRY(box_small<T>(t, mins, maxs, nb, stride, offsets_out, out, &served));
+    if (served) return 0;
+  }
   CallCtx c;
   PICO_TRY(c.init(t->device));
   if (nb == 0) {

@@ -96,6 +96,31 @@ int main(int argc, char** argv) {
     }
     double const s = seconds_since(t0);
     std::printf("knn k=1 single-query loop over %zu queries: %.1f us per call (%zu results)\n", nq, s / nq * 1e6, sum);
+    // RadiusCtSldMid / box, one call per query
+    sum = 0;
+    t0 = std::chrono::steady_clock::now();
+    for (std::size_t i = 0; i < nq; ++i) {
+      tree.search_radius(points_test[i], 0.01f, results);
+      sum += results.size();
+    }
+    double const sr = seconds_since(t0);
+    std::printf("radius r^2=0.01 single-query loop: %.1f us per call (%.1f hits/query)\n", sr / nq * 1e6,
+                static_cast<double>(sum) / static_cast<double>(nq));
+    std::vector<int> idxs;
+    sum = 0;
+    t0 = std::chrono::steady_clock::now();
+    for (std::size_t i = 0; i < nq; ++i) {
+      point_type lo = points_test[i], hi = points_test[i];
+      for (int d = 0; d < 3; ++d) {
+        lo[d] -= 0.1f;
+        hi[d] += 0.1f;
+      }
+      tree.search_box(lo, hi, idxs);
+      sum += idxs.size();
+    }
+    double const sb = seconds_since(t0);
+    std::printf("box 0.2 m edge single-query loop: %.1f us per call (%.1f hits/box)\n", sb / nq * 1e6,
+                static_cast<double>(sum) / static_cast<double>(nq));
   }
   return 0;
 }
