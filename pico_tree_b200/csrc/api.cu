@@ -30,12 +30,14 @@ int check_device(int device, int* sm_count) {
   }
   if (device < 0 || device >= count) return fail(PICO_B200_ERR_INVALID_ARGUMENT, "device ordinal out of range");
   PICO_CUDA(cudaSetDevice(device));
-  cudaDeviceProp prop;
-  PICO_CUDA(cudaGetDeviceProperties(&prop, device));
-  if (prop.major < 10)
-    return fail(PICO_B200_ERR_NO_DEVICE, "libpico_b200 is built for sm_100a only; found sm_" +
-                                             std::to_string(prop.major) + std::to_string(prop.minor));
-  *sm_count = prop.multiProcessorCount;
+  int major = 0, minor = 0, sms = 0;  // (cudaGetDeviceProperties costs milliseconds; three attributes do not)
+  PICO_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+  PICO_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device));
+  PICO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  if (major < 10)
+    return fail(PICO_B200_ERR_NO_DEVICE, "libpico_b200 is built for sm_100a only; found sm_" + std::to_string(major) +
+                                             std::to_string(minor));
+  *sm_count = sms;
   // Per-call workspaces come from the stream-ordered allocator; keep freed blocks cached in
   // the pool instead of returning them to the driver at every synchronisation.
   cudaMemPool_t pool;

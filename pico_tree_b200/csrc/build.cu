@@ -954,10 +954,13 @@ __global__ void pack_pointsN(const T* raw, const int32_t* idx, size_t n, int sdi
   for (int d = lane; d < sdim; d += 32) dst[d] = src[d];
 }
 
+// Build-time scratch comes from the stream-ordered pool (kept warm by check_device's release
+// threshold): a second build on the same device finds its ~1.5 GB of tables without a driver call.
 struct DevBuf {
   void* p = nullptr;
+  cudaStream_t st = nullptr;
   ~DevBuf() {
-    if (p) cudaFree(p);
+    if (p) cudaFreeAsync(p, st);
   }
   template <typename U>
   U* as() {
@@ -965,16 +968,20 @@ struct DevBuf {
   }
 };
 
-int alloc(DevBuf& b, size_t bytes) {
-  PICO_CUDA(cudaMalloc(&b.p, bytes ? bytes : 16));
+int alloc(DevBuf& b, size_t bytes, cudaStream_t st) {
+  b.st = st;
+  PICO_CUDA(cudaMallocAsync(&b.p, bytes ? bytes : 16, st));
   return 0;
 }
 
 // Staging: host rows (any stride) -> packed device rows.
 template <typename T>
 int stage_points(const T* h_pts, size_t n, size_t sdim, size_t stride, T* d_raw, cudaStream_t st) {
-  PICO_CUDA(cudaMemcpy2DAsync(d_raw, sdim * sizeof(T), h_pts, stride * sizeof(T), sdim * sizeof(T), n,
-                              cudaMemcpyHostToDevice, st));
+  if (stride == sdim)
+    PICO_CUDA(cudaMemcpyAsync(d_raw, h_pts, n * sdim * sizeof(T), cudaMemcpyHostToDevice, st));
+  else
+    PICO_CUDA(cudaMemcpy2DAsync(d_raw, sdim * sizeof(T), h_pts, stride * sizeof(T), sdim * sizeof(T), n,
+                                cudaMemcpyHostToDevice, st));
   return 0;
 }
 
@@ -1013,29 +1020,29 @@ int build_tree(pico_b200_tree* t, const T* h_pts, size_t stride, int rule, int s
   } guard{st};
 
   DevBuf raw, tmp, tmp2, nodes, boxes, counters, big_a, big_b, partial, huge_a, huge_b, huge_nodes, chunk_stats;
-  PICO_TRY(alloc(raw, n * sdim * sizeof(T)));
+  PICO_TRY(alloc(raw, n * sdim * sizeof(T), st));
   PICO_TRY(stage_points(h_pts, n, sdim, stride, raw.as<T>(), st));
   PICO_CUDA(cudaMalloc(&t->d_indices, n * sizeof(int32_t)));
   PICO_CUDA(cudaMalloc(&t->d_root_box, 2 * sdim * sizeof(T)));
-  PICO_TRY(alloc(tmp, n * sizeof(int32_t)));
-  PICO_TRY(alloc(tmp2, n * sizeof(int32_t)));
+  PICO_TRY(alloc(tmp, n * sizeof(int32_t), st));
+  PICO_TRY(alloc(tmp2, n * sizeof(int32_t), st));
 
   // --- BFS node table
   size_t cap = 2 * n + 1024;
-  PICO_TRY(alloc(nodes, cap * sizeof(BNode<T>)));
-  PICO_TRY(alloc(boxes, cap * 2 * sdim * sizeof(T)));
-  PICO_TRY(alloc(counters, 8 * sizeof(uint32_t)));
-  PICO_TRY(alloc(big_a, cap * sizeof(uint32_t)));
-  PICO_TRY(alloc(big_b, cap * sizeof(uint32_t)));
+  PICO_TRY(alloc(nodes, cap * sizeof(BNode<T>), st));
+  PICO_TRY(alloc(boxes, cap * 2 * sdim * sizeof(T), st));
+  PICO_TRY(alloc(counters, 8 * sizeof(uint32_t), st));
+  PICO_TRY(alloc(big_a, cap * sizeof(uint32_t), st));
+  PICO_TRY(alloc(big_b, cap * sizeof(uint32_t), st));
   // huge nodes of one level are disjoint ranges of more than kHugeMin points each
   int huge_min = kHugeMin;
   if (const char* e = getenv("PICO_B200_HUGE_MIN")) huge_min = std::max(atoi(e), kWarpNodeMax);  // test hook
   const size_t huge_cap = n / (size_t)huge_min + 16;
   const size_t chunk_cap = n / kChunk + huge_cap + 16;
-  PICO_TRY(alloc(huge_a, huge_cap * sizeof(uint32_t)));
-  PICO_TRY(alloc(huge_b, huge_cap * sizeof(uint32_t)));
-  PICO_TRY(alloc(huge_nodes, huge_cap * sizeof(HugeNode<T>)));
-  PICO_TRY(alloc(chunk_stats, chunk_cap * sizeof(ChunkStat<T>)));
+  PICO_TRY(alloc(huge_a, huge_cap * sizeof(uint32_t), st));
+  PICO_TRY(alloc(huge_b, huge_cap * sizeof(uint32_t), st));
+  PICO_TRY(alloc(huge_nodes, huge_cap * sizeof(HugeNode<T>), st));
+  PICO_TRY(alloc(chunk_stats, chunk_cap * sizeof(ChunkStat<T>), st));
 
   // build_ms covers the kernels and the per-level round trips, not the allocations above
   cudaEvent_t ev0, ev1;
@@ -1061,7 +1068,7 @@ int build_tree(pico_b200_tree* t, const T* h_pts, size_t stride, int rule, int s
     PICO_CUDA(cudaMemcpyAsync(d_root, h_root.data(), 2 * sdim * sizeof(T), cudaMemcpyHostToDevice, st));
   } else {
     const int parts = (int)std::min<size_t>((n + 1023) / 1024, (size_t)t->sm_count * 4);
-    PICO_TRY(alloc(partial, (size_t)parts * 2 * sdim * sizeof(T)));
+    PICO_TRY(alloc(partial, (size_t)parts * 2 * sdim * sizeof(T), st));
     root_box_kernel<T><<<parts, 1024, 0, st>>>(raw.as<T>(), n, sdim, partial.as<T>());
     root_box_final<T><<<(sdim + 127) / 128, 128, 0, st>>>(partial.as<T>(), parts, sdim, d_root);
     PICO_CUDA(cudaGetLastError());
@@ -1134,10 +1141,10 @@ int build_tree(pico_b200_tree* t, const T* h_pts, size_t stride, int rule, int s
       // grow the tables (midpoint rule can create many empty leaves)
       const size_t ncap = std::max(cap * 2, (size_t)level_end + 2 * (size_t)width + 1024);
       DevBuf nn, nb, na, nbb;
-      PICO_TRY(alloc(nn, ncap * sizeof(BNode<T>)));
-      PICO_TRY(alloc(nb, ncap * 2 * sdim * sizeof(T)));
-      PICO_TRY(alloc(na, ncap * sizeof(uint32_t)));
-      PICO_TRY(alloc(nbb, ncap * sizeof(uint32_t)));
+      PICO_TRY(alloc(nn, ncap * sizeof(BNode<T>), st));
+      PICO_TRY(alloc(nb, ncap * 2 * sdim * sizeof(T), st));
+      PICO_TRY(alloc(na, ncap * sizeof(uint32_t), st));
+      PICO_TRY(alloc(nbb, ncap * sizeof(uint32_t), st));
       PICO_CUDA(cudaMemcpyAsync(nn.p, nodes.p, cap * sizeof(BNode<T>), cudaMemcpyDeviceToDevice, st));
       PICO_CUDA(cudaMemcpyAsync(nb.p, boxes.p, cap * 2 * sdim * sizeof(T), cudaMemcpyDeviceToDevice, st));
       PICO_CUDA(cudaMemcpyAsync(na.p, big_cur, (size_t)n_big * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
@@ -1269,7 +1276,7 @@ int upload_tree(pico_b200_tree* t, const T* h_pts, size_t stride, const void* h_
     ~StreamGuard() { cudaStreamDestroy(s); }
   } guard{st};
   DevBuf raw;
-  PICO_TRY(alloc(raw, n * sdim * sizeof(T)));
+  PICO_TRY(alloc(raw, n * sdim * sizeof(T), st));
   PICO_TRY(stage_points(h_pts, n, sdim, stride, raw.as<T>(), st));
   PICO_CUDA(cudaMalloc(&t->d_indices, n * sizeof(int32_t)));
   PICO_CUDA(cudaMalloc(&t->d_root_box, 2 * sdim * sizeof(T)));
