@@ -489,6 +489,11 @@ struct PinnedMirror {
   }
 };
 thread_local PinnedMirror g_pin_in, g_pin_out;
+// Pinning costs close to a millisecond per megabyte, once. The mirrors are therefore bounded, and a
+// host thread only gets them from its second big pageable batch on: a one-off call takes the plain
+// pageable copies, a caller that keeps searching pays the allocation once and is 1.5x faster after.
+constexpr size_t kMirrorBudget = (size_t)256 << 20;
+thread_local int g_pageable_batches = 0;
 
 // Small batches from host memory (the reference's one-query-per-call loops end up here): the
 // queries are written into a pinned, device-mapped buffer that the kernel reads and writes over
@@ -875,7 +880,13 @@ int knn_batch(const pico_b200_tree* t, const T* q, size_t nq, size_t stride, siz
     const int n_streams = host_streams();
     const size_t sdim = t->sdim;
     // pageable buffers go through pinned mirrors (see PinnedMirror)
-    const bool stage_in = is_pageable(q), stage_out = is_pageable(out);
+    bool stage_in = is_pageable(q), stage_out = is_pageable(out);
+    if (stage_in || stage_out) {
+      const size_t need = (stage_in ? nq * sdim * sizeof(T) : 0) + (stage_out ? nq * k * sizeof(Neighbor<T>) : 0);
+      const bool have = (!stage_in || g_pin_in.cap >= nq * sdim * sizeof(T)) &&
+                        (!stage_out || g_pin_out.cap >= nq * k * sizeof(Neighbor<T>));
+      if (!have && (need > kMirrorBudget || ++g_pageable_batches < 2)) stage_in = stage_out = false;
+    }
     const T* src = q;
     size_t src_stride = stride;
     Neighbor<T>* dst = out;
