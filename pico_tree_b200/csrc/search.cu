@@ -506,10 +506,10 @@ struct PinnedMirror {
   }
 };
 thread_local PinnedMirror g_pin_in, g_pin_out;
-// Pinning costs close to a millisecond per megabyte, once. The mirrors are therefore bounded, and a
+// Pinning costs close to a millisecond per megabyte, once. The mirrors are therefore bounded (1 GiB), and a
 // host thread only gets them from its second big pageable batch on: a one-off call takes the plain
 // pageable copies, a caller that keeps searching pays the allocation once and is 1.5x faster after.
-constexpr size_t kMirrorBudget = (size_t)256 << 20;
+constexpr size_t kMirrorBudget = (size_t)1 << 30;
 thread_local int g_pageable_batches = 0;
 
 // Small batches from host memory (the reference's one-query-per-call loops end up here): the
