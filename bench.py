@@ -162,6 +162,41 @@ class ClockSampler:
         return out
 
 
+def tree_leaf_scan(L, handle, q_dev, n_query, dev, repeats):
+    """pico_b200_profile_leaf_scan: (neighbours, {descend_ms, scan_ms, scan_bytes}) per launch."""
+    import torch
+    from pico_tree_b200 import _lib
+    out = torch.empty((n_query, 1, 2), dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    d_ms, s_ms, nbytes = C.c_double(), C.c_double(), C.c_uint64()
+    _lib.check(L.pico_b200_profile_leaf_scan(handle, C.c_void_p(q_dev.data_ptr()), n_query, 3,
+                                             C.c_void_p(out.data_ptr()), repeats, C.byref(d_ms), C.byref(s_ms),
+                                             C.byref(nbytes)))
+    return out, {"descend_ms": d_ms.value, "scan_ms": s_ms.value, "scan_bytes": int(nbytes.value)}
+
+
+def pcie_floor_ms(q_pin, out_pin, dev, reps=10):
+    """One full-size H2D of the queries and D2H of the results, issued together on two streams (PCIe is
+    full duplex): the time no host-buffer call can beat on this box."""
+    import torch
+    s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    d_in = torch.empty(q_pin.shape, dtype=q_pin.dtype, device=dev)
+    d_out = torch.empty(out_pin.shape, dtype=out_pin.dtype, device=dev)
+    scratch = torch.empty_like(out_pin).pin_memory()
+    best = None
+    for _ in range(reps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with torch.cuda.stream(s_in):
+            d_in.copy_(q_pin, non_blocking=True)
+        with torch.cuda.stream(s_out):
+            scratch.copy_(d_out, non_blocking=True)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) * 1e3
+        best = dt if best is None else min(best, dt)
+    return best
+
+
 # --------------------------------------------------------------------------- our arm
 def run_ours(args, n_tree, n_query):
     import torch
@@ -247,6 +282,13 @@ def run_ours(args, n_tree, n_query):
     ms_step = ms_total / args.steps
     kernel_ms = trav_ms.value / max(trav_n.value, 1)
 
+    # ---- the leaf scan in isolation: first-leaf ranges, then a kernel that only streams them
+    leaf_scan = None
+    if k == 1 and not args.warp_per_query:
+        _lib.check(L.pico_b200_set_stream(None))
+        _, ls = tree_leaf_scan(L, handle, q_dev, n_query, dev, repeats=20)
+        leaf_scan = ls
+
     # ---- e2e: public API, pinned host buffers, H2D + D2H inside the timed region
     q_pin = torch.from_numpy(q_host).pin_memory()
     out_pin = torch.empty((n_query, k, 2), dtype=torch.int32).pin_memory()
@@ -266,6 +308,8 @@ def run_ours(args, n_tree, n_query):
         step_e2e()
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
+
+    floor_ms = pcie_floor_ms(q_pin, out_pin, dev)
 
     # resident and host paths must agree
     res_dev = out_dev.cpu().numpy()
@@ -343,6 +387,17 @@ def run_ours(args, n_tree, n_query):
                     else "knn_warp_kernel<float,PACKED,REG>", "kernel_ms": kernel_ms,
                     "algorithmic_bytes_per_query": bytes_per_query,
                     "per_query_branches_leaves_points": counters, "peak_source": peak_kind}
+    if leaf_scan is not None:
+        # same peak; bytes = what one launch of the isolated kernel reads and writes (queries, slot ids,
+        # leaf ranges, the leaves' float4 records, results)
+        gbs = leaf_scan["scan_bytes"] / (leaf_scan["scan_ms"] * 1e-3) / 1e9
+        leaf_scan = dict(leaf_scan, kernel="leaf_scan_kernel<float,3>", achieved=gbs, peak=peak, unit="GB/s",
+                         frac=gbs / peak, note="first leaf of every query, Z-ordered slots; ranges written by "
+                         "first_leaf_kernel (descend_ms)")
+        if roofline is not None:
+            roofline["leaf_scan"] = leaf_scan
+        else:
+            roofline = {"bound": "hbm", "leaf_scan": leaf_scan}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -352,7 +407,9 @@ def run_ours(args, n_tree, n_query):
             "tree_nodes": int(info.n_nodes), "tree_height": int(info.height), "build_ms_device": info.build_ms,
             "build_wall_s": build_wall, "tree_broadcast_ms": bcast_ms, "tree_device_bytes": int(info.device_bytes)}),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(q_host.nbytes),
-                "d2h_bytes_per_step": int(n_query * k * 8), "ms_per_step": e2e_s * 1e3, "steps": e2e_steps},
+                "d2h_bytes_per_step": int(n_query * k * 8), "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+                "pcie_floor_ms": floor_ms,
+                "pcie_floor_note": "one H2D of all queries + one D2H of all results issued together, best of 10"},
         "gpu_launches": int(args.steps * (1 + (0 if args.no_reorder else 1))),
         "gpu_launches_note": "own kernels per step: morton_kernel + knn traversal kernel (CUB radix-sort passes "
                              "of the Z-order step not counted)",

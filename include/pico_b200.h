@@ -252,6 +252,19 @@ int pico_b200_set_stream(void* cuda_stream);
 int pico_b200_profile_begin(void);
 int pico_b200_profile_end(double* traversal_ms, uint64_t* traversal_launches);
 
+/*
+ * Measurement only (SURVEY.md §8d "leaf-scan HBM GB/s"): the leaf scan of kd_tree_search.hpp:54-59 in
+ * isolation. Pass 1 walks every query (device pointer, Z-ordered like pico_b200_knn) from the root to its
+ * first leaf (kd_tree_search.hpp:60-88) and stores the leaf's point range; pass 2 only streams those
+ * contiguous point records through the search_nn visitor (search_visitor.hpp:41-65) and writes one
+ * neighbour per query to `d_neighbors_out` (device pointer) — the nearest point inside the query's own
+ * leaf. Both passes are timed with CUDA events over `repeats` runs; `scan_bytes` is what one pass-2
+ * launch reads and writes (queries, ranges, point records, results). sdim <= 3, metric_l2_squared.
+ */
+int pico_b200_profile_leaf_scan(const pico_b200_tree* tree, const void* d_queries, size_t nq, size_t stride,
+                                void* d_neighbors_out, int repeats, double* descend_ms, double* scan_ms,
+                                uint64_t* scan_bytes);
+
 void pico_b200_free(void* p);
 /* frees a device buffer returned by pico_b200_radius / pico_b200_box under PICO_B200_DEVICE_POINTERS */
 void pico_b200_free_device(void* p);

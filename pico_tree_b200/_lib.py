@@ -26,7 +26,7 @@ EXPORTS = [
     "pico_b200_tree_serialize_size", "pico_b200_tree_serialize", "pico_b200_tree_deserialize", "pico_b200_free",
     "pico_b200_free_device",
     "pico_b200_tree_save_size", "pico_b200_tree_save", "pico_b200_tree_load", "pico_b200_set_stream",
-    "pico_b200_profile_begin", "pico_b200_profile_end",
+    "pico_b200_profile_begin", "pico_b200_profile_end", "pico_b200_profile_leaf_scan",
 ]
 
 
@@ -91,6 +91,8 @@ def lib():
     L.pico_b200_set_stream.argtypes = [vp]
     L.pico_b200_profile_begin.argtypes = []
     L.pico_b200_profile_end.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
+    L.pico_b200_profile_leaf_scan.argtypes = [vp, vp, sz, sz, vp, i32, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                              C.POINTER(C.c_uint64)]
     _lib = L
     return L
 

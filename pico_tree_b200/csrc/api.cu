@@ -275,6 +275,20 @@ int pico_b200_profile_end(double* traversal_ms, uint64_t* traversal_launches) {
   return profile_end(traversal_ms, traversal_launches);
 }
 
+int pico_b200_profile_leaf_scan(const pico_b200_tree* t, const void* d_queries, size_t nq, size_t stride,
+                                void* d_neighbors_out, int repeats, double* descend_ms, double* scan_ms,
+                                uint64_t* scan_bytes) {
+  if (!t || !d_queries || !d_neighbors_out) return fail(PICO_B200_ERR_INVALID_ARGUMENT, "null argument");
+  if (stride < t->sdim) return fail(PICO_B200_ERR_INVALID_ARGUMENT, "stride smaller than sdim");
+  if (t->scalar == PICO_B200_F32)
+    return leaf_scan_profile<float>(t, static_cast<const float*>(d_queries), nq, stride,
+                                    static_cast<Neighbor<float>*>(d_neighbors_out), repeats, descend_ms, scan_ms,
+                                    scan_bytes);
+  return leaf_scan_profile<double>(t, static_cast<const double*>(d_queries), nq, stride,
+                                   static_cast<Neighbor<double>*>(d_neighbors_out), repeats, descend_ms, scan_ms,
+                                   scan_bytes);
+}
+
 // ---------------------------------------------------------------- (de)serialisation
 int pico_b200_tree_serialize_size(const pico_b200_tree* t, uint64_t* bytes) {
   if (!t || !bytes) return fail(PICO_B200_ERR_INVALID_ARGUMENT, "null argument");

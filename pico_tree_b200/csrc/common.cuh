@@ -130,6 +130,9 @@ template <typename T>
 int knn_batch(const pico_b200_tree* t, const T* q, size_t nq, size_t stride, size_t k, double e, Neighbor<T>* out,
               unsigned flags, pico_b200_search_stats* stats);
 template <typename T>
+int leaf_scan_profile(const pico_b200_tree* t, const T* d_q, size_t nq, size_t stride, Neighbor<T>* d_out, int repeats,
+                      double* descend_ms, double* scan_ms, uint64_t* scan_bytes);
+template <typename T>
 int radius_batch(const pico_b200_tree* t, const T* q, size_t nq, size_t stride, double radius, double e,
                  uint64_t* offsets_out, void** out, unsigned flags, pico_b200_search_stats* stats);
 template <typename T>

@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstring>
 #include <mutex>
 #include <thread>
@@ -129,6 +130,71 @@ __global__ void __launch_bounds__(kThreadsPerBlock) knn_thread_kernel(KnnArgs<T>
       }
       vis.store(out);
     }
+  }
+}
+
+// ------------------------------------------------------------------ isolated leaf scan (measurement)
+// SURVEY.md §8d asks for the leaf scan (kd_tree_search.hpp:54-59) timed on its own next to the fused
+// traversal: first_leaf_kernel walks root -> first leaf (kd_tree_search.hpp:60-88, no far children) and
+// stores the leaf's point range per slot; leaf_scan_kernel then only streams those contiguous float4
+// records through the search_nn visitor. Same query order (Z-order slots), same loads, same arithmetic
+// as the fused kernel's leaf loop.
+template <typename T, int DIM>
+__global__ void __launch_bounds__(kThreadsPerBlock) first_leaf_kernel(KnnArgs<T> a, int2* __restrict__ ranges,
+                                                                      unsigned long long* __restrict__ n_streamed) {
+  const size_t total = (size_t)gridDim.x * blockDim.x;
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long mine = 0;
+  for (size_t slot = tid; slot < a.nq; slot += total) {
+    const uint32_t qi = a.perm ? a.perm[slot] : (uint32_t)slot;
+    T q[DIM];
+    const T* qp = a.q + (size_t)qi * a.q_stride;
+#pragma unroll
+    for (int j = 0; j < DIM; ++j) q[j] = qp[j];
+    uint32_t node = 0, right, sd;
+    T na, nb;
+    int lb, le;
+    load_node(a.nodes, node, na, nb, right, sd, lb, le);
+    while (sd != PICO_B200_LEAF) {
+      T v = q[0];
+#pragma unroll
+      for (int j = 1; j < DIM; ++j)
+        if (sd == (uint32_t)j) v = q[j];
+      bool go_left;
+      T unused;
+      branch_choice((int)PICO_B200_METRIC_L2_SQUARED, a.outer, node, na, nb, v, sd, go_left, unused);
+      node = go_left ? node + 1 : right;
+      load_node(a.nodes, node, na, nb, right, sd, lb, le);
+    }
+    ranges[slot] = make_int2(lb, le);
+    mine += (unsigned long long)(le - lb);
+  }
+  for (int o = 16; o > 0; o >>= 1) mine += __shfl_down_sync(0xffffffffu, mine, o);
+  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(n_streamed, mine);
+}
+
+template <typename T, int DIM>
+__global__ void __launch_bounds__(kThreadsPerBlock) leaf_scan_kernel(KnnArgs<T> a, const int2* __restrict__ ranges) {
+  const size_t total = (size_t)gridDim.x * blockDim.x;
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (size_t slot = tid; slot < a.nq; slot += total) {
+    const uint32_t qi = a.perm ? a.perm[slot] : (uint32_t)slot;
+    T q[DIM];
+    const T* qp = a.q + (size_t)qi * a.q_stride;
+#pragma unroll
+    for (int j = 0; j < DIM; ++j) q[j] = qp[j];
+    const int2 r = ranges[slot];
+    VisitNn<T> vis;
+    for (int i = r.x; i < r.y; ++i) {
+      const typename Vec4Of<T>::type p = ldg4(a.pts4 + i);
+      T d = T(0);
+      d = metric_fold((int)PICO_B200_METRIC_L2_SQUARED, d, q[0], p.x, 0);
+      if (DIM > 1) d = metric_fold((int)PICO_B200_METRIC_L2_SQUARED, d, q[DIM > 1 ? 1 : 0], p.y, 1);
+      if (DIM > 2) d = metric_fold((int)PICO_B200_METRIC_L2_SQUARED, d, q[DIM > 2 ? 2 : 0], p.z, 2);
+      vis.visit(index_of(p), d);
+    }
+    a.out[qi].index = vis.idx;
+    a.out[qi].distance = vis.best;
   }
 }
 
@@ -584,12 +650,16 @@ int stage_queries(CallCtx& c, const T* q, size_t nq, size_t stride, size_t sdim,
 }
 
 // The batch is sorted on the top morton_bits() bits of the 30-bit code (stable radix sort, 8 bits per
-// pass): 24 bits = 3 passes with 8 bits per dimension. PICO_B200_MORTON_BITS is a tuning hook.
+// pass). 16 bits = 2 passes: against 24 bits the traversal loses about what the third pass costs on a
+// resident batch (1.50 vs 1.51 ms per 7.2M queries), and the 1 Mi chunks of the host pipeline, where the
+// small sort kernels are latency-bound, gain 5 % (profiles/r1/host_pipeline_sweep.txt). A counting sort
+// into 2^16 cells (warp-aggregated atomics, one-block scan, scatter) was slower than CUB's two passes
+// (1.76 ms resident, host_pipeline_sweep2.txt) and was dropped. PICO_B200_MORTON_BITS is a tuning hook.
 int morton_bits() {
   static const int v = [] {
     const char* e = getenv("PICO_B200_MORTON_BITS");
     const int x = e ? atoi(e) : 0;
-    return (x >= 3 && x <= 30) ? x : 24;  // profiles/r1/morton_sweep.txt
+    return (x >= 3 && x <= 30) ? x : 16;
   }();
   return v;
 }
@@ -607,19 +677,22 @@ int make_perm(CallCtx& c, const pico_b200_tree* t, const T* d_q, size_t stride, 
     const double ext = t->root_box_host[4 + j] - t->root_box_host[j];
     inv[j] = ext > 0 ? 1023.999 / ext : 0.0;
   }
-  uint32_t *codes = nullptr, *ids = nullptr, *codes2 = nullptr, *ids2 = nullptr;
-  PICO_TRY(c.alloc(reinterpret_cast<void**>(&codes), nq * 4));
-  PICO_TRY(c.alloc(reinterpret_cast<void**>(&ids), nq * 4));
-  PICO_TRY(c.alloc(reinterpret_cast<void**>(&codes2), nq * 4));
-  PICO_TRY(c.alloc(reinterpret_cast<void**>(&ids2), nq * 4));
+  // one workspace: 4 key / value arrays + CUB's temporary storage
+  size_t tmp_bytes = 0;
+  PICO_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr,
+                                            (uint32_t*)nullptr, (int)nq, 30 - morton_bits(), 30, c.st));
+  const size_t arr = (nq * 4 + 255) & ~(size_t)255;
+  char* ws = nullptr;
+  PICO_TRY(c.alloc(reinterpret_cast<void**>(&ws), 4 * arr + tmp_bytes));
+  uint32_t* codes = reinterpret_cast<uint32_t*>(ws);
+  uint32_t* ids = reinterpret_cast<uint32_t*>(ws + arr);
+  uint32_t* codes2 = reinterpret_cast<uint32_t*>(ws + 2 * arr);
+  uint32_t* ids2 = reinterpret_cast<uint32_t*>(ws + 3 * arr);
+  void* tmp = ws + 4 * arr;
   morton_kernel<T><<<(unsigned)((nq + 255) / 256), 256, 0, c.st>>>(d_q, stride, (uint32_t)nq, dims,
                                                                     make_double3(lo[0], lo[1], lo[2]),
                                                                     make_double3(inv[0], inv[1], inv[2]), codes, ids);
   PICO_CUDA(cudaGetLastError());
-  size_t tmp_bytes = 0;
-  PICO_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, codes, codes2, ids, ids2, (int)nq, 30 - morton_bits(), 30, c.st));
-  void* tmp = nullptr;
-  PICO_TRY(c.alloc(&tmp, tmp_bytes));
   PICO_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, codes, codes2, ids, ids2, (int)nq, 30 - morton_bits(), 30, c.st));
   *perm = ids2;
   return 0;
@@ -876,6 +949,65 @@ int host_streams() {
   }();
   return v;
 }
+// The call ends one traversal + one D2H after the last chunk's H2D, so the tail of the batch is cut
+// into halving chunks down to this many queries (0 = equal chunks). PICO_B200_HOST_TAPER is a tuning hook.
+constexpr size_t kHostTaper = 0;
+size_t host_taper() {
+  static const size_t v = [] {
+    const char* e = getenv("PICO_B200_HOST_TAPER");
+    const long long x = e ? atoll(e) : -1;
+    return x >= 0 ? (size_t)x : kHostTaper;
+  }();
+  return v;
+}
+// Chunks whose H2D copy is issued (on a copy stream of its own) before the traversal of the current one is
+// enqueued; 0 = every chunk copies on its own compute stream. PICO_B200_HOST_AHEAD is a tuning hook.
+constexpr int kHostAhead = 64;  // all chunks (profiles/r1/host_pipeline_sweep.txt)
+int host_ahead() {
+  static const int v = [] {
+    const char* e = getenv("PICO_B200_HOST_AHEAD");
+    const int x = e ? atoi(e) : -1;
+    return x >= 0 ? x : kHostAhead;
+  }();
+  return v;
+}
+constexpr size_t kHostHead = 262144;
+size_t host_head() {
+  static const size_t v = [] {
+    const char* e = getenv("PICO_B200_HOST_HEAD");
+    const long long x = e ? atoll(e) : -1;
+    return x >= 0 ? (size_t)x : kHostHead;
+  }();
+  return v;
+}
+bool host_timeline() {
+  static const bool v = getenv("PICO_B200_TIMELINE") != nullptr;  // per-chunk event times on stderr
+  return v;
+}
+
+// [begin, count) of every chunk of a pipelined host batch
+std::vector<std::pair<size_t, size_t>> host_chunk_plan(size_t nq, size_t chunk, size_t taper, size_t head) {
+  std::vector<std::pair<size_t, size_t>> plan;
+  size_t pos = 0;
+  // a short first chunk lets the first traversal start early (the device idles during the first H2D)
+  for (size_t c = head; c && c < chunk && nq - pos > 2 * chunk; c *= 2) {
+    plan.emplace_back(pos, c);
+    pos += c;
+  }
+  while (nq - pos > chunk && !(taper && nq - pos < 2 * chunk)) {
+    plan.emplace_back(pos, chunk);
+    pos += chunk;
+  }
+  if (taper) {
+    while (nq - pos > 2 * taper) {
+      const size_t c = ((nq - pos) / 2 + 4095) & ~(size_t)4095;
+      plan.emplace_back(pos, c);
+      pos += c;
+    }
+  }
+  if (nq > pos) plan.emplace_back(pos, nq - pos);
+  return plan;
+}
 
 }  // namespace
 
@@ -919,14 +1051,48 @@ int knn_batch(const pico_b200_tree* t, const T* q, size_t nq, size_t stride, siz
       PICO_TRY(g_pin_out.reserve(nq * k * sizeof(Neighbor<T>)));
       dst = static_cast<Neighbor<T>*>(g_pin_out.p);
     }
+    CallCtx cp;  // copy stream + whole-batch device buffers (declared first: released after the compute streams)
     CallCtx ctx_all[kMaxHostStreams];
     CallCtx* ctx = ctx_all;
     for (int i = 0; i < n_streams; ++i) PICO_TRY(ctx[i].init(t->device));
+    const auto plan = host_chunk_plan(nq, chunk, host_taper(), host_head());
+    const size_t n_chunks = plan.size();
+    // copy-ahead mode (pinned buffers): the queries of the next `ahead` chunks go up on one copy stream, each
+    // followed by an event its compute stream waits for, so the H2D engine never idles behind the host thread
+    // that is still enqueueing the ordering / traversal launches of earlier chunks. Pageable buffers keep the
+    // per-chunk copies on the compute streams, interleaved with the host-side packing / page touching.
+    const size_t ahead = (stage_in || stage_out || touch_out) ? 0 : (size_t)host_ahead();
+    T* d_q_all = nullptr;
+    Neighbor<T>* d_out_all = nullptr;
+    std::vector<cudaEvent_t> ready(ahead ? n_chunks : 0);
+    if (ahead) {
+      PICO_TRY(cp.init(t->device));
+      cp.timed = false;
+      PICO_TRY(cp.alloc(reinterpret_cast<void**>(&d_q_all), nq * sdim * sizeof(T)));
+      PICO_TRY(cp.alloc(reinterpret_cast<void**>(&d_out_all), nq * k * sizeof(Neighbor<T>)));
+      for (auto& ev : ready) PICO_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    }
+    size_t uploaded = 0;  // chunks whose H2D has been issued
+    auto upload_until = [&](size_t last) -> int {
+      for (; uploaded <= last && uploaded < n_chunks; ++uploaded) {
+        const size_t begin = plan[uploaded].first, cnt = plan[uploaded].second;
+        if (src_stride == sdim)
+          PICO_CUDA(cudaMemcpyAsync(d_q_all + begin * sdim, src + begin * sdim, cnt * sdim * sizeof(T),
+                                    cudaMemcpyHostToDevice, cp.st));
+        else
+          PICO_CUDA(cudaMemcpy2DAsync(d_q_all + begin * sdim, sdim * sizeof(T), src + begin * src_stride,
+                                      src_stride * sizeof(T), sdim * sizeof(T), cnt, cudaMemcpyHostToDevice, cp.st));
+        PICO_CUDA(cudaEventRecord(ready[uploaded], cp.st));
+      }
+      return 0;
+    };
     cudaEvent_t e0, e1;
     PICO_CUDA(cudaEventCreate(&e0));
     PICO_CUDA(cudaEventCreate(&e1));
-    PICO_CUDA(cudaEventRecord(e0, ctx[0].st));
-    const size_t n_chunks = (nq + chunk - 1) / chunk;
+    PICO_CUDA(cudaEventRecord(e0, ahead ? cp.st : ctx[0].st));
+    const auto cpu0 = std::chrono::steady_clock::now();
+    auto cpu_ms = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - cpu0).count(); };
+    std::vector<double> cpu_at(2 * n_chunks, 0.0);
     std::vector<cudaEvent_t> done(stage_out ? n_chunks : 0);
     for (auto& ev : done) PICO_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     // results are copied out of the pinned mirror by a second thread while this one keeps
@@ -947,31 +1113,52 @@ int knn_batch(const pico_b200_tree* t, const T* q, size_t nq, size_t stride, siz
             drain_failed.store(true);
             return;
           }
-          const size_t begin = ci * chunk, cnt = std::min(chunk, nq - begin);
+          const size_t begin = plan[ci].first, cnt = plan[ci].second;
           parallel_memcpy(reinterpret_cast<char*>(out + begin * k), reinterpret_cast<const char*>(dst + begin * k),
                           cnt * k * sizeof(Neighbor<T>));
         }
       });
     }
     int rc = 0;
-    size_t ci = 0;
-    for (size_t begin = 0; begin < nq && !rc; begin += chunk, ++ci) {
-      const size_t cnt = std::min(chunk, nq - begin);
+    const bool timeline = host_timeline() && n_chunks <= (size_t)n_streams;
+    for (size_t ci = 0; ci < n_chunks && !rc; ++ci) {
+      const size_t begin = plan[ci].first, cnt = plan[ci].second;
       CallCtx& c = ctx[ci % n_streams];
+      c.timed = timeline;
       c.release();
-      if (stage_in)
-        parallel_pack_rows(reinterpret_cast<char*>(const_cast<T*>(src) + begin * sdim),
-                           reinterpret_cast<const char*>(q + begin * stride), cnt, sdim * sizeof(T), stride * sizeof(T));
-      if (touch_out) parallel_touch(reinterpret_cast<char*>(out + begin * k), cnt * k * sizeof(Neighbor<T>));
-      rc = knn_enqueue<T>(c, t, src + begin * src_stride, cnt, src_stride, k, e, dst + begin * k, flags, false,
-                          &launches);
+      cpu_at[2 * ci] = cpu_ms();
+      if (ahead) {
+        rc = upload_until(ci + ahead - 1);
+        if (!rc && cudaStreamWaitEvent(c.st, ready[ci], 0) != cudaSuccess)
+          rc = fail(PICO_B200_ERR_CUDA, "stream wait failed");
+        if (!rc)
+          rc = knn_enqueue<T>(c, t, d_q_all + begin * sdim, cnt, sdim, k, e, d_out_all + begin * k, flags, true,
+                              &launches);
+        if (!rc && cudaMemcpyAsync(dst + begin * k, d_out_all + begin * k, cnt * k * sizeof(Neighbor<T>),
+                                   cudaMemcpyDeviceToHost, c.st) != cudaSuccess)
+          rc = fail(PICO_B200_ERR_CUDA, "result copy failed");
+        if (!rc) rc = c.mark(4);
+      } else {
+        if (stage_in)
+          parallel_pack_rows(reinterpret_cast<char*>(const_cast<T*>(src) + begin * sdim),
+                             reinterpret_cast<const char*>(q + begin * stride), cnt, sdim * sizeof(T),
+                             stride * sizeof(T));
+        if (touch_out) parallel_touch(reinterpret_cast<char*>(out + begin * k), cnt * k * sizeof(Neighbor<T>));
+        rc = knn_enqueue<T>(c, t, src + begin * src_stride, cnt, src_stride, k, e, dst + begin * k, flags, false,
+                            &launches);
+      }
       if (!rc && stage_out && cudaEventRecord(done[ci], c.st) != cudaSuccess)
         rc = fail(PICO_B200_ERR_CUDA, "event record failed");
       if (rc) failed.store(true);
       enqueued.store(ci + 1, std::memory_order_release);
+      cpu_at[2 * ci + 1] = cpu_ms();
     }
     if (drain.joinable()) drain.join();
     for (auto& ev : done) cudaEventDestroy(ev);
+    if (rc || drain_failed.load())  // quiesce before the events the streams wait on go away
+      for (int i = 0; i < n_streams; ++i) cudaStreamSynchronize(ctx[i].st);
+    if (rc || drain_failed.load())
+      for (auto& ev : ready) cudaEventDestroy(ev);
     if (!rc && drain_failed.load()) rc = fail(PICO_B200_ERR_CUDA, "copying results out of the pinned mirror failed");
     if (rc) {
       cudaEventDestroy(e0);
@@ -979,8 +1166,19 @@ int knn_batch(const pico_b200_tree* t, const T* q, size_t nq, size_t stride, siz
       return rc;
     }
     for (int i = 0; i < n_streams; ++i) PICO_CUDA(cudaStreamSynchronize(ctx[i].st));
+    for (auto& ev : ready) cudaEventDestroy(ev);
     PICO_CUDA(cudaEventRecord(e1, ctx[0].st));
     PICO_CUDA(cudaEventSynchronize(e1));
+    if (timeline) {
+      // device times of the chunk's stream (start = first work after its queries arrived when copying ahead),
+      // and the host thread's clock when it began / finished enqueueing the chunk
+      for (size_t i = 0; i < n_chunks; ++i)
+        fprintf(stderr,
+                "chunk %zu (%zu q): start %.3f h2d %.3f order %.3f traverse %.3f d2h %.3f ms | host enqueue %.3f-%.3f ms\n",
+                i, plan[i].second, elapsed(e0, ctx[i].ev[0]), elapsed(e0, ctx[i].ev[1]), elapsed(e0, ctx[i].ev[2]),
+                elapsed(e0, ctx[i].ev[3]), elapsed(e0, ctx[i].ev[4]), cpu_at[2 * i], cpu_at[2 * i + 1]);
+      fprintf(stderr, "call: %.3f ms (copy-ahead %zu)\n", elapsed(e0, e1), ahead);
+    }
     if (stats) {
       stats->h2d_ms = stats->reorder_ms = stats->d2h_ms = 0;
       stats->kernel_ms = elapsed(e0, e1);  // whole pipelined call
@@ -1562,6 +1760,77 @@ int profile_end(double* ms, uint64_t* launches) {
   return 0;
 }
 
+// ------------------------------------------------------------------ leaf scan in isolation (measurement)
+template <typename T>
+int leaf_scan_profile(const pico_b200_tree* t, const T* d_q, size_t nq, size_t stride, Neighbor<T>* d_out, int repeats,
+                      double* descend_ms, double* scan_ms, uint64_t* scan_bytes) {
+  if (!t->packed() || t->metric != PICO_B200_METRIC_L2_SQUARED)
+    return fail(PICO_B200_ERR_UNSUPPORTED, "leaf-scan profile: sdim <= 3 and metric_l2_squared only");
+  if (nq == 0 || nq > 0xfffffff0u || repeats < 1) return fail(PICO_B200_ERR_INVALID_ARGUMENT, "bad nq or repeats");
+  CallCtx c;
+  PICO_TRY(c.init(t->device));
+  c.timed = false;
+  uint32_t* perm = nullptr;
+  PICO_TRY(make_perm(c, t, d_q, stride, nq, 0, &perm));
+  KnnArgs<T> a;
+  fill_base(a, t, d_q, stride, nq, perm, 0.0);
+  a.out = d_out;
+  a.k = 1;
+  int2* ranges = nullptr;
+  unsigned long long* n_streamed = nullptr;
+  PICO_TRY(c.alloc(reinterpret_cast<void**>(&ranges), nq * sizeof(int2)));
+  PICO_TRY(c.alloc(reinterpret_cast<void**>(&n_streamed), sizeof(unsigned long long)));
+  const unsigned blocks = (unsigned)((nq + kThreadsPerBlock - 1) / kThreadsPerBlock);
+  cudaEvent_t ev[3];
+  for (auto& e : ev) PICO_CUDA(cudaEventCreate(&e));
+  double ms_descend = 0, ms_scan = 0;
+  unsigned long long streamed = 0;
+  int rc = 0;
+  for (int r = 0; r < repeats && !rc; ++r) {
+    cudaMemsetAsync(n_streamed, 0, sizeof(unsigned long long), c.st);
+    cudaEventRecord(ev[0], c.st);
+    switch (t->sdim) {
+      case 1:
+        first_leaf_kernel<T, 1><<<blocks, kThreadsPerBlock, 0, c.st>>>(a, ranges, n_streamed);
+        cudaEventRecord(ev[1], c.st);
+        leaf_scan_kernel<T, 1><<<blocks, kThreadsPerBlock, 0, c.st>>>(a, ranges);
+        break;
+      case 2:
+        first_leaf_kernel<T, 2><<<blocks, kThreadsPerBlock, 0, c.st>>>(a, ranges, n_streamed);
+        cudaEventRecord(ev[1], c.st);
+        leaf_scan_kernel<T, 2><<<blocks, kThreadsPerBlock, 0, c.st>>>(a, ranges);
+        break;
+      default:
+        first_leaf_kernel<T, 3><<<blocks, kThreadsPerBlock, 0, c.st>>>(a, ranges, n_streamed);
+        cudaEventRecord(ev[1], c.st);
+        leaf_scan_kernel<T, 3><<<blocks, kThreadsPerBlock, 0, c.st>>>(a, ranges);
+        break;
+    }
+    cudaEventRecord(ev[2], c.st);
+    cudaMemcpyAsync(&streamed, n_streamed, sizeof(streamed), cudaMemcpyDeviceToHost, c.st);
+    if (cudaStreamSynchronize(c.st) != cudaSuccess || cudaGetLastError() != cudaSuccess) {
+      rc = fail(PICO_B200_ERR_CUDA, "leaf-scan profile kernels failed");
+      break;
+    }
+    ms_descend += elapsed(ev[0], ev[1]);
+    ms_scan += elapsed(ev[1], ev[2]);
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  if (rc) return rc;
+  if (descend_ms) *descend_ms = ms_descend / repeats;
+  if (scan_ms) *scan_ms = ms_scan / repeats;
+  // per launch: slot -> query id (4 B, Z-ordered batches only), query (sdim scalars), range (8 B), the leaf's
+  // vec4 records, one neighbour record
+  if (scan_bytes)
+    *scan_bytes = nq * ((perm ? 4 : 0) + t->sdim * sizeof(T) + sizeof(int2) + sizeof(Neighbor<T>)) +
+                  streamed * 4 * sizeof(T);
+  return 0;
+}
+
+template int leaf_scan_profile<float>(const pico_b200_tree*, const float*, size_t, size_t, Neighbor<float>*, int, double*,
+                                      double*, uint64_t*);
+template int leaf_scan_profile<double>(const pico_b200_tree*, const double*, size_t, size_t, Neighbor<double>*, int,
+                                       double*, double*, uint64_t*);
 template int knn_batch<float>(const pico_b200_tree*, const float*, size_t, size_t, size_t, double, Neighbor<float>*,
                               unsigned, pico_b200_search_stats*);
 template int knn_batch<double>(const pico_b200_tree*, const double*, size_t, size_t, size_t, double,

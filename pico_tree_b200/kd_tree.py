@@ -307,6 +307,23 @@ class KdTree:
             _lib.check(L.pico_b200_set_stream(None))
         return nns
 
+    def profile_leaf_scan(self, pts, repeats=1):
+        """Measurement only (pico_b200_profile_leaf_scan): the leaf scan in isolation. `pts` is a device
+        array like in search_knn_device. Returns (nns, stats): nns[i] = nearest point inside the leaf the
+        descent of query i ends in, stats = {descend_ms, scan_ms, scan_bytes} per launch."""
+        import torch
+        ptr, shape, typestr = self._cuda_view(pts, "pts")
+        if typestr != ("<f4" if self._dtype == np.float32 else "<f8") or len(shape) != 2 or shape[1] != self.sdim:
+            raise ValueError("pts must be an (n, sdim) device array of the tree's dtype")
+        words = 2 if self._dtype == np.float32 else 4
+        nns = torch.empty((shape[0], 1, words), dtype=torch.int32, device=torch.device("cuda", self._device))
+        torch.cuda.synchronize(self._device)
+        d_ms, s_ms, nbytes = C.c_double(), C.c_double(), C.c_uint64()
+        _lib.check(_lib.lib().pico_b200_profile_leaf_scan(self._h, C.c_void_p(ptr), shape[0], self.sdim,
+                                                          C.c_void_p(nns.data_ptr()), int(repeats), C.byref(d_ms),
+                                                          C.byref(s_ms), C.byref(nbytes)))
+        return nns, {"descend_ms": d_ms.value, "scan_ms": s_ms.value, "scan_bytes": int(nbytes.value)}
+
     def search_knn(self, pts, k, *args, **kw):
         """search_knn(pts, k[, e][, nns]) — def_kd_tree.cpp:59-110. Returns / fills an array
         of shape (npts, k) (or (k, npts) for column-major input, kd_tree.hpp:362-378). Device arrays

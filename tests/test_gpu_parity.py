@@ -540,6 +540,49 @@ def test_build_paths_agree(pt, monkeypatch):
 
 
 # ---------------------------------------------------------------- BASELINE sizes: properties
+def test_isolated_leaf_scan(pt):
+    """pico_b200_profile_leaf_scan (the leaf-scan measurement of SURVEY.md §8d): the neighbour it returns is
+    the first nearest point, in leaf order, of the leaf a numpy descent over the exported nodes ends in
+    (kd_tree_search.hpp:60-88 then :54-59), with bit-equal distance; the byte count matches the ranges."""
+    import torch
+    from parity import ref_distance
+    from pico_tree_b200 import datasets as D
+    pts = D.lidar_shape(200_000, seed=1)
+    q = D.lidar_shape(100_000, seed=2, pose_shift=0.35)
+    t = pt.KdTree(pts, pt.Metric.L2Squared, 10)
+    nodes, indices, _ = t.export()
+    a, b = nodes["a"].view(np.float32), nodes["b"].view(np.float32)
+    node = np.zeros(len(q), dtype=np.int64)
+    rows = np.arange(len(q))
+    while True:
+        sd = nodes["split_dim"][node]
+        live = sd != 0xFFFFFFFF
+        if not live.any():
+            break
+        v = q[rows, np.where(live, sd, 0)]
+        left = (a[node] + b[node] - v - v) > 0  # float32, left to right
+        node = np.where(live, np.where(left, node + 1, nodes["right"][node]), node)
+    lb = nodes["a"][node].astype(np.int64)
+    le = nodes["b"][node].astype(np.int64)
+    width = int((le - lb).max())
+    pos = lb[:, None] + np.arange(width)[None, :]
+    valid = pos < le[:, None]
+    cand = indices[np.minimum(pos, len(indices) - 1)]
+    d = np.stack([ref_distance(pts, q, cand[:, j]) for j in range(width)], axis=1)
+    d[~valid] = np.inf
+    best = np.argmin(d, axis=1)  # first minimum = the strict `max() > d` of search_nn
+    nns, st = t.profile_leaf_scan(torch.from_numpy(q).cuda(), repeats=2)
+    got = nns.cpu().numpy()
+    assert np.array_equal(got[:, 0, 0], cand[rows, best])
+    assert np.array_equal(got[:, 0, 1].view(np.float32), d[rows, best].astype(np.float32))
+    assert st["scan_bytes"] == len(q) * (4 + 12 + 8 + 8) + int((le - lb).sum()) * 16
+    assert st["scan_ms"] > 0 and st["descend_ms"] > 0
+    # never better than the true nearest neighbour, and equal to it for most queries
+    nn = t.search_knn(q, 1)
+    assert np.all(got[:, 0, 1].view(np.float32) >= nn["distance"][:, 0])
+    assert np.mean(got[:, 0, 0] == nn["index"][:, 0]) > 0.3
+
+
 def test_full_size_properties(pt):
     """cfg2 at full size (7,733,372 / 7,200,863): size-independent properties instead of the oracle —
     (a) nn of a tree point is itself at distance 0; (b) nn distance is a lower bound of the distance
