@@ -212,6 +212,11 @@ def run_ours(args, n_tree, n_query):
         raise SystemExit("bench.py --impl ours needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # host buffers next to the GPU: first-touch puts the pinned pages of this rank on the GPU's NUMA node
+    # (pico_tree_b200/hostmem.py); the CPU baseline further down gets all host threads back
+    from pico_tree_b200 import hostmem
+    cpus_all = os.sched_getaffinity(0)
+    binding = hostmem.bind_to_gpu_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
@@ -310,6 +315,7 @@ def run_ours(args, n_tree, n_query):
     e2e_s = (time.perf_counter() - t0) / e2e_steps
 
     floor_ms = pcie_floor_ms(q_pin, out_pin, dev)
+    os.sched_setaffinity(0, cpus_all)
 
     # resident and host paths must agree
     res_dev = out_dev.cpu().numpy()
@@ -391,8 +397,14 @@ def run_ours(args, n_tree, n_query):
         # same peak; bytes = what one launch of the isolated kernel reads and writes (queries, slot ids,
         # leaf ranges, the leaves' float4 records, results)
         gbs = leaf_scan["scan_bytes"] / (leaf_scan["scan_ms"] * 1e-3) / 1e9
+        ls_traffic = None
+        try:
+            ls_traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(
+                "leaf_scan_dram_bytes_per_launch")
+        except (OSError, ValueError):
+            pass
         leaf_scan = dict(leaf_scan, kernel="leaf_scan_kernel<float,3>", achieved=gbs, peak=peak, unit="GB/s",
-                         frac=gbs / peak, note="first leaf of every query, Z-ordered slots; ranges written by "
+                         frac=gbs / peak, traffic=ls_traffic, note="first leaf of every query, Z-ordered slots; ranges written by "
                          "first_leaf_kernel (descend_ms)")
         if roofline is not None:
             roofline["leaf_scan"] = leaf_scan
@@ -408,7 +420,7 @@ def run_ours(args, n_tree, n_query):
             "build_wall_s": build_wall, "tree_broadcast_ms": bcast_ms, "tree_device_bytes": int(info.device_bytes)}),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(q_host.nbytes),
                 "d2h_bytes_per_step": int(n_query * k * 8), "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
-                "pcie_floor_ms": floor_ms,
+                "pcie_floor_ms": floor_ms, "host_binding": binding,
                 "pcie_floor_note": "one H2D of all queries + one D2H of all results issued together, best of 10"},
         "gpu_launches": int(args.steps * (1 + (0 if args.no_reorder else 1))),
         "gpu_launches_note": "own kernels per step: morton_kernel + knn traversal kernel (CUB radix-sort passes "

@@ -1,5 +1,6 @@
-"""Workload for ncu captures: cfg2 tree, then knn=1, knn=16 and radius r^2=0.01 once each with
-device-resident queries (see profiles/README.md for the command lines)."""
+"""Workload for ncu captures: cfg2 tree, then knn=1, knn=16, radius r^2=0.01 and the isolated leaf scan
+("leaf": first_leaf_kernel + leaf_scan_kernel) with device-resident queries (see profiles/README.md for the
+command lines)."""
 import ctypes as C
 import os
 import sys
@@ -25,6 +26,8 @@ for w in which:
         for _ in range(2):
             _lib.check(L.pico_b200_knn(tree._h, C.c_void_p(qd.data_ptr()), len(q), 3, k, 0.0,
                                        C.c_void_p(out.data_ptr()), _lib.FLAG_DEVICE_POINTERS, None))
+    elif w == "leaf":
+        tree.profile_leaf_scan(qd, repeats=2)
     elif w == "radius":
         n = 2_000_000
         offs = torch.empty(n + 1, dtype=torch.int64, device=dev)
