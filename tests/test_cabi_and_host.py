@@ -105,3 +105,17 @@ def test_datasets_are_deterministic():
     assert not np.array_equal(a, D.lidar_shape(10000, seed=4))
     s = D.sift_shape(100)
     assert s.shape == (100, 128) and s.min() >= 0 and s.max() <= 255 and np.all(s == np.floor(s))
+
+
+def test_hostmem_helpers_without_gpu():
+    """pico_tree_b200/hostmem.py: cpulist parsing, and binding is a described no-op where the GPU's NUMA node
+    cannot be told (no GPU here)."""
+    import os
+
+    from pico_tree_b200 import hostmem
+    assert hostmem._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert hostmem._parse_cpulist("") == set()
+    before = os.sched_getaffinity(0)
+    info = hostmem.bind_to_gpu_node(0)
+    assert info["bound"] is False and info["numa_node"] is None
+    assert os.sched_getaffinity(0) == before
