@@ -649,25 +649,29 @@ int stage_queries(CallCtx& c, const T* q, size_t nq, size_t stride, size_t sdim,
   return 0;
 }
 
-// The batch is sorted on the top morton_bits() bits of the 30-bit code (stable radix sort, 8 bits per
-// pass). 16 bits = 2 passes: against 24 bits the traversal loses about what the third pass costs on a
-// resident batch (1.50 vs 1.51 ms per 7.2M queries), and the 1 Mi chunks of the host pipeline, where the
-// small sort kernels are latency-bound, gain 5 % (profiles/r1/host_pipeline_sweep.txt). A counting sort
-// into 2^16 cells (warp-aggregated atomics, one-block scan, scatter) was slower than CUB's two passes
-// (1.76 ms resident, host_pipeline_sweep2.txt) and was dropped. PICO_B200_MORTON_BITS is a tuning hook.
-int morton_bits() {
-  static const int v = [] {
+// The batch is sorted on the top bits of the 30-bit code (stable radix sort, 8 bits per pass): 16 bits
+// (2 passes) for single-neighbour searches, 24 bits (3 passes) for everything else. At k = 1 the third pass
+// costs a resident batch what the finer order saves in the traversal (1.50 vs 1.51 ms per 7.2M queries),
+// and the 1 Mi chunks of the host pipeline, where the small sort kernels are latency-bound, gain 5 %
+// (profiles/r1/host_pipeline_sweep.txt); the heavier traversals (k = 16: 6.3 ms, radius) keep the finer
+// order. A counting sort into 2^16 cells (warp-aggregated atomics, one-block scan, scatter) was slower
+// than CUB's two passes (1.76 ms resident, host_pipeline_sweep2.txt) and was dropped.
+// PICO_B200_MORTON_BITS overrides both (tuning hook).
+constexpr int kMortonBitsNn = 16, kMortonBits = 24;
+int morton_bits(bool single_neighbour) {
+  static const int forced = [] {
     const char* e = getenv("PICO_B200_MORTON_BITS");
     const int x = e ? atoi(e) : 0;
-    return (x >= 3 && x <= 30) ? x : 16;
+    return (x >= 3 && x <= 30) ? x : 0;
   }();
-  return v;
+  return forced ? forced : (single_neighbour ? kMortonBitsNn : kMortonBits);
 }
 
 // Z-order permutation of the batch (device). Returns nullptr in *perm for tiny batches.
 template <typename T>
 int make_perm(CallCtx& c, const pico_b200_tree* t, const T* d_q, size_t stride, size_t nq, unsigned flags,
-              uint32_t** perm) {
+              uint32_t** perm, bool single_neighbour = false) {
+  const int bits = morton_bits(single_neighbour);
   *perm = nullptr;
   if ((flags & PICO_B200_NO_REORDER) || nq < 2048) return 0;
   const int dims = (int)std::min<size_t>(t->sdim, 3);
@@ -680,7 +684,7 @@ int make_perm(CallCtx& c, const pico_b200_tree* t, const T* d_q, size_t stride, 
   // one workspace: 4 key / value arrays + CUB's temporary storage
   size_t tmp_bytes = 0;
   PICO_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr,
-                                            (uint32_t*)nullptr, (int)nq, 30 - morton_bits(), 30, c.st));
+                                            (uint32_t*)nullptr, (int)nq, 30 - bits, 30, c.st));
   const size_t arr = (nq * 4 + 255) & ~(size_t)255;
   char* ws = nullptr;
   PICO_TRY(c.alloc(reinterpret_cast<void**>(&ws), 4 * arr + tmp_bytes));
@@ -693,7 +697,7 @@ int make_perm(CallCtx& c, const pico_b200_tree* t, const T* d_q, size_t stride, 
                                                                     make_double3(lo[0], lo[1], lo[2]),
                                                                     make_double3(inv[0], inv[1], inv[2]), codes, ids);
   PICO_CUDA(cudaGetLastError());
-  PICO_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, codes, codes2, ids, ids2, (int)nq, 30 - morton_bits(), 30, c.st));
+  PICO_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, codes, codes2, ids, ids2, (int)nq, 30 - bits, 30, c.st));
   *perm = ids2;
   return 0;
 }
@@ -868,7 +872,7 @@ int knn_enqueue(CallCtx& c, const pico_b200_tree* t, const T* q, size_t nq, size
   if (!on_device) PICO_TRY(c.alloc(reinterpret_cast<void**>(&d_out), nq * k * sizeof(Neighbor<T>)));
   PICO_TRY(c.mark(1));
   uint32_t* perm = nullptr;
-  PICO_TRY(make_perm(c, t, d_q, d_stride, nq, flags, &perm));
+  PICO_TRY(make_perm(c, t, d_q, d_stride, nq, flags, &perm, k == 1));
   PICO_TRY(c.mark(2));
   PICO_TRY(c.span_begin());
 
@@ -1771,7 +1775,7 @@ int leaf_scan_profile(const pico_b200_tree* t, const T* d_q, size_t nq, size_t s
   PICO_TRY(c.init(t->device));
   c.timed = false;
   uint32_t* perm = nullptr;
-  PICO_TRY(make_perm(c, t, d_q, stride, nq, 0, &perm));
+  PICO_TRY(make_perm(c, t, d_q, stride, nq, 0, &perm, true));
   KnnArgs<T> a;
   fill_base(a, t, d_q, stride, nq, perm, 0.0);
   a.out = d_out;
