@@ -80,7 +80,15 @@ def lib():
 
 
 def max_threads():
-    return int(lib().po_max_threads())
+    """Host threads the batch loops may use: the CPUs this process is allowed on. (Not omp_get_max_threads():
+    torchrun exports OMP_NUM_THREADS=1 to its workers, which would silently make the all-cores reference arm
+    single-threaded; the loops take their thread count explicitly, `num_threads(threads)`.)"""
+    if int(lib().po_max_threads()) < 1:
+        return 1
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
 
 def _take(ptr, count, dtype, free):
