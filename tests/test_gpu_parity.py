@@ -583,6 +583,41 @@ def test_isolated_leaf_scan(pt):
     assert np.mean(got[:, 0, 0] == nn["index"][:, 0]) > 0.3
 
 
+def test_pinned_host_pipeline(pt):
+    """Pinned host buffers take the copy-ahead pipeline of pico_b200_knn (all H2D copies up front on a copy
+    stream, head chunks, per-chunk Z-order / traversal / D2H): same neighbours as the resident path, for packed
+    rows, for rows with padding (stride 4: the 2-D copy) and for pageable buffers (per-chunk copies)."""
+    import ctypes as C
+
+    import torch
+    from pico_tree_b200 import _lib, datasets as D
+    pts = D.uniform(300_000, 3, seed=3)
+    nq = 2_600_000  # > 2 chunks of 1 Mi: the chunked path
+    q = D.uniform(nq, 3, seed=4)
+    t = pt.KdTree(pts, pt.Metric.L2Squared, 10)
+    want = t.search_knn(torch.from_numpy(q).cuda(), 1).cpu().numpy().reshape(nq, 2)
+    L = _lib.lib()
+    for k in (1, 3):
+        ref = want if k == 1 else t.search_knn(torch.from_numpy(q).cuda(), k).cpu().numpy().reshape(nq, k * 2)
+        # packed pinned rows
+        qp = torch.from_numpy(q).pin_memory()
+        out = torch.zeros((nq, k * 2), dtype=torch.int32).pin_memory()
+        _lib.check(L.pico_b200_knn(t._h, C.c_void_p(qp.data_ptr()), nq, 3, k, 0.0, C.c_void_p(out.data_ptr()), 0, None))
+        assert np.array_equal(out.numpy(), ref)
+        # padded pinned rows (stride 4)
+        q4 = torch.zeros((nq, 4), dtype=torch.float32).pin_memory()
+        q4[:, :3] = torch.from_numpy(q)
+        q4[:, 3] = 1e30
+        out.zero_()
+        _lib.check(L.pico_b200_knn(t._h, C.c_void_p(q4.data_ptr()), nq, 4, k, 0.0, C.c_void_p(out.data_ptr()), 0, None))
+        assert np.array_equal(out.numpy(), ref)
+        # pageable buffers, twice (the second big pageable batch of a thread goes through the pinned mirrors)
+        for _ in range(2):
+            got = t.search_knn(q, k)
+            assert np.array_equal(got["index"], ref[:, 0::2])
+            assert np.array_equal(got["distance"], ref[:, 1::2].view(np.float32))
+
+
 def test_full_size_properties(pt):
     """cfg2 at full size (7,733,372 / 7,200,863): size-independent properties instead of the oracle —
     (a) nn of a tree point is itself at distance 0; (b) nn distance is a lower bound of the distance
