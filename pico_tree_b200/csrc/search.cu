@@ -1065,7 +1065,11 @@ int knn_batch(const pico_b200_tree* t, const T* q, size_t nq, size_t stride, siz
     // followed by an event its compute stream waits for, so the H2D engine never idles behind the host thread
     // that is still enqueueing the ordering / traversal launches of earlier chunks. Pageable buffers keep the
     // per-chunk copies on the compute streams, interleaved with the host-side packing / page touching.
-    const size_t ahead = (stage_in || stage_out || touch_out) ? 0 : (size_t)host_ahead();
+    // (whole-batch device buffers: only while they stay small against the HBM; huge batches keep per-chunk buffers)
+    constexpr size_t kAheadBudget = (size_t)8 << 30;
+    const size_t batch_bytes = nq * sdim * sizeof(T) + nq * k * sizeof(Neighbor<T>);
+    const size_t ahead =
+        (stage_in || stage_out || touch_out || batch_bytes > kAheadBudget) ? 0 : (size_t)host_ahead();
     T* d_q_all = nullptr;
     Neighbor<T>* d_out_all = nullptr;
     std::vector<cudaEvent_t> ready(ahead ? n_chunks : 0);
