@@ -73,6 +73,14 @@ def lib():
             getattr(L, f"po_splitter_once_{s}").argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p,
                                                             C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p,
                                                             C.POINTER(C.c_size_t), C.c_void_p]
+            getattr(L, f"po_forest_build_{s}").restype = C.c_void_p
+            getattr(L, f"po_forest_build_{s}").argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t,
+                                                           C.c_void_p, C.c_size_t]
+            getattr(L, f"po_forest_free_{s}").argtypes = [C.c_void_p]
+            getattr(L, f"po_forest_space_{s}").restype = C.c_void_p
+            getattr(L, f"po_forest_space_{s}").argtypes = [C.c_void_p, C.c_size_t]
+            getattr(L, f"po_forest_knn_batch_{s}").argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t,
+                                                               C.c_size_t, C.c_size_t, C.c_void_p, C.c_int]
         L.po_free_buffer.argtypes = [C.c_void_p]
         L.po_max_threads.restype = C.c_int
         _lib = L
@@ -346,3 +354,83 @@ class RefTree(_Base):
         p = C.c_void_p()
         ref_lib().ref_box(self._h, _ptr(mins), _ptr(maxs), len(mins), _ptr(offs), C.byref(p))
         return offs, _take(p, int(offs[-1]), np.int32, ref_lib().ref_free_buffer)
+
+
+# ---------------------------------------------------------------------------------------------- kd_forest
+# SURVEY.md §8 f4 (examples/pico_understory/pico_understory/kd_forest.hpp): oracle first, product next round.
+_ref_forest_lib = None
+
+
+def ref_forest_available():
+    return os.path.exists(os.path.join(_HERE, "_ref", "libpico_ref_forest.so"))
+
+
+def ref_forest_lib():
+    global _ref_forest_lib
+    if _ref_forest_lib is None:
+        L = C.CDLL(os.path.join(_HERE, "_ref", "libpico_ref_forest.so"))
+        L.ref_forest_create.restype = C.c_void_p
+        L.ref_forest_create.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_size_t, C.c_size_t]
+        L.ref_forest_free.argtypes = [C.c_void_p]
+        L.ref_forest_size.restype = C.c_size_t
+        L.ref_forest_size.argtypes = [C.c_void_p]
+        L.ref_forest_rotations.argtypes = [C.c_void_p, C.c_void_p]
+        L.ref_forest_knn.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p, C.c_int]
+        _ref_forest_lib = L
+    return _ref_forest_lib
+
+
+class RefForest(_Base):
+    """The unmodified reference kd_forest<space_map<point_map<T const, dynamic_extent>>> (its Householder vectors
+    come from std::random_device; `rotations` returns the ones this instance drew)."""
+
+    def __init__(self, pts, max_leaf_size=10, forest_size=4):
+        self._prep(pts)
+        self._h = ref_forest_lib().ref_forest_create(_ptr(self.pts), self.n, self.sdim, int(self.dtype == np.float64),
+                                                     int(max_leaf_size), int(forest_size))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            ref_forest_lib().ref_forest_free(self._h)
+            self._h = None
+
+    @property
+    def rotations(self):
+        out = np.empty((int(ref_forest_lib().ref_forest_size(self._h)), self.sdim), dtype=self.dtype)
+        ref_forest_lib().ref_forest_rotations(self._h, _ptr(out))
+        return out
+
+    def search_knn(self, q, k, max_leaves_visited, threads=1):
+        q = self._q(q)
+        out = np.empty((len(q), int(k)), dtype=self.nb_dtype)
+        ref_forest_lib().ref_forest_knn(self._h, _ptr(q), len(q), int(k), int(max_leaves_visited), _ptr(out),
+                                        int(threads))
+        return out
+
+
+class OracleForest(_Base):
+    """Plain-C restatement of kd_forest (po_forest_*), Householder vectors given."""
+
+    def __init__(self, pts, rotations, max_leaf_size=10):
+        self._prep(pts)
+        self.s = _sfx(self.dtype)
+        self.rot = np.ascontiguousarray(rotations, dtype=self.dtype).reshape(-1, self.sdim)
+        self._h = getattr(lib(), f"po_forest_build_{self.s}")(_ptr(self.pts), self.n, self.sdim, self.sdim,
+                                                              int(max_leaf_size), _ptr(self.rot), len(self.rot))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            getattr(lib(), f"po_forest_free_{self.s}")(self._h)
+            self._h = None
+
+    def rotated_space(self, t):
+        p = getattr(lib(), f"po_forest_space_{self.s}")(self._h, int(t))
+        buf = (C.c_char * (self.n * self.sdim * self.dtype.itemsize)).from_address(p)
+        return np.frombuffer(buf, dtype=self.dtype).copy().reshape(self.n, self.sdim)
+
+    def search_knn(self, q, k, max_leaves_visited, threads=1):
+        q = self._q(q)
+        out = np.empty((len(q), int(k)), dtype=self.nb_dtype)
+        getattr(lib(), f"po_forest_knn_batch_{self.s}")(self._h, _ptr(q), len(q), self.sdim, int(k),
+                                                        int(max_leaves_visited), _ptr(out), int(threads))
+        return out

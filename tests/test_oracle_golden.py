@@ -182,3 +182,51 @@ def test_introselect_heap_select_fallback_matches_reference(oracle):
         assert np.array_equal(idx, o.indices), key
         for f in GOLDEN_NODE_FIELDS:
             assert np.array_equal(o.nodes[f], nodes[f]), (key, f)
+
+
+# ---------------------------------------------------------------- kd_forest: oracle first
+def _forest_files():
+    d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "forest")
+    return sorted(glob.glob(os.path.join(d, "*.npz")))
+
+
+def test_forest_fixtures_present():
+    assert len(_forest_files()) >= 4
+
+
+@pytest.mark.parametrize("path", _forest_files(), ids=lambda p: os.path.basename(p)[:-4])
+def test_forest_oracle_matches_reference_fixture(oracle, path):
+    """po_forest_* (Householder-rotated copies, one kd-tree each, best-bin-first search bounded by
+    max_leaves_visited) against outputs of the unmodified pico_tree::kd_forest on the vectors that forest drew
+    (oracle/make_golden_forest.py): indices and rotated-space distances bit for bit."""
+    g = np.load(path)
+    f = oracle.OracleForest(g["pts"], g["rotations"], int(g["max_leaf_size"]))
+    # the reflection is an isometry up to rounding, and applying it twice gives the point back
+    r0 = f.rotated_space(0)
+    assert np.allclose(np.linalg.norm(r0, axis=1), np.linalg.norm(g["pts"], axis=1), rtol=1e-4)
+    for k, ml in g["searches"]:
+        r = f.search_knn(g["q"], int(k), int(ml), threads=2)
+        assert np.array_equal(r["index"], g[f"index_k{k}_m{ml}"]), (k, ml)
+        assert np.array_equal(r["distance"], g[f"distance_k{k}_m{ml}"]), (k, ml)
+    # with no leaf budget and one neighbour the forest is exact: same point as the plain kd-tree
+    exact = oracle.OracleTree(g["pts"], int(g["max_leaf_size"])).search_knn(g["q"], 1)
+    got = f.search_knn(g["q"], 1, 1 << 30)
+    d_true = ((g["q"].astype(np.float64) - g["pts"][got["index"][:, 0]].astype(np.float64)) ** 2).sum(1)
+    assert np.allclose(d_true, exact["distance"][:, 0].astype(np.float64), rtol=1e-4, atol=1e-12)
+
+
+def test_forest_oracle_matches_live_reference(oracle):
+    if not oracle.ref_forest_available():
+        pytest.skip("oracle/_ref/libpico_ref_forest.so not built here")
+    rng = np.random.default_rng(11)
+    for dtype, n, sdim, leaf, trees in ((np.float32, 15000, 3, 10, 4), (np.float64, 4000, 24, 6, 5),
+                                        (np.float32, 9, 2, 1, 3)):
+        pts = rng.random((n, sdim)).astype(dtype)
+        pts[::7] = pts[2]  # duplicates
+        q = rng.random((2000, sdim)).astype(dtype)
+        ref = oracle.RefForest(pts, leaf, trees)
+        ora = oracle.OracleForest(pts, ref.rotations, leaf)
+        for k, ml in ((1, 1), (1, 7), (1, 1 << 30), (5, 16)):
+            a, b = ref.search_knn(q, k, ml), ora.search_knn(q, k, ml, threads=4)
+            assert np.array_equal(a["index"], b["index"]), (dtype, n, sdim, k, ml)
+            assert np.array_equal(a["distance"], b["distance"]), (dtype, n, sdim, k, ml)
