@@ -77,6 +77,8 @@ def lib():
             getattr(L, f"po_forest_build_{s}").argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t,
                                                            C.c_void_p, C.c_size_t]
             getattr(L, f"po_forest_free_{s}").argtypes = [C.c_void_p]
+            getattr(L, f"po_forest_tree_{s}").restype = C.c_void_p
+            getattr(L, f"po_forest_tree_{s}").argtypes = [C.c_void_p, C.c_size_t]
             getattr(L, f"po_forest_space_{s}").restype = C.c_void_p
             getattr(L, f"po_forest_space_{s}").argtypes = [C.c_void_p, C.c_size_t]
             getattr(L, f"po_forest_knn_batch_{s}").argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t,
@@ -423,6 +425,10 @@ class OracleForest(_Base):
             getattr(lib(), f"po_forest_free_{self.s}")(self._h)
             self._h = None
 
+    def tree(self, t):
+        """Tree t of the forest as an OracleTree view (nodes, outer_bounds, indices, height); owned by the forest."""
+        return _ForestTreeView(self, int(t))
+
     def rotated_space(self, t):
         p = getattr(lib(), f"po_forest_space_{self.s}")(self._h, int(t))
         buf = (C.c_char * (self.n * self.sdim * self.dtype.itemsize)).from_address(p)
@@ -434,3 +440,14 @@ class OracleForest(_Base):
         getattr(lib(), f"po_forest_knn_batch_{self.s}")(self._h, _ptr(q), len(q), self.sdim, int(k),
                                                         int(max_leaves_visited), _ptr(out), int(threads))
         return out
+
+
+class _ForestTreeView(OracleTree):
+    def __init__(self, forest, t):  # noqa: super().__init__ not called: nothing is built here
+        self._forest = forest  # keeps the owner alive
+        self.s, self.dtype, self.nb_dtype = forest.s, forest.dtype, forest.nb_dtype
+        self.n, self.sdim, self.metric = forest.n, forest.sdim, "l2_squared"
+        self._h = getattr(lib(), f"po_forest_tree_{self.s}")(forest._h, t)
+
+    def __del__(self):
+        self._h = None
