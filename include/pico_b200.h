@@ -240,7 +240,9 @@ int pico_b200_tree_load(const void* pts, size_t n, size_t sdim, size_t stride, i
 /*
  * Caller-provided CUDA stream (cudaStream_t) for the calling host thread; NULL restores the
  * default (a private stream per call). With a caller stream the searches are ordered on that
- * stream, so they compose with the caller's own kernels, events and CUDA graphs.
+ * stream, so they compose with the caller's own kernels, events and CUDA graphs. NULL never means
+ * "the default stream": pass cudaStreamLegacy ((cudaStream_t)0x1) or cudaStreamPerThread (0x2) to
+ * order the searches after work pending on those.
  */
 int pico_b200_set_stream(void* cuda_stream);
 

@@ -76,6 +76,7 @@ void release(pico_b200_tree* t) {
   cudaFree(t->d_root_box);
   cudaFree(t->d_outer);
   cudaFree(t->d_spans);
+  cudaFree(t->d_fat_nodes);
   delete t;
 }
 
@@ -380,6 +381,11 @@ int pico_b200_tree_deserialize(const void* src, uint64_t bytes, int src_is_devic
   t->device_bytes =
       t->pts_bytes() + t->n_nodes * t->node_size() + t->n * 4 + 2 * t->sdim * t->scalar_size() + t->outer_bytes() +
       t->spans_bytes();
+  rc = build_fat_nodes(t, nullptr);
+  if (rc) {
+    release(t);
+    return rc;
+  }
   *out = t;
   return 0;
 }

@@ -1220,6 +1220,7 @@ int build_tree(pico_b200_tree* t, const T* h_pts, size_t stride, int rule, int s
                                                         static_cast<T*>(t->d_outer), t->d_spans);
   PICO_CUDA(cudaGetLastError());
   PICO_TRY(finalize_storage<T>(t, raw.as<T>(), st));
+  PICO_TRY(build_fat_nodes(t, st));
   PICO_CUDA(cudaEventRecord(ev1, st));
   PICO_CUDA(cudaStreamSynchronize(st));
   float ms = 0;
@@ -1309,6 +1310,7 @@ int upload_tree(pico_b200_tree* t, const T* h_pts, size_t stride, const void* h_
     t->root_box_host[4 + d] = (double)root_box[sdim + d];
   }
   PICO_TRY(finalize_storage<T>(t, raw.as<T>(), st));
+  PICO_TRY(build_fat_nodes(t, st));
   PICO_CUDA(cudaStreamSynchronize(st));
   return 0;
 }

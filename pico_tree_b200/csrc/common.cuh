@@ -84,6 +84,7 @@ struct Limits<double> {
 constexpr int kMaxPackedDim = 3;   // sdim <= 3 uses the Vec4 layout
 constexpr int kLocalStack = 64;    // traversal stack kept in per-thread local memory
 constexpr int kSmBlocks = 148;     // B200 SM count (grid sizing; queried at runtime too)
+constexpr int kFatLeafPoints = 32; // subtrees of at most this many points are one leaf of the search image (fat.cu)
 
 }  // namespace pico
 
@@ -99,6 +100,8 @@ struct pico_b200_tree {
   void* d_root_box = nullptr;  // min[sdim] then max[sdim], device copy
   void* d_outer = nullptr;     // topological metrics: {left_min, right_max}[n_nodes] (kd_tree_node.hpp:52-59)
   uint2* d_spans = nullptr;    // row storage (sdim > 3): {first point, point count} below every node
+  void* d_fat_nodes = nullptr; // packed trees: `nodes` with small subtrees collapsed into leaves (fat.cu), or null
+  int fat_limit = 0;           // points per collapsed subtree (0 = no search image)
   double root_box_host[2 * 4] = {0};  // first min(sdim,4) dims, as double, for query ordering
   double build_ms = 0.0;
   size_t device_bytes = 0;
@@ -121,6 +124,9 @@ int build_tree(pico_b200_tree* t, const T* h_pts, size_t stride, int rule, int s
 template <typename T>
 int upload_tree(pico_b200_tree* t, const T* h_pts, size_t stride, const void* nodes, size_t n_nodes,
                 const int32_t* indices, const T* root_box, const T* outer_bounds);
+
+// fat.cu: (re)builds t->d_fat_nodes from t->d_nodes; every way of making a tree ends with it
+int build_fat_nodes(pico_b200_tree* t, cudaStream_t st);
 
 // search.cu
 int set_thread_stream(void* stream, bool has);

@@ -81,13 +81,22 @@ struct KnnArgs {
   int warp_smem, tile_rows, cache_rows;
   // warp kernels are persistent (one wave of resident blocks): every warp draws its next query here
   unsigned long long* counter;
+  // exact nn over the search image (nn_fat_kernel): collapsed nodes, the array far children are walked in,
+  // and the list of queries whose best distance is attained twice (re-run by knn_thread_kernel, which
+  // then takes its query count from *nq_from)
+  const typename NodeOf<T>::type* fat;
+  const typename NodeOf<T>::type* far_nodes;
+  uint32_t* tie_count;
+  uint32_t* tie_list;
+  const uint32_t* nq_from;
 };
 
 template <typename T, int DIM, int KMAX, bool FAST, bool DEEP>
 __global__ void __launch_bounds__(kThreadsPerBlock) knn_thread_kernel(KnnArgs<T> a) {
   const size_t total = (size_t)gridDim.x * blockDim.x;
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  for (size_t slot = tid; slot < a.nq; slot += total) {
+  const uint32_t nq = a.nq_from ? *a.nq_from : a.nq;
+  for (size_t slot = tid; slot < nq; slot += total) {
     const uint32_t qi = a.perm ? a.perm[slot] : (uint32_t)slot;
     T q[DIM];
     const T* qp = a.q + (size_t)qi * a.q_stride;
@@ -130,6 +139,28 @@ __global__ void __launch_bounds__(kThreadsPerBlock) knn_thread_kernel(KnnArgs<T>
       }
       vis.store(out);
     }
+  }
+}
+
+// Exact nn over the search image (fat.cu, traverse_nn_fat): metric_l2_squared, k = 1, trees no deeper than the
+// local stack. Queries with a tie at the best distance are listed for the order-exact kernel above.
+template <typename T, int DIM, int NREC>
+__global__ void __launch_bounds__(kThreadsPerBlock) nn_fat_kernel(KnnArgs<T> a) {
+  const size_t total = (size_t)gridDim.x * blockDim.x;
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (size_t slot = tid; slot < a.nq; slot += total) {
+    const uint32_t qi = a.perm ? a.perm[slot] : (uint32_t)slot;
+    T q[DIM];
+    const T* qp = a.q + (size_t)qi * a.q_stride;
+#pragma unroll
+    for (int j = 0; j < DIM; ++j) q[j] = qp[j];
+    VisitNnTie<T> vis;
+    LocalStack<T, DIM, kLocalStack> st;
+    traverse_nn_fat<T, DIM, NREC>(a.fat, a.far_nodes, a.pts4, q, st, vis);
+    Neighbor<T>* out = a.out + qi;
+    out->index = vis.idx;
+    out->distance = vis.best;
+    if (vis.tie) a.tie_list[atomicAdd(a.tie_count, 1u)] = qi;
   }
 }
 
@@ -728,6 +759,9 @@ void fill_base(KnnArgs<T>& a, const pico_b200_tree* t, const T* d_q, size_t d_st
   a.tile_rows = 0;
   a.cache_rows = 0;
   a.counter = nullptr;
+  a.fat = a.far_nodes = nullptr;
+  a.tie_count = a.tie_list = nullptr;
+  a.nq_from = nullptr;
 }
 
 // Shared memory per warp of the warp-per-query kernels, in bytes; decides whether leaves are
@@ -854,6 +888,17 @@ void launch_knn_thread(const KnnArgs<T>& a, bool fast, bool deep, unsigned block
   }
 }
 
+// PICO_B200_NN_FAT (tuning hook): 0 = order-exact kernel only; bit 0 = search image on; bit 1 = far children
+// are walked in the search image too (default: in the real tree); bit 2 = no prefix-minimum restart records
+int nn_fat_mode() {
+  static const int v = [] {
+    const char* e = getenv("PICO_B200_NN_FAT");
+    const int x = e ? atoi(e) : -1;
+    return (x >= 0 && x <= 7) ? x : 1;
+  }();
+  return v;
+}
+
 float elapsed(cudaEvent_t a, cudaEvent_t b) {
   float ms = 0;
   cudaEventElapsedTime(&ms, a, b);
@@ -887,16 +932,50 @@ int knn_enqueue(CallCtx& c, const pico_b200_tree* t, const T* q, size_t nq, size
     unsigned blocks;
     PICO_TRY(thread_geometry(c, t, a, (int)t->sdim, &deep, &blocks));
     const bool fast = t->metric == PICO_B200_METRIC_L2_SQUARED && !(e > 0);
-    switch (t->sdim) {
-      case 1:
-        launch_knn_thread<T, 1>(a, fast, deep, blocks, c.st);
-        break;
-      case 2:
-        launch_knn_thread<T, 2>(a, fast, deep, blocks, c.st);
-        break;
-      default:
-        launch_knn_thread<T, 3>(a, fast, deep, blocks, c.st);
-        break;
+    const int fat_mode = nn_fat_mode();
+    if (fast && !deep && k == 1 && t->d_fat_nodes && fat_mode && t->sdim >= 2) {
+      // exact nn over the search image; ties at the best distance go through the order-exact kernel after
+      uint32_t* tie = nullptr;
+      PICO_TRY(c.alloc(reinterpret_cast<void**>(&tie), (nq + 1) * sizeof(uint32_t)));
+      PICO_CUDA(cudaMemsetAsync(tie, 0, sizeof(uint32_t), c.st));
+      a.fat = static_cast<const typename NodeOf<T>::type*>(t->d_fat_nodes);
+      a.far_nodes = (fat_mode & 2) ? a.fat : a.nodes;
+      a.tie_count = tie;
+      a.tie_list = tie + 1;
+      const bool rec = !(fat_mode & 4);
+      if (t->sdim == 2) {
+        if (rec)
+          nn_fat_kernel<T, 2, 3><<<blocks, kThreadsPerBlock, 0, c.st>>>(a);
+        else
+          nn_fat_kernel<T, 2, 0><<<blocks, kThreadsPerBlock, 0, c.st>>>(a);
+      } else {
+        if (rec)
+          nn_fat_kernel<T, 3, 3><<<blocks, kThreadsPerBlock, 0, c.st>>>(a);
+        else
+          nn_fat_kernel<T, 3, 0><<<blocks, kThreadsPerBlock, 0, c.st>>>(a);
+      }
+      PICO_CUDA(cudaGetLastError());
+      KnnArgs<T> f = a;
+      f.perm = a.tie_list;
+      f.nq_from = a.tie_count;
+      const unsigned fix_blocks = std::min<unsigned>(blocks, (unsigned)t->sm_count * 2);
+      if (t->sdim == 2)
+        knn_thread_kernel<T, 2, 1, true, false><<<fix_blocks, kThreadsPerBlock, 0, c.st>>>(f);
+      else
+        knn_thread_kernel<T, 3, 1, true, false><<<fix_blocks, kThreadsPerBlock, 0, c.st>>>(f);
+      *launches += 1;
+    } else {
+      switch (t->sdim) {
+        case 1:
+          launch_knn_thread<T, 1>(a, fast, deep, blocks, c.st);
+          break;
+        case 2:
+          launch_knn_thread<T, 2>(a, fast, deep, blocks, c.st);
+          break;
+        default:
+          launch_knn_thread<T, 3>(a, fast, deep, blocks, c.st);
+          break;
+      }
     }
   } else {
     unsigned blocks;
@@ -1020,7 +1099,7 @@ template <typename T>
 int knn_batch(const pico_b200_tree* t, const T* q, size_t nq, size_t stride, size_t k, double e, Neighbor<T>* out,
               unsigned flags, pico_b200_search_stats* stats) {
   if (nq == 0 || k == 0) return 0;
-  if (nq > 0xfffffff0u) return fail(PICO_B200_ERR_UNSUPPORTED, "more than 2^32-16 queries in one call");
+  if (nq > 0x7fffffffu) return fail(PICO_B200_ERR_UNSUPPORTED, "more than 2^31-1 queries in one call (sort and scan counts are 32-bit)");
   if (k > 0x7fffffffu) return fail(PICO_B200_ERR_INVALID_ARGUMENT, "k too large");
   const bool on_device = flags & PICO_B200_DEVICE_POINTERS;
   const bool want_async = (flags & PICO_B200_ASYNC) && on_device;
@@ -1429,7 +1508,7 @@ template <typename T>
 int radius_batch(const pico_b200_tree* t, const T* q, size_t nq, size_t stride, double radius, double e,
                  uint64_t* offsets_out, void** out, unsigned flags, pico_b200_search_stats* stats) {
   *out = nullptr;
-  if (nq > 0xfffffff0u) return fail(PICO_B200_ERR_UNSUPPORTED, "more than 2^32-16 queries in one call");
+  if (nq > 0x7fffffffu) return fail(PICO_B200_ERR_UNSUPPORTED, "more than 2^31-1 queries in one call (sort and scan counts are 32-bit)");
   // PICO_B200_DEVICE_POINTERS: queries and offsets_out are device pointers and *out receives a device
   // buffer (pico_b200_free_device); the call still synchronises once to learn the total.
   const bool on_device = flags & PICO_B200_DEVICE_POINTERS;
@@ -1611,7 +1690,7 @@ template <typename T>
 int box_batch(const pico_b200_tree* t, const T* mins, const T* maxs, size_t nb, size_t stride, uint64_t* offsets_out,
               int32_t** out, unsigned flags, pico_b200_search_stats* stats) {
   *out = nullptr;
-  if (nb > 0xfffffff0u) return fail(PICO_B200_ERR_UNSUPPORTED, "more than 2^32-16 boxes in one call");
+  if (nb > 0x7fffffffu) return fail(PICO_B200_ERR_UNSUPPORTED, "more than 2^31-1 boxes in one call (scan counts are 32-bit)");
   const bool on_device = flags & PICO_B200_DEVICE_POINTERS;  // same convention as radius_batch
   if (!on_device && nb > 0 && !stats) {
     bool served = false;
@@ -1774,7 +1853,7 @@ int leaf_scan_profile(const pico_b200_tree* t, const T* d_q, size_t nq, size_t s
                       double* descend_ms, double* scan_ms, uint64_t* scan_bytes) {
   if (!t->packed() || t->metric != PICO_B200_METRIC_L2_SQUARED)
     return fail(PICO_B200_ERR_UNSUPPORTED, "leaf-scan profile: sdim <= 3 and metric_l2_squared only");
-  if (nq == 0 || nq > 0xfffffff0u || repeats < 1) return fail(PICO_B200_ERR_INVALID_ARGUMENT, "bad nq or repeats");
+  if (nq == 0 || nq > 0x7fffffffu || repeats < 1) return fail(PICO_B200_ERR_INVALID_ARGUMENT, "bad nq or repeats");
   CallCtx c;
   PICO_TRY(c.init(t->device));
   c.timed = false;

@@ -467,3 +467,176 @@ struct VisitRadiusFill {
 };
 
 }  // namespace pico
+
+namespace pico {
+
+// ---------------------------------------------------------------- exact nn over the search image (fat.cu)
+// search_nn (search_visitor.hpp:41-65) that also notices when a second point attains the current
+// best distance. The reference keeps the FIRST point visited at the minimum distance, and "first"
+// depends on its visit order inside the collapsed subtrees, which a linear scan does not follow. A
+// query whose final best is attained twice is therefore re-run by the order-exact traversal
+// (traverse_packed); every other query has ONE point at the minimum distance, which any exact
+// search returns.
+template <typename T>
+struct VisitNnTie {
+  T best = Limits<T>::max();
+  int idx = -1;
+  bool tie = false;
+  __device__ __forceinline__ void visit(int i, T d) {
+    if (best > d) {
+      best = d;
+      idx = i;
+      tie = false;
+    } else if (best == d) {
+      tie = true;
+    }
+  }
+};
+
+// Exact nearest neighbour, metric_l2_squared, sdim <= 3, for ONE query held in registers.
+//
+//   fat        search image: `nodes` with every subtree of <= fat_limit points collapsed to a leaf
+//   far_nodes  the array far children are traversed in (`fat` again, or the real `nodes`)
+//
+// 1. first descent over `fat`, no frames (kd_tree_search.hpp:60-88 without the recursion), keeping the
+//    last NREC strict prefix minima of the far-child offsets met on the way {value, branch node};
+// 2. scan of the first (fat) leaf -> best; reach = best widened by 2^-13 of the first best, so that a
+//    far_dist that rounding left a few ulps above the exact box distance (it is a running sum with one
+//    rounding per level) can never hide a point AT the best distance: ties are always seen;
+// 3. the far children of the first path that can matter are those with offset <= reach; the topmost of
+//    them is necessarily a strict prefix minimum (everything above it is > reach >= it). If the newest
+//    record is already > reach no far child matters and the query is done. Otherwise the second walk
+//    (kd_tree_search.hpp:89-103 with an explicit stack) starts at the oldest recorded node whose value is
+//    <= reach — from the root only when the evicted record would qualify as well. On the first path
+//    node_box_distance and every offset are zero, so starting anywhere on it needs no other state.
+template <typename T, int DIM, int NREC, typename Stack>
+__device__ __forceinline__ void traverse_nn_fat(const typename NodeOf<T>::type* __restrict__ fat,
+                                                const typename NodeOf<T>::type* __restrict__ far_nodes,
+                                                const typename Vec4Of<T>::type* __restrict__ pts4, const T (&q)[DIM],
+                                                Stack& stack, VisitNnTie<T>& vis) {
+  constexpr int metric = PICO_B200_METRIC_L2_SQUARED;
+  T a, b;
+  uint32_t right, sd;
+  int lb, le;
+  uint32_t node = 0;
+  T pm_val[NREC > 0 ? NREC : 1];
+  uint32_t pm_node[NREC > 0 ? NREC : 1];
+  T pm_evicted = Limits<T>::max();
+#pragma unroll
+  for (int r = 0; r < (NREC > 0 ? NREC : 1); ++r) {
+    pm_val[r] = Limits<T>::max();
+    pm_node[r] = 0;
+  }
+  load_node(fat, node, a, b, right, sd, lb, le);
+  while (sd != PICO_B200_LEAF) {
+    T v = q[0];
+#pragma unroll
+    for (int j = 1; j < DIM; ++j)
+      if (sd == (uint32_t)j) v = q[j];
+    const bool go_left = sub_rn(sub_rn(add_rn(a, b), v), v) > T(0);
+    if (NREC > 0) {
+      const T t = sub_rn(go_left ? b : a, v);
+      const T new_off = mul_rn(t, t);
+      if (new_off < pm_val[0]) {
+        pm_evicted = pm_val[NREC > 0 ? NREC - 1 : 0];
+#pragma unroll
+        for (int r = (NREC > 0 ? NREC - 1 : 0); r > 0; --r) {
+          pm_val[r] = pm_val[r - 1];
+          pm_node[r] = pm_node[r - 1];
+        }
+        pm_val[0] = new_off;
+        pm_node[0] = node;
+      }
+    }
+    node = go_left ? node + 1 : right;
+    load_node(fat, node, a, b, right, sd, lb, le);
+  }
+  const uint32_t primed_leaf = node;
+  for (int i = lb; i < le; ++i) {
+    const typename Vec4Of<T>::type p = ldg4(pts4 + i);
+    T d = T(0);
+    d = metric_fold(metric, d, q[0], p.x, 0);
+    if (DIM > 1) d = metric_fold(metric, d, q[DIM > 1 ? 1 : 0], p.y, 1);
+    if (DIM > 2) d = metric_fold(metric, d, q[DIM > 2 ? 2 : 0], p.z, 2);
+    vis.visit(index_of(p), d);
+  }
+  const T margin = mul_rn(vis.best, sizeof(T) == 4 ? T(1.2207031e-4) : T(2.2737368e-13));
+  T reach = add_rn(vis.best, margin);
+  node = 0;
+  if (NREC > 0) {
+    if (reach < pm_val[0]) return;
+    bool found = false;
+#pragma unroll
+    for (int r = (NREC > 0 ? NREC - 1 : 0); r >= 0; --r) {
+      if (!found && pm_val[r] <= reach) {
+        found = true;
+        node = (r == NREC - 1 && pm_evicted <= reach) ? 0u : pm_node[r];
+      }
+    }
+  }
+  T off[DIM];
+#pragma unroll
+  for (int j = 0; j < DIM; ++j) off[j] = T(0);
+  T node_dist = T(0);
+  int sp = 0;
+  const typename NodeOf<T>::type* cur = fat;
+  for (;;) {
+    load_node(cur, node, a, b, right, sd, lb, le);
+    while (sd != PICO_B200_LEAF) {
+      T v = q[0], old = off[0];
+#pragma unroll
+      for (int j = 1; j < DIM; ++j) {
+        if (sd == (uint32_t)j) {
+          v = q[j];
+          old = off[j];
+        }
+      }
+      const bool go_left = sub_rn(sub_rn(add_rn(a, b), v), v) > T(0);
+      const T t = sub_rn(go_left ? b : a, v);
+      const T new_off = mul_rn(t, t);
+      const uint32_t far = go_left ? right : node + 1;
+      node = go_left ? node + 1 : right;
+      const T far_dist = add_rn(sub_rn(node_dist, old), new_off);
+      if (reach >= far_dist) {
+        T snap[DIM];
+#pragma unroll
+        for (int j = 0; j < DIM; ++j) snap[j] = (sd == (uint32_t)j) ? new_off : off[j];
+        stack.push(sp, far, far_dist, snap);
+        ++sp;
+      }
+      load_node(cur, node, a, b, right, sd, lb, le);
+    }
+    if (node == primed_leaf) le = lb;
+    if (lb < le) {
+      for (int i = lb; i < le; ++i) {
+        const typename Vec4Of<T>::type p = ldg4(pts4 + i);
+        T d = T(0);
+        d = metric_fold(metric, d, q[0], p.x, 0);
+        if (DIM > 1) d = metric_fold(metric, d, q[DIM > 1 ? 1 : 0], p.y, 1);
+        if (DIM > 2) d = metric_fold(metric, d, q[DIM > 2 ? 2 : 0], p.z, 2);
+        vis.visit(index_of(p), d);
+      }
+      reach = add_rn(vis.best, margin);
+    }
+    bool found = false;
+    while (sp > 0) {
+      --sp;
+      T d;
+      uint32_t n;
+      T snap[DIM];
+      stack.pop(sp, n, d, snap);
+      if (reach >= d) {
+        node = n;
+        node_dist = d;
+#pragma unroll
+        for (int j = 0; j < DIM; ++j) off[j] = snap[j];
+        found = true;
+        break;
+      }
+    }
+    if (!found) return;
+    cur = far_nodes;
+  }
+}
+
+}  // namespace pico

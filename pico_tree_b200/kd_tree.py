@@ -18,6 +18,9 @@ from . import _lib
 __all__ = ["Metric", "KdTree", "DArray", "load_kd_tree", "save_kd_tree"]
 
 
+_CUDA_STREAM_LEGACY = 0x1  # driver_types.h: #define cudaStreamLegacy ((cudaStream_t)0x1)
+
+
 class Metric(enum.Enum):
     """metric_t of the binding (def_kd_tree.cpp:14-17) plus the fourth euclidean metric of
     metric.hpp (metric_lninf), which the reference binding does not expose."""
@@ -298,6 +301,10 @@ class KdTree:
         if stream is None:
             import torch
             stream = torch.cuda.current_stream(self._device).cuda_stream
+        # torch reports its default stream as handle 0, which pico_b200_set_stream reads as "no caller
+        # stream" (a private non-blocking stream that is NOT ordered after pending default-stream work):
+        # name the legacy default stream explicitly (cudaStreamLegacy).
+        stream = int(stream) or _CUDA_STREAM_LEGACY
         L = _lib.lib()
         _lib.check(L.pico_b200_set_stream(C.c_void_p(stream)))
         try:

@@ -1,0 +1,130 @@
+// traverse_host.cpp — TEST ONLY: compiles the thread-per-query traversals of pico_tree_b200/csrc/traverse.cuh
+// (the product's device code) for the HOST, one "thread" at a time, so that their control flow — the
+// search-image nn traversal with its prefix-minimum restart and tie detection, and the order-exact
+// traverse_packed — can be checked against the oracle without a GPU (tests/test_traverse_host.py).
+// The CUDA intrinsics the header uses are given their IEEE meaning here; the file is compiled with
+// -ffp-contract=off like every other host translation unit that has to match the reference bit for bit.
+// Built by tests/cpp/Makefile into tests/_bin/libtraverse_host.so. Not part of the product.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+
+static inline float __fadd_rn(float a, float b) { return a + b; }
+static inline float __fsub_rn(float a, float b) { return a - b; }
+static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline double __dadd_rn(double a, double b) { return a + b; }
+static inline double __dsub_rn(double a, double b) { return a - b; }
+static inline double __dmul_rn(double a, double b) { return a * b; }
+static inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); return i; }
+static inline float __uint_as_float(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }
+static inline long long __double_as_longlong(double d) { long long i; std::memcpy(&i, &d, 8); return i; }
+static inline double __longlong_as_double(long long i) { double d; std::memcpy(&d, &i, 8); return d; }
+// loads by record type (uint4 = f32 node, float4 = f32 point ...): statistics for tests/test_traverse_host.py
+static thread_local unsigned long long g_loads16 = 0, g_loads_pts = 0;
+template <typename V>
+static inline V __ldg(const V* p) {
+  ++g_loads16;
+  return *p;
+}
+static inline float4 __ldg(const float4* p) {
+  ++g_loads_pts;
+  return *p;
+}
+
+#include "../../pico_tree_b200/csrc/traverse.cuh"
+
+namespace {
+
+template <typename T, int DIM>
+void nn_fat(const void* fat, const void* far_nodes, const void* pts4, const T* q, size_t nq, int nrec, int32_t* idx,
+            T* dist, uint8_t* tie) {
+  using namespace pico;
+  using NodeT = typename NodeOf<T>::type;
+  using V4 = typename Vec4Of<T>::type;
+  for (size_t i = 0; i < nq; ++i) {
+    T qq[DIM];
+    for (int j = 0; j < DIM; ++j) qq[j] = q[i * DIM + j];
+    VisitNnTie<T> vis;
+    LocalStack<T, DIM, kLocalStack> st;
+    if (nrec == 0)
+      traverse_nn_fat<T, DIM, 0>(static_cast<const NodeT*>(fat), static_cast<const NodeT*>(far_nodes),
+                                 static_cast<const V4*>(pts4), qq, st, vis);
+    else if (nrec == 1)
+      traverse_nn_fat<T, DIM, 1>(static_cast<const NodeT*>(fat), static_cast<const NodeT*>(far_nodes),
+                                 static_cast<const V4*>(pts4), qq, st, vis);
+    else
+      traverse_nn_fat<T, DIM, 3>(static_cast<const NodeT*>(fat), static_cast<const NodeT*>(far_nodes),
+                                 static_cast<const V4*>(pts4), qq, st, vis);
+    idx[i] = vis.idx;
+    dist[i] = vis.best;
+    tie[i] = vis.tie ? 1 : 0;
+  }
+}
+
+// order-exact search_nn / search_knn (k <= 16) through traverse_packed, PRIME as the kernels use it
+template <typename T, int DIM>
+void knn_packed(const void* nodes, const void* pts4, const T* q, size_t nq, int k, int n_points, int32_t* idx, T* dist) {
+  using namespace pico;
+  using NodeT = typename NodeOf<T>::type;
+  using V4 = typename Vec4Of<T>::type;
+  for (size_t i = 0; i < nq; ++i) {
+    T qq[DIM];
+    for (int j = 0; j < DIM; ++j) qq[j] = q[i * DIM + j];
+    LocalStack<T, DIM, kLocalStack> st;
+    if (k == 1) {
+      VisitNn<T> vis;
+      traverse_packed<T, DIM, true, kPrimeFirstLeaf>(static_cast<const NodeT*>(nodes), static_cast<const V4*>(pts4),
+                                                     nullptr, qq, 0, false, T(1), st, vis);
+      idx[i] = vis.idx;
+      dist[i] = vis.best;
+    } else {
+      VisitKnn<T, 16> vis;
+      vis.init(k);
+      traverse_packed<T, DIM, true, kPrimeBound>(static_cast<const NodeT*>(nodes), static_cast<const V4*>(pts4), nullptr,
+                                                 qq, 0, false, T(1), st, vis, n_points, k);
+      for (int j = 0; j < k; ++j) {
+        idx[i * k + j] = vis.id[16 - k + j];
+        dist[i * k + j] = vis.d[16 - k + j];
+      }
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" {
+// node loads / f32 point loads since the last call
+unsigned long long host_take_loads16() {
+  const unsigned long long v = g_loads16;
+  g_loads16 = 0;
+  return v;
+}
+unsigned long long host_take_point_loads() {
+  const unsigned long long v = g_loads_pts;
+  g_loads_pts = 0;
+  return v;
+}
+void host_nn_fat_f32(const void* fat, const void* far_nodes, const void* pts4, const float* q, size_t nq, int sdim,
+                     int nrec, int32_t* idx, float* dist, uint8_t* tie) {
+  if (sdim == 2)
+    nn_fat<float, 2>(fat, far_nodes, pts4, q, nq, nrec, idx, dist, tie);
+  else
+    nn_fat<float, 3>(fat, far_nodes, pts4, q, nq, nrec, idx, dist, tie);
+}
+void host_nn_fat_f64(const void* fat, const void* far_nodes, const void* pts4, const double* q, size_t nq, int sdim,
+                     int nrec, int32_t* idx, double* dist, uint8_t* tie) {
+  if (sdim == 2)
+    nn_fat<double, 2>(fat, far_nodes, pts4, q, nq, nrec, idx, dist, tie);
+  else
+    nn_fat<double, 3>(fat, far_nodes, pts4, q, nq, nrec, idx, dist, tie);
+}
+void host_knn_packed_f32(const void* nodes, const void* pts4, const float* q, size_t nq, int sdim, int k, int n_points,
+                         int32_t* idx, float* dist) {
+  if (sdim == 2)
+    knn_packed<float, 2>(nodes, pts4, q, nq, k, n_points, idx, dist);
+  else
+    knn_packed<float, 3>(nodes, pts4, q, nq, k, n_points, idx, dist);
+}
+}

@@ -448,6 +448,18 @@ def test_python_device_arrays(pt):
         t.search_knn(qd.double(), 1)
     with pytest.raises(ValueError):
         t.search_knn(qd[:, :2], 1)
+    # queries PRODUCED on torch's default stream (handle 0) right before the call: the search has to be ordered
+    # after the producer (the library must not fall back to a private stream for handle 0)
+    big = torch.from_numpy(D.uniform(4_000_000, 3, seed=3)).cuda()
+    torch.cuda.synchronize()
+    for _ in range(3):
+        qd2 = torch.zeros_like(big)
+        for _ in range(8):
+            qd2 = qd2 * 0.5 + big * 0.5  # a chain of async producer kernels; ends close to `big`
+        got2 = t.search_knn(qd2, 1)
+        torch.cuda.synchronize()
+        want2 = t.search_knn(qd2.cpu().numpy(), 1)
+        assert np.array_equal(got2[..., 0].cpu().numpy(), want2["index"])
 
 
 def test_device_resident_ragged_results(pt):
@@ -695,3 +707,27 @@ def test_nccl_tree_broadcast_two_gpus(pt):
     L.pico_b200_tree_destroy(handles[1])
     for c in comms:
         nccl.ncclCommDestroy(C.c_void_p(c))
+
+
+@pytest.mark.parametrize("dtype,sdim", [(np.float32, 3), (np.float32, 2), (np.float64, 3)])
+def test_search_image_nn_with_ties(pt, oracle, dtype, sdim):
+    """k = 1 goes through the search image (fat.cu, nn_fat_kernel). On an integer lattice most queries have
+    several points at the minimum distance: those are detected and re-run by the order-exact kernel, so the
+    INDEX is still the reference's first-visited one. Duplicated points included."""
+    rng = np.random.default_rng(11)
+    pts = rng.integers(0, 24, size=(60_000, sdim)).astype(dtype)
+    q = (rng.integers(0, 24, size=(40_000, sdim)) + rng.choice([0.0, 0.5], size=(40_000, sdim))).astype(dtype)
+    t = pt.KdTree(pts, pt.Metric.L2Squared, 10)
+    ora = oracle.OracleTree(pts, 10)
+    want = ora.search_knn(q, 1)
+    for kw in ({}, {"reorder": False}):
+        got = t.search_knn(q, 1, **kw)
+        assert np.array_equal(got["distance"], want["distance"])
+        assert np.array_equal(got["index"], want["index"])
+    # and a cloud without ties, far children of every depth: uniform points, queries partly outside the box
+    pts = rng.random((200_000, sdim)).astype(dtype)
+    q = (rng.random((100_000, sdim)) * 1.5 - 0.25).astype(dtype)
+    t = pt.KdTree(pts, pt.Metric.L2Squared, 10)
+    want = oracle.OracleTree(pts, 10).search_knn(q, 1)
+    got = t.search_knn(q, 1)
+    assert np.array_equal(got["distance"], want["distance"]) and np.array_equal(got["index"], want["index"])
