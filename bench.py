@@ -46,6 +46,10 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--warp-per-query", action="store_true")
     ap.add_argument("--no-reorder", action="store_true")
+    ap.add_argument("--no-configs", action="store_true",
+                    help="skip BASELINE.json's other configurations (bench_configs.py; N=1 only, adds ~2 minutes)")
+    ap.add_argument("--configs", default=None,
+                    help="comma list out of cfg1,cfg3_knn16,cfg3_radius,box,cfg4_exact,cfg4_approx (default: all)")
     return ap.parse_args()
 
 
@@ -389,7 +393,8 @@ def run_ours(args, n_tree, n_query):
         except (OSError, ValueError):
             pass
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": traffic, "kernel": "knn_thread_kernel<float,3,1,FAST>" if not args.warp_per_query
+                    "traffic": traffic, "kernel": ("nn_fat_kernel<float,3,3>" if k == 1 else
+                                                   "knn_thread_kernel<float,3,K,FAST>") if not args.warp_per_query
                     else "knn_warp_kernel<float,PACKED,REG>", "kernel_ms": kernel_ms,
                     "algorithmic_bytes_per_query": bytes_per_query,
                     "per_query_branches_leaves_points": counters, "peak_source": peak_kind}
@@ -411,6 +416,14 @@ def run_ours(args, n_tree, n_query):
         else:
             roofline = {"bound": "hbm", "leaf_scan": leaf_scan}
 
+    # ---- BASELINE.json's other configurations (N=1 only): each with value, e2e, parity vs the reference, roofline
+    configs = None
+    if world == 1 and not args.no_configs and not args.no_cpu_baseline and k == 1 and not args.warp_per_query:
+        import bench_configs
+        from oracle import oracle as O
+        ctx = {"torch": torch, "lib": _lib, "oracle": O, "pt": pt, "peak": peak, "peak_kind": peak_kind}
+        configs = bench_configs.run_all(ctx, tree, tree_pts, q_host, args.configs.split(",") if args.configs else None)
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -422,10 +435,12 @@ def run_ours(args, n_tree, n_query):
                 "d2h_bytes_per_step": int(n_query * k * 8), "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
                 "pcie_floor_ms": floor_ms, "host_binding": binding,
                 "pcie_floor_note": "one H2D of all queries + one D2H of all results issued together, best of 10"},
-        "gpu_launches": int(args.steps * (1 + (0 if args.no_reorder else 1))),
-        "gpu_launches_note": "own kernels per step: morton_kernel + knn traversal kernel (CUB radix-sort passes "
-                             "of the Z-order step not counted)",
-        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        "gpu_launches": int(args.steps * ((2 if k == 1 and not args.warp_per_query else 1) +
+                                          (0 if args.no_reorder else 1))),
+        "gpu_launches_note": "own kernels per step: morton_kernel + the traversal (k = 1: nn_fat_kernel over the search "
+                             "image + the order-exact kernel on its tie list); CUB radix-sort passes of the Z-order "
+                             "step not counted",
+        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "configs": configs,
     }
     print(json.dumps(line))
     if world > 1:

@@ -69,6 +69,10 @@ def lib():
                                                            C.c_double, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
             getattr(L, f"po_box_batch_{s}").argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t,
                                                         C.c_void_p, C.POINTER(C.c_void_p)]
+            getattr(L, f"po_radius_counters_{s}").argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, sc,
+                                                              C.c_double, C.c_void_p]
+            getattr(L, f"po_box_counters_{s}").argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t,
+                                                           C.c_void_p]
             getattr(L, f"po_splitter_once_{s}").restype = C.c_size_t
             getattr(L, f"po_splitter_once_{s}").argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p,
                                                             C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p,
@@ -200,6 +204,19 @@ class OracleTree(_Base):
                                    C.byref(p))
         return offs, _take(p, int(offs[-1]), self.nb_dtype, lib().po_free_buffer)
 
+    def radius_counters(self, q, radius, e=0.0):
+        """{branch nodes, leaves, points tested, hits} summed over the batch (SURVEY.md §8d byte model)."""
+        q = self._q(q)
+        c = np.zeros(4, dtype=np.uint64)
+        self._f("po_radius_counters")(self._h, _ptr(q), len(q), self.sdim, float(radius), float(e), _ptr(c))
+        return c
+
+    def box_counters(self, mins, maxs):
+        mins, maxs = self._q(mins), self._q(maxs)
+        c = np.zeros(4, dtype=np.uint64)
+        self._f("po_box_counters")(self._h, _ptr(mins), _ptr(maxs), len(mins), self.sdim, _ptr(c))
+        return c
+
     def search_box(self, mins, maxs):
         mins, maxs = self._q(mins), self._q(maxs)
         offs = np.zeros(len(mins) + 1, dtype=np.uint64)
@@ -244,6 +261,8 @@ def ref_lib():
         L.ref_radius.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_double, C.c_double, C.c_int, C.c_void_p,
                                  C.POINTER(C.c_void_p)]
         L.ref_box.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.ref_radius_mt.argtypes = L.ref_radius.argtypes + [C.c_int]
+        L.ref_box_mt.argtypes = L.ref_box.argtypes + [C.c_int]
         L.ref_free_buffer.argtypes = [C.c_void_p]
         _ref = L
     return _ref
@@ -343,18 +362,19 @@ class RefTree(_Base):
         ref_lib().ref_knn(self._h, _ptr(q), len(q), k, float(e), _ptr(out), int(threads))
         return out
 
-    def search_radius(self, q, radius, e=0.0, sort=False):
+    def search_radius(self, q, radius, e=0.0, sort=False, threads=1):
         q = self._q(q)
         offs = np.zeros(len(q) + 1, dtype=np.uint64)
         p = C.c_void_p()
-        ref_lib().ref_radius(self._h, _ptr(q), len(q), float(radius), float(e), int(sort), _ptr(offs), C.byref(p))
+        ref_lib().ref_radius_mt(self._h, _ptr(q), len(q), float(radius), float(e), int(sort), _ptr(offs), C.byref(p),
+                                int(threads))
         return offs, _take(p, int(offs[-1]), self.nb_dtype, ref_lib().ref_free_buffer)
 
-    def search_box(self, mins, maxs):
+    def search_box(self, mins, maxs, threads=1):
         mins, maxs = self._q(mins), self._q(maxs)
         offs = np.zeros(len(mins) + 1, dtype=np.uint64)
         p = C.c_void_p()
-        ref_lib().ref_box(self._h, _ptr(mins), _ptr(maxs), len(mins), _ptr(offs), C.byref(p))
+        ref_lib().ref_box_mt(self._h, _ptr(mins), _ptr(maxs), len(mins), _ptr(offs), C.byref(p), int(threads))
         return offs, _take(p, int(offs[-1]), np.int32, ref_lib().ref_free_buffer)
 
 

@@ -6,6 +6,7 @@
 // this file only *uses* the public API (kd_tree.hpp:72-88,125-318,336-370).
 //
 // Flags (oracle/Makefile): -std=c++17 -O3 -DNDEBUG -ffp-contract=off -fopenmp.
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
 #include <memory>
@@ -28,9 +29,10 @@ struct tree_base {
   virtual void knn(void const* q, size_t nq, size_t k, double e, void* out, int threads) const = 0;
   virtual void radius(
       void const* q, size_t nq, double radius, double e, int sort, uint64_t* offsets,
-      void** out) const = 0;
+      void** out, int threads) const = 0;
   virtual void box(
-      void const* mins, void const* maxs, size_t nb, uint64_t* offsets, int32_t** out) const = 0;
+      void const* mins, void const* maxs, size_t nb, uint64_t* offsets, int32_t** out,
+      int threads) const = 0;
 };
 
 template <typename T, size_t Dim, typename Metric>
@@ -107,41 +109,62 @@ struct tree_impl final : tree_base {
     }
   }
 
+  // The reference's binding runs these loops under OpenMP (dynamic,128) into per-query vectors
+  // (_pyco_tree/kd_tree.hpp:158-167,193-199,260-267); here each thread keeps the results of a block of
+  // queries and the blocks are concatenated in query order afterwards.
+  template <typename Item, typename One>
+  static void ragged(size_t n, int threads, uint64_t* offsets, void** outv, One&& one) {
+    constexpr size_t kBlock = 1024;
+    size_t const nblocks = (n + kBlock - 1) / kBlock;
+    std::vector<std::vector<Item>> parts(nblocks);
+    std::vector<uint32_t> counts(n);
+    std::ptrdiff_t const cnt = static_cast<std::ptrdiff_t>(nblocks);
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads > 1 ? threads : 1)
+    for (std::ptrdiff_t b = 0; b < cnt; ++b) {
+      std::vector<Item> tmp;
+      auto& part = parts[size_t(b)];
+      size_t const end = std::min(n, (size_t(b) + 1) * kBlock);
+      for (size_t i = size_t(b) * kBlock; i < end; ++i) {
+        one(i, tmp);
+        counts[i] = static_cast<uint32_t>(tmp.size());
+        part.insert(part.end(), tmp.begin(), tmp.end());
+      }
+    }
+    offsets[0] = 0;
+    for (size_t i = 0; i < n; ++i) offsets[i + 1] = offsets[i] + counts[i];
+    auto* buf = static_cast<Item*>(std::malloc(sizeof(Item) * (offsets[n] + 1)));
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads > 1 ? threads : 1)
+    for (std::ptrdiff_t b = 0; b < cnt; ++b) {
+      auto const& part = parts[size_t(b)];
+      if (!part.empty())
+        std::memcpy(buf + offsets[size_t(b) * kBlock], part.data(), sizeof(Item) * part.size());
+    }
+    *outv = buf;
+  }
+
   void radius(
       void const* qv, size_t nq, double radius, double e, int sort, uint64_t* offsets,
-      void** outv) const override {
+      void** outv, int threads) const override {
     T const* q = static_cast<T const*>(qv);
-    std::vector<neighbor_type> all, one;
-    offsets[0] = 0;
-    for (size_t i = 0; i < nq; ++i) {
+    ragged<neighbor_type>(nq, threads, offsets, outv, [&](size_t i, std::vector<neighbor_type>& one) {
       point_type p(q + i * sdim_, sdim_);
       if (e > 0) {
         tree_.search_radius(p, T(radius), T(e), one, sort != 0);
       } else {
         tree_.search_radius(p, T(radius), one, sort != 0);
       }
-      all.insert(all.end(), one.begin(), one.end());
-      offsets[i + 1] = all.size();
-    }
-    auto* buf = static_cast<neighbor_type*>(std::malloc(sizeof(neighbor_type) * (all.size() + 1)));
-    std::memcpy(buf, all.data(), sizeof(neighbor_type) * all.size());
-    *outv = buf;
+    });
   }
 
-  void box(void const* mins, void const* maxs, size_t nb, uint64_t* offsets, int32_t** outv)
+  void box(void const* mins, void const* maxs, size_t nb, uint64_t* offsets, int32_t** outv, int threads)
       const override {
     T const* mn = static_cast<T const*>(mins);
     T const* mx = static_cast<T const*>(maxs);
-    std::vector<int> all, one;
-    offsets[0] = 0;
-    for (size_t i = 0; i < nb; ++i) {
+    void* out = nullptr;
+    ragged<int>(nb, threads, offsets, &out, [&](size_t i, std::vector<int>& one) {
       tree_.search_box(point_type(mn + i * sdim_, sdim_), point_type(mx + i * sdim_, sdim_), one);
-      all.insert(all.end(), one.begin(), one.end());
-      offsets[i + 1] = all.size();
-    }
-    auto* buf = static_cast<int32_t*>(std::malloc(sizeof(int32_t) * (all.size() + 1)));
-    std::memcpy(buf, all.data(), sizeof(int32_t) * all.size());
-    *outv = buf;
+    });
+    *outv = static_cast<int32_t*>(out);
   }
 
   size_t sdim_;
@@ -225,13 +248,26 @@ void ref_knn(void const* h, void const* q, size_t nq, size_t k, double e, void* 
 void ref_radius(
     void const* h, void const* q, size_t nq, double radius, double e, int sort, uint64_t* offsets,
     void** out) {
-  static_cast<tree_base const*>(h)->radius(q, nq, radius, e, sort, offsets, out);
+  static_cast<tree_base const*>(h)->radius(q, nq, radius, e, sort, offsets, out, 1);
 }
 
 void ref_box(
     void const* h, void const* mins, void const* maxs, size_t nb, uint64_t* offsets,
     int32_t** out) {
-  static_cast<tree_base const*>(h)->box(mins, maxs, nb, offsets, out);
+  static_cast<tree_base const*>(h)->box(mins, maxs, nb, offsets, out, 1);
+}
+
+// the same loops on `threads` host threads (results still in query order)
+void ref_radius_mt(
+    void const* h, void const* q, size_t nq, double radius, double e, int sort, uint64_t* offsets,
+    void** out, int threads) {
+  static_cast<tree_base const*>(h)->radius(q, nq, radius, e, sort, offsets, out, threads);
+}
+
+void ref_box_mt(
+    void const* h, void const* mins, void const* maxs, size_t nb, uint64_t* offsets, int32_t** out,
+    int threads) {
+  static_cast<tree_base const*>(h)->box(mins, maxs, nb, offsets, out, threads);
 }
 
 void ref_free_buffer(void* p) { std::free(p); }
