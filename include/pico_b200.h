@@ -238,6 +238,45 @@ int pico_b200_tree_load(const void* pts, size_t n, size_t sdim, size_t stride, i
                         uint64_t* consumed);
 
 /*
+ * ---- kd_forest ---------------------------------------------------------------
+ * Replaces pico_tree::kd_forest (examples/pico_understory/pico_understory/kd_forest.hpp:15-138):
+ * `forest_size` kd-trees (sliding_midpoint_max_side, max_leaf_size, bounds from the space) over
+ * Householder-reflected copies of the point set (internal/rkd_tree_hh_data.hpp:51-90,
+ * internal/rkd_tree_builder.hpp:26-41), searched best-bin-first with at most `max_leaves_visited`
+ * leaves per tree and one neighbour list shared by all trees
+ * (internal/kd_tree_priority_search.hpp:24-142, kd_forest.hpp:91-120). metric_l2_squared only, like
+ * the reference's priority search. Distances are measured in each tree's reflected space, as in the
+ * reference.
+ *   rotations  forest_size unit vectors of sdim scalars (row-major), or NULL: drawn at random like
+ *              rkd_tree_hh_data::random_rotation (std::random_device-seeded, not reproducible)
+ */
+typedef struct pico_b200_forest pico_b200_forest;
+
+typedef struct pico_b200_forest_info {
+  uint64_t n_points, sdim, n_trees, max_leaf_size, height;  /* height: the tallest tree */
+  int32_t scalar, device;
+  double build_ms;          /* device time of reflections + builds (CUDA events) */
+  uint64_t device_bytes;
+} pico_b200_forest_info;
+
+int pico_b200_forest_create(const void* pts, size_t n, size_t sdim, size_t stride_elems, int scalar,
+                            size_t max_leaf_size, const void* rotations, size_t forest_size, int device,
+                            pico_b200_forest** out);
+void pico_b200_forest_destroy(pico_b200_forest* forest);
+int pico_b200_forest_info_get(const pico_b200_forest* forest, pico_b200_forest_info* info);
+/* the reflection vectors in use: forest_size * sdim scalars (kd_forest keeps them in rkd_tree_hh_data::rotation) */
+int pico_b200_forest_rotations(const pico_b200_forest* forest, void* rotations_out);
+/* tree `i` of the forest, borrowed (valid until the forest is destroyed): export / info of the per-tree structure */
+int pico_b200_forest_tree(const pico_b200_forest* forest, size_t i, const pico_b200_tree** tree);
+/*
+ * kd_forest::search_nn (k = 1) / search_nearest with a search_knn visitor, one call per batch
+ * (kd_forest.hpp:76-120). neighbors_out: nq * k records {int32 index, scalar distance}, ascending;
+ * slots never filled keep index -1. flags: PICO_B200_DEVICE_POINTERS.
+ */
+int pico_b200_forest_knn(const pico_b200_forest* forest, const void* queries, size_t nq, size_t stride_elems, size_t k,
+                         size_t max_leaves_visited, void* neighbors_out, unsigned flags, pico_b200_search_stats* stats);
+
+/*
  * Caller-provided CUDA stream (cudaStream_t) for the calling host thread; NULL restores the
  * default (a private stream per call). With a caller stream the searches are ordered on that
  * stream, so they compose with the caller's own kernels, events and CUDA graphs. NULL never means

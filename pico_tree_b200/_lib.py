@@ -27,6 +27,8 @@ EXPORTS = [
     "pico_b200_free_device",
     "pico_b200_tree_save_size", "pico_b200_tree_save", "pico_b200_tree_load", "pico_b200_set_stream",
     "pico_b200_profile_begin", "pico_b200_profile_end", "pico_b200_profile_leaf_scan",
+    "pico_b200_forest_create", "pico_b200_forest_destroy", "pico_b200_forest_info_get", "pico_b200_forest_rotations",
+    "pico_b200_forest_tree", "pico_b200_forest_knn",
 ]
 
 
@@ -39,6 +41,12 @@ class TreeInfo(C.Structure):
 class SearchStats(C.Structure):
     _fields_ = [("h2d_ms", C.c_double), ("reorder_ms", C.c_double), ("kernel_ms", C.c_double),
                 ("d2h_ms", C.c_double), ("kernel_launches", C.c_uint64)]
+
+
+class ForestInfo(C.Structure):
+    _fields_ = [("n_points", C.c_uint64), ("sdim", C.c_uint64), ("n_trees", C.c_uint64), ("max_leaf_size", C.c_uint64),
+                ("height", C.c_uint64), ("scalar", C.c_int32), ("device", C.c_int32), ("build_ms", C.c_double),
+                ("device_bytes", C.c_uint64)]
 
 
 class PicoB200Error(RuntimeError):
@@ -93,6 +101,13 @@ def lib():
     L.pico_b200_profile_end.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
     L.pico_b200_profile_leaf_scan.argtypes = [vp, vp, sz, sz, vp, i32, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                               C.POINTER(C.c_uint64)]
+    L.pico_b200_forest_create.argtypes = [vp, sz, sz, sz, i32, sz, vp, sz, i32, C.POINTER(vp)]
+    L.pico_b200_forest_destroy.argtypes = [vp]
+    L.pico_b200_forest_destroy.restype = None
+    L.pico_b200_forest_info_get.argtypes = [vp, C.POINTER(ForestInfo)]
+    L.pico_b200_forest_rotations.argtypes = [vp, vp]
+    L.pico_b200_forest_tree.argtypes = [vp, sz, C.POINTER(vp)]
+    L.pico_b200_forest_knn.argtypes = [vp, vp, sz, sz, sz, sz, vp, u32, C.POINTER(SearchStats)]
     _lib = L
     return L
 

@@ -209,7 +209,7 @@ int pico_b200_tree_info_get(const pico_b200_tree* t, pico_b200_tree_info* info) 
 
 int pico_b200_tree_export_outer_bounds(const pico_b200_tree* t, void* outer_out) {
   if (!t || !outer_out) return fail(PICO_B200_ERR_INVALID_ARGUMENT, "null argument");
-  if (!t->topological()) return fail(PICO_B200_ERR_INVALID_ARGUMENT, "only trees of a topological metric keep outer bounds");
+  if (!t->outer_bytes()) return fail(PICO_B200_ERR_INVALID_ARGUMENT, "only trees of a topological metric (and the trees of a kd_forest) keep outer bounds");
   PICO_CUDA(cudaSetDevice(t->device));
   PICO_CUDA(cudaMemcpy(outer_out, t->d_outer, t->outer_bytes(), cudaMemcpyDeviceToHost));
   return 0;
@@ -326,7 +326,7 @@ int pico_b200_tree_serialize(const pico_b200_tree* t, void* dst, int dst_is_devi
   p += align16(t->n * 4);
   PICO_CUDA(cudaMemcpy(p, t->d_pts, t->pts_bytes(), kd));
   p += align16(t->pts_bytes());
-  if (t->topological()) PICO_CUDA(cudaMemcpy(p, t->d_outer, t->outer_bytes(), kd));
+  if (t->outer_bytes()) PICO_CUDA(cudaMemcpy(p, t->d_outer, t->outer_bytes(), kd));
   p += align16(t->outer_bytes());
   if (!t->packed()) PICO_CUDA(cudaMemcpy(p, t->d_spans, t->spans_bytes(), kd));
   return 0;

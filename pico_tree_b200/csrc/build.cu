@@ -974,14 +974,15 @@ int alloc(DevBuf& b, size_t bytes, cudaStream_t st) {
   return 0;
 }
 
-// Staging: host rows (any stride) -> packed device rows.
+// Staging: rows (any stride; host memory, or device memory of this GPU — the kd_forest builds its trees over
+// reflected copies that never leave the device) -> packed device rows.
 template <typename T>
 int stage_points(const T* h_pts, size_t n, size_t sdim, size_t stride, T* d_raw, cudaStream_t st) {
   if (stride == sdim)
-    PICO_CUDA(cudaMemcpyAsync(d_raw, h_pts, n * sdim * sizeof(T), cudaMemcpyHostToDevice, st));
+    PICO_CUDA(cudaMemcpyAsync(d_raw, h_pts, n * sdim * sizeof(T), cudaMemcpyDefault, st));
   else
     PICO_CUDA(cudaMemcpy2DAsync(d_raw, sdim * sizeof(T), h_pts, stride * sizeof(T), sdim * sizeof(T), n,
-                                cudaMemcpyHostToDevice, st));
+                                cudaMemcpyDefault, st));
   return 0;
 }
 
@@ -1213,7 +1214,7 @@ int build_tree(pico_b200_tree* t, const T* h_pts, size_t stride, int rule, int s
     number_level<T><<<(le - lb + 127) / 128, 128, 0, st>>>(s.nodes, lb, le);
   }
   PICO_CUDA(cudaMalloc(&t->d_nodes, (size_t)n_nodes * t->node_size()));
-  if (t->topological()) PICO_CUDA(cudaMalloc(&t->d_outer, t->outer_bytes()));
+  if (t->outer_bytes()) PICO_CUDA(cudaMalloc(&t->d_outer, t->outer_bytes()));
   if (!t->packed()) PICO_CUDA(cudaMalloc(reinterpret_cast<void**>(&t->d_spans), t->spans_bytes()));
   emit_nodes<T><<<(n_nodes + 255) / 256, 256, 0, st>>>(s.nodes, n_nodes,
                                                         static_cast<typename NodeOf<T>::type*>(t->d_nodes),

@@ -5,10 +5,10 @@
 // kd_forest::search_nearest drives it, one tree after the other with a shared visitor
 // (examples/pico_understory/pico_understory/kd_forest.hpp:91-120). SURVEY.md §8 f4.
 //
-// STATUS: the traversal core only. It is written `__host__ __device__` so that the very same source is
-// checked on the CPU against the reference fixtures (tests/cpp/forest_host.cpp -> tests/test_forest_core.py);
-// the kernel, the forest handle and the C-ABI around it are not built yet, and nothing in
-// libpico_b200.so includes this header so far.
+// The arithmetic of the search (reflection, branch step, queue order) is written `__host__ __device__`: the very
+// same source is checked on the CPU against the reference fixtures (tests/cpp/forest_host.cpp ->
+// tests/test_forest_core.py, scalar driver `priority_search_tree` below) and runs inside the warp-per-query
+// kernel of forest.cu (handle + C-ABI pico_b200_forest_*).
 //
 // Reference recursion -> iteration. One "descent" of the reference (:66-125) walks from a queued node to a
 // leaf through the nearer children, scans the leaf, and while the recursion unwinds queues every farther
@@ -158,6 +158,32 @@ PICO_FOREST_HD void load(const pico_b200_node_f64* nodes, uint32_t i, T& a, T& b
   sd = nd.split_dim;
 }
 
+// One branch of a descent (kd_tree_priority_search.hpp:88-119): the nearer child is entered, the farther one is
+// recorded with the box distance  parent_dist - old_offset + new_offset  (one rounding each, left to right). The
+// nearer child inherits parent_dist (:114). Shared by the scalar core below and the warp kernel (forest.cu).
+//   a = left_max, b = right_min, v = query coordinate on the split dimension
+template <typename T>
+PICO_FOREST_HD void branch_step(T a, T b, T left_min, T right_max, T v, T parent_dist, uint32_t node, uint32_t right,
+                                uint32_t& first, uint32_t& second, T& second_dist) {
+  T old_offset, new_offset;
+  if (f_sub(f_sub(f_add(a, b), v), v) > T(0)) {  // :92-101
+    first = node + 1;
+    second = right;
+    const T t0 = f_sub(left_min, v);
+    old_offset = (v > left_min) ? T(0) : f_mul(t0, t0);
+    const T t1 = f_sub(b, v);
+    new_offset = f_mul(t1, t1);
+  } else {  // :102-111
+    first = right;
+    second = node + 1;
+    const T t0 = f_sub(right_max, v);
+    old_offset = (v < right_max) ? T(0) : f_mul(t0, t0);
+    const T t1 = f_sub(a, v);
+    new_offset = f_mul(t1, t1);
+  }
+  second_dist = f_add(f_sub(parent_dist, old_offset), new_offset);  // :119
+}
+
 // priority_search_nearest_euclidean::operator() (:47-63) for one tree, metric_l2_squared.
 //   q          the query already reflected into this tree's space (kd_forest.hpp:103)
 //   vis        visitor with max() and visit(index, distance), shared by all trees of the forest
@@ -180,27 +206,12 @@ PICO_FOREST_HD uint32_t priority_search_tree(const TreeView<T>& tree, const T* q
     int32_t lb, le;
     load<T>(tree.nodes, node, a, b, right, sd, lb, le);
     while (sd != PICO_B200_LEAF) {
-      const T v = q[sd];
-      const T left_min = tree.outer[2 * (size_t)node], right_max = tree.outer[2 * (size_t)node + 1];
-      T old_offset, new_offset;
       uint32_t first, second;
-      if (f_sub(f_sub(f_add(a, b), v), v) > T(0)) {  // :92-101
-        first = node + 1;
-        second = right;
-        const T t0 = f_sub(left_min, v);
-        old_offset = (v > left_min) ? T(0) : f_mul(t0, t0);
-        const T t1 = f_sub(b, v);
-        new_offset = f_mul(t1, t1);
-      } else {  // :102-111
-        first = right;
-        second = node + 1;
-        const T t0 = f_sub(right_max, v);
-        old_offset = (v < right_max) ? T(0) : f_mul(t0, t0);
-        const T t1 = f_sub(a, v);
-        new_offset = f_mul(t1, t1);
-      }
+      T dist;
+      branch_step<T>(a, b, tree.outer[2 * (size_t)node], tree.outer[2 * (size_t)node + 1], q[sd], top.dist, node, right,
+                     first, second, dist);
       path[n_path].node = second;
-      path[n_path].dist = f_add(f_sub(top.dist, old_offset), new_offset);  // :119
+      path[n_path].dist = dist;
       ++n_path;
       node = first;
       load<T>(tree.nodes, node, a, b, right, sd, lb, le);
