@@ -84,7 +84,7 @@ struct Limits<double> {
 constexpr int kMaxPackedDim = 3;   // sdim <= 3 uses the Vec4 layout
 constexpr int kLocalStack = 64;    // traversal stack kept in per-thread local memory
 constexpr int kSmBlocks = 148;     // B200 SM count (grid sizing; queried at runtime too)
-constexpr int kFatLeafPoints = 32; // subtrees of at most this many points are one leaf of the search image (fat.cu)
+constexpr int kFatLeafPoints = 0;  // subtrees of at most this many points are one leaf of the search image (fat.cu); 0 = none
 
 }  // namespace pico
 

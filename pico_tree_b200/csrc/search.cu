@@ -142,10 +142,14 @@ __global__ void __launch_bounds__(kThreadsPerBlock) knn_thread_kernel(KnnArgs<T>
   }
 }
 
-// Exact nn over the search image (fat.cu, traverse_nn_fat): metric_l2_squared, k = 1, trees no deeper than the
-// local stack. Queries with a tie at the best distance are listed for the order-exact kernel above.
-template <typename T, int DIM, int NREC>
-__global__ void __launch_bounds__(kThreadsPerBlock) nn_fat_kernel(KnnArgs<T> a) {
+// Exact nn (traverse_nn): metric_l2_squared, k = 1, trees no deeper than the local stack. FAT: the first
+// descent and the second walk run over the search image (fat.cu); queries with a tie at the best distance are
+// listed for the order-exact kernel above.
+template <typename T, int DIM, int NREC, bool FAT>
+__global__ void __launch_bounds__(kThreadsPerBlock, 2048 / kThreadsPerBlock) nn_kernel(KnnArgs<T> a) {
+  __shared__ uint32_t s_tag[kSharedSlots][kThreadsPerBlock];
+  __shared__ T s_x[kSharedSlots][kThreadsPerBlock];
+  __shared__ T s_y[kSharedSlots][kThreadsPerBlock];
   const size_t total = (size_t)gridDim.x * blockDim.x;
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   for (size_t slot = tid; slot < a.nq; slot += total) {
@@ -155,12 +159,15 @@ __global__ void __launch_bounds__(kThreadsPerBlock) nn_fat_kernel(KnnArgs<T> a) 
 #pragma unroll
     for (int j = 0; j < DIM; ++j) q[j] = qp[j];
     VisitNnTie<T> vis;
-    LocalStack<T, DIM, kLocalStack> st;
-    traverse_nn_fat<T, DIM, NREC>(a.fat, a.far_nodes, a.pts4, q, st, vis);
+    SlotStack<T, kThreadsPerBlock> st;
+    st.tag = s_tag;
+    st.x = s_x;
+    st.y = s_y;
+    traverse_nn<T, DIM, NREC, FAT>(a.fat, a.far_nodes, a.pts4, q, st, vis);
     Neighbor<T>* out = a.out + qi;
     out->index = vis.idx;
     out->distance = vis.best;
-    if (vis.tie) a.tie_list[atomicAdd(a.tie_count, 1u)] = qi;
+    if (FAT && vis.tie) a.tie_list[atomicAdd(a.tie_count, 1u)] = qi;
   }
 }
 
@@ -888,13 +895,14 @@ void launch_knn_thread(const KnnArgs<T>& a, bool fast, bool deep, unsigned block
   }
 }
 
-// PICO_B200_NN_FAT (tuning hook): 0 = order-exact kernel only; bit 0 = search image on; bit 1 = far children
-// are walked in the search image too (default: in the real tree); bit 2 = no prefix-minimum restart records
-int nn_fat_mode() {
+// PICO_B200_NN (tuning hook): 0 = round-1 order-exact kernel (local-memory stack); bit 0 = nn_kernel (shared slot
+// stack); bit 1 = far children are walked in the search image too (default: in the real tree); bit 2 = no
+// prefix-minimum restart records; bit 3 = ignore the search image even if the tree has one
+int nn_mode() {
   static const int v = [] {
-    const char* e = getenv("PICO_B200_NN_FAT");
+    const char* e = getenv("PICO_B200_NN");
     const int x = e ? atoi(e) : -1;
-    return (x >= 0 && x <= 7) ? x : 1;
+    return (x >= 0 && x <= 15) ? x : 1;
   }();
   return v;
 }
@@ -932,38 +940,52 @@ int knn_enqueue(CallCtx& c, const pico_b200_tree* t, const T* q, size_t nq, size
     unsigned blocks;
     PICO_TRY(thread_geometry(c, t, a, (int)t->sdim, &deep, &blocks));
     const bool fast = t->metric == PICO_B200_METRIC_L2_SQUARED && !(e > 0);
-    const int fat_mode = nn_fat_mode();
-    if (fast && !deep && k == 1 && t->d_fat_nodes && fat_mode && t->sdim >= 2) {
-      // exact nn over the search image; ties at the best distance go through the order-exact kernel after
-      uint32_t* tie = nullptr;
-      PICO_TRY(c.alloc(reinterpret_cast<void**>(&tie), (nq + 1) * sizeof(uint32_t)));
-      PICO_CUDA(cudaMemsetAsync(tie, 0, sizeof(uint32_t), c.st));
-      a.fat = static_cast<const typename NodeOf<T>::type*>(t->d_fat_nodes);
-      a.far_nodes = (fat_mode & 2) ? a.fat : a.nodes;
-      a.tie_count = tie;
-      a.tie_list = tie + 1;
-      const bool rec = !(fat_mode & 4);
-      if (t->sdim == 2) {
-        if (rec)
-          nn_fat_kernel<T, 2, 3><<<blocks, kThreadsPerBlock, 0, c.st>>>(a);
-        else
-          nn_fat_kernel<T, 2, 0><<<blocks, kThreadsPerBlock, 0, c.st>>>(a);
-      } else {
-        if (rec)
-          nn_fat_kernel<T, 3, 3><<<blocks, kThreadsPerBlock, 0, c.st>>>(a);
-        else
-          nn_fat_kernel<T, 3, 0><<<blocks, kThreadsPerBlock, 0, c.st>>>(a);
+    const int mode = nn_mode();
+    if (fast && !deep && k == 1 && mode && t->sdim >= 2 && t->n_nodes < ((size_t)1 << 30)) {
+      // exact nn with the shared-memory slot stack; with a search image (fat.cu) ties at the best distance go
+      // through the order-exact kernel afterwards
+      const bool use_fat = t->d_fat_nodes != nullptr && !(mode & 8);
+      a.fat = use_fat ? static_cast<const typename NodeOf<T>::type*>(t->d_fat_nodes) : a.nodes;
+      a.far_nodes = (mode & 2) ? a.fat : a.nodes;
+      if (use_fat) {
+        uint32_t* tie = nullptr;
+        PICO_TRY(c.alloc(reinterpret_cast<void**>(&tie), (nq + 1) * sizeof(uint32_t)));
+        PICO_CUDA(cudaMemsetAsync(tie, 0, sizeof(uint32_t), c.st));
+        a.tie_count = tie;
+        a.tie_list = tie + 1;
       }
-      PICO_CUDA(cudaGetLastError());
-      KnnArgs<T> f = a;
-      f.perm = a.tie_list;
-      f.nq_from = a.tie_count;
-      const unsigned fix_blocks = std::min<unsigned>(blocks, (unsigned)t->sm_count * 2);
+      const bool rec = !(mode & 4);
+#define PICO_LAUNCH_NN(D)                                                                  \
+  do {                                                                                     \
+    if (use_fat) {                                                                         \
+      if (rec)                                                                             \
+        nn_kernel<T, D, 3, true><<<blocks, kThreadsPerBlock, 0, c.st>>>(a);                \
+      else                                                                                 \
+        nn_kernel<T, D, 0, true><<<blocks, kThreadsPerBlock, 0, c.st>>>(a);                \
+    } else {                                                                               \
+      if (rec)                                                                             \
+        nn_kernel<T, D, 3, false><<<blocks, kThreadsPerBlock, 0, c.st>>>(a);               \
+      else                                                                                 \
+        nn_kernel<T, D, 0, false><<<blocks, kThreadsPerBlock, 0, c.st>>>(a);               \
+    }                                                                                      \
+  } while (0)
       if (t->sdim == 2)
-        knn_thread_kernel<T, 2, 1, true, false><<<fix_blocks, kThreadsPerBlock, 0, c.st>>>(f);
+        PICO_LAUNCH_NN(2);
       else
-        knn_thread_kernel<T, 3, 1, true, false><<<fix_blocks, kThreadsPerBlock, 0, c.st>>>(f);
-      *launches += 1;
+        PICO_LAUNCH_NN(3);
+#undef PICO_LAUNCH_NN
+      PICO_CUDA(cudaGetLastError());
+      if (use_fat) {
+        KnnArgs<T> f = a;
+        f.perm = a.tie_list;
+        f.nq_from = a.tie_count;
+        const unsigned fix_blocks = std::min<unsigned>(blocks, (unsigned)t->sm_count * 2);
+        if (t->sdim == 2)
+          knn_thread_kernel<T, 2, 1, true, false><<<fix_blocks, kThreadsPerBlock, 0, c.st>>>(f);
+        else
+          knn_thread_kernel<T, 3, 1, true, false><<<fix_blocks, kThreadsPerBlock, 0, c.st>>>(f);
+        *launches += 1;
+      }
     } else {
       switch (t->sdim) {
         case 1:

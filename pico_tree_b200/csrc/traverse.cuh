@@ -493,37 +493,85 @@ struct VisitNnTie {
   }
 };
 
+// ---------------------------------------------------------------- slot stack of the nn traversal
+// Three words per slot, `[slot][thread]` in shared memory: the bank of an access is the thread's lane whatever
+// its slot, so lanes that push and pop at different depths never conflict (per-thread local memory puts
+// every lane's word in a line of its own: 158 M of the 344 M L1 sectors of the round-1 kernel were stack
+// words, profiles/r1/kernels_v9_summary.txt). Slots beyond kSharedSlots spill to local memory (3 % of the
+// cfg2 queries go deeper than four).
+//   far child : tag = node | split_dim << 30, x = box distance, y = offset on split_dim inside it
+//   restore   : tag = 3 << 30 | split_dim,    x = offset to put back when the subtree is done
+// The reference sets node_box_offset_[split_dim] before it enters the far child and puts the old value back
+// after (kd_tree_search.hpp:93-103); a far child that is taken leaves a restore record in its slot.
+constexpr int kSharedSlots = 4;
+constexpr uint32_t kTagRestore = 3u << 30, kTagNodeMask = (1u << 30) - 1u;
+
+template <typename T, int THREADS>
+struct SlotStack {
+  uint32_t (*tag)[THREADS];  // shared [kSharedSlots][THREADS]
+  T (*x)[THREADS];
+  T (*y)[THREADS];
+  uint32_t ltag[kLocalStack];  // spill
+  T lx[kLocalStack], ly[kLocalStack];
+  __device__ __forceinline__ void push(int sp, uint32_t t, T a, T b) {
+    if (sp < kSharedSlots) {
+      tag[sp][threadIdx.x] = t;
+      x[sp][threadIdx.x] = a;
+      y[sp][threadIdx.x] = b;
+    } else {
+      ltag[sp - kSharedSlots] = t;
+      lx[sp - kSharedSlots] = a;
+      ly[sp - kSharedSlots] = b;
+    }
+  }
+  __device__ __forceinline__ void pop(int sp, uint32_t& t, T& a, T& b) const {
+    if (sp < kSharedSlots) {
+      t = tag[sp][threadIdx.x];
+      a = x[sp][threadIdx.x];
+      b = y[sp][threadIdx.x];
+    } else {
+      t = ltag[sp - kSharedSlots];
+      a = lx[sp - kSharedSlots];
+      b = ly[sp - kSharedSlots];
+    }
+  }
+};
+
 // Exact nearest neighbour, metric_l2_squared, sdim <= 3, for ONE query held in registers.
 //
-//   fat        search image: `nodes` with every subtree of <= fat_limit points collapsed to a leaf
+//   fat        search image: `nodes` with every subtree of <= fat_limit points collapsed to a leaf (fat.cu), or
+//              the real `nodes` (FAT = false)
 //   far_nodes  the array far children are traversed in (`fat` again, or the real `nodes`)
 //
-// 1. first descent over `fat`, no frames (kd_tree_search.hpp:60-88 without the recursion), keeping the
-//    last NREC strict prefix minima of the far-child offsets met on the way {value, branch node};
-// 2. scan of the first (fat) leaf -> best; reach = best widened by 2^-13 of the first best, so that a
-//    far_dist that rounding left a few ulps above the exact box distance (it is a running sum with one
-//    rounding per level) can never hide a point AT the best distance: ties are always seen;
-// 3. the far children of the first path that can matter are those with offset <= reach; the topmost of
-//    them is necessarily a strict prefix minimum (everything above it is > reach >= it). If the newest
-//    record is already > reach no far child matters and the query is done. Otherwise the second walk
+// 1. first descent, no frames (kd_tree_search.hpp:60-88 without the recursion), keeping the last NREC strict
+//    prefix minima of the far-child offsets met on the way {value, branch node};
+// 2. scan of the first leaf -> best. FAT: reach = best widened by 2^-13 of the first best, so that a far_dist
+//    that rounding left a few ulps above the exact box distance (it is a running sum with one rounding per
+//    level) can never hide a point AT the best distance — ties are always seen, and a query with a tie is
+//    re-run in the reference's visit order (VisitNnTie). Not FAT: reach = best, the reference's own test, and
+//    the visit order is the reference's (same argument as PRIME == kPrimeFirstLeaf of traverse_packed);
+// 3. the far children of the first path that can matter are those with offset <= reach; the topmost of them is
+//    necessarily a strict prefix minimum (everything above it is > reach >= it). If the newest record is
+//    already > reach no far child matters and the query is done. Otherwise the second walk
 //    (kd_tree_search.hpp:89-103 with an explicit stack) starts at the oldest recorded node whose value is
 //    <= reach — from the root only when the evicted record would qualify as well. On the first path
 //    node_box_distance and every offset are zero, so starting anywhere on it needs no other state.
-template <typename T, int DIM, int NREC, typename Stack>
-__device__ __forceinline__ void traverse_nn_fat(const typename NodeOf<T>::type* __restrict__ fat,
-                                                const typename NodeOf<T>::type* __restrict__ far_nodes,
-                                                const typename Vec4Of<T>::type* __restrict__ pts4, const T (&q)[DIM],
-                                                Stack& stack, VisitNnTie<T>& vis) {
+template <typename T, int DIM, int NREC, bool FAT, typename Stack>
+__device__ __forceinline__ void traverse_nn(const typename NodeOf<T>::type* __restrict__ fat,
+                                            const typename NodeOf<T>::type* __restrict__ far_nodes,
+                                            const typename Vec4Of<T>::type* __restrict__ pts4, const T (&q)[DIM],
+                                            Stack& stack, VisitNnTie<T>& vis) {
   constexpr int metric = PICO_B200_METRIC_L2_SQUARED;
+  constexpr int R = NREC > 0 ? NREC : 1;
   T a, b;
   uint32_t right, sd;
   int lb, le;
   uint32_t node = 0;
-  T pm_val[NREC > 0 ? NREC : 1];
-  uint32_t pm_node[NREC > 0 ? NREC : 1];
+  T pm_val[R];
+  uint32_t pm_node[R];
   T pm_evicted = Limits<T>::max();
 #pragma unroll
-  for (int r = 0; r < (NREC > 0 ? NREC : 1); ++r) {
+  for (int r = 0; r < R; ++r) {
     pm_val[r] = Limits<T>::max();
     pm_node[r] = 0;
   }
@@ -538,9 +586,9 @@ __device__ __forceinline__ void traverse_nn_fat(const typename NodeOf<T>::type* 
       const T t = sub_rn(go_left ? b : a, v);
       const T new_off = mul_rn(t, t);
       if (new_off < pm_val[0]) {
-        pm_evicted = pm_val[NREC > 0 ? NREC - 1 : 0];
+        pm_evicted = pm_val[R - 1];
 #pragma unroll
-        for (int r = (NREC > 0 ? NREC - 1 : 0); r > 0; --r) {
+        for (int r = R - 1; r > 0; --r) {
           pm_val[r] = pm_val[r - 1];
           pm_node[r] = pm_node[r - 1];
         }
@@ -560,17 +608,17 @@ __device__ __forceinline__ void traverse_nn_fat(const typename NodeOf<T>::type* 
     if (DIM > 2) d = metric_fold(metric, d, q[DIM > 2 ? 2 : 0], p.z, 2);
     vis.visit(index_of(p), d);
   }
-  const T margin = mul_rn(vis.best, sizeof(T) == 4 ? T(1.2207031e-4) : T(2.2737368e-13));
-  T reach = add_rn(vis.best, margin);
+  const T margin = FAT ? mul_rn(vis.best, sizeof(T) == 4 ? T(1.2207031e-4) : T(2.2737368e-13)) : T(0);
+  T reach = FAT ? add_rn(vis.best, margin) : vis.best;
   node = 0;
   if (NREC > 0) {
     if (reach < pm_val[0]) return;
     bool found = false;
 #pragma unroll
-    for (int r = (NREC > 0 ? NREC - 1 : 0); r >= 0; --r) {
+    for (int r = R - 1; r >= 0; --r) {
       if (!found && pm_val[r] <= reach) {
         found = true;
-        node = (r == NREC - 1 && pm_evicted <= reach) ? 0u : pm_node[r];
+        node = (r == R - 1 && pm_evicted <= reach) ? 0u : pm_node[r];
       }
     }
   }
@@ -598,10 +646,7 @@ __device__ __forceinline__ void traverse_nn_fat(const typename NodeOf<T>::type* 
       node = go_left ? node + 1 : right;
       const T far_dist = add_rn(sub_rn(node_dist, old), new_off);
       if (reach >= far_dist) {
-        T snap[DIM];
-#pragma unroll
-        for (int j = 0; j < DIM; ++j) snap[j] = (sd == (uint32_t)j) ? new_off : off[j];
-        stack.push(sp, far, far_dist, snap);
+        stack.push(sp, far | (sd << 30), far_dist, new_off);
         ++sp;
       }
       load_node(cur, node, a, b, right, sd, lb, le);
@@ -616,20 +661,35 @@ __device__ __forceinline__ void traverse_nn_fat(const typename NodeOf<T>::type* 
         if (DIM > 2) d = metric_fold(metric, d, q[DIM > 2 ? 2 : 0], p.z, 2);
         vis.visit(index_of(p), d);
       }
-      reach = add_rn(vis.best, margin);
+      reach = FAT ? add_rn(vis.best, margin) : vis.best;
     }
     bool found = false;
     while (sp > 0) {
       --sp;
-      T d;
-      uint32_t n;
-      T snap[DIM];
-      stack.pop(sp, n, d, snap);
-      if (reach >= d) {
-        node = n;
-        node_dist = d;
+      uint32_t tag;
+      T x, y;
+      stack.pop(sp, tag, x, y);
+      const uint32_t hi = tag >> 30;
+      if (hi == 3u) {  // the far subtree of this slot is done: put its offset back
 #pragma unroll
-        for (int j = 0; j < DIM; ++j) off[j] = snap[j];
+        for (int j = 0; j < DIM; ++j)
+          if ((tag & 3u) == (uint32_t)j) off[j] = x;
+        continue;
+      }
+      if (reach >= x) {
+        node = tag & kTagNodeMask;
+        node_dist = x;
+        T old = off[0];
+#pragma unroll
+        for (int j = 1; j < DIM; ++j)
+          if (hi == (uint32_t)j) old = off[j];
+#pragma unroll
+        for (int j = 0; j < DIM; ++j)
+          if (hi == (uint32_t)j) off[j] = y;
+        if (sp > 0) {  // something is still pending below: it must see the offsets as they are now
+          stack.push(sp, kTagRestore | hi, old, T(0));
+          ++sp;
+        }
         found = true;
         break;
       }

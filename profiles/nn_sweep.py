@@ -1,5 +1,5 @@
 """Resident cfg2 knn=1 step and traversal-kernel time for the tuning hooks of the search-image nn kernel
-(PICO_B200_FAT_LEAF, PICO_B200_NN_FAT, ...), each point in its own process (the hooks are read once), with the
+(PICO_B200_NN, PICO_B200_FAT_LEAF, ...), each point in its own process (the hooks are read once), with the
 full-size parity check against the unmodified reference (oracle/_ref) done once and every point compared with it.
 
     python profiles/nn_sweep.py [point ...]      point = KEY=VAL,KEY=VAL (PICO_B200_ prefix implied)
@@ -68,7 +68,7 @@ if __name__ == "__main__":
         from oracle import oracle as O
         ref = O.RefTree(tree_pts, 10) if O.ref_available() else O.OracleTree(tree_pts, 10)
         np.save(WANT, ref.search_knn(q, 1, threads=O.max_threads()))
-    points = sys.argv[1:] or ["NN_FAT=0"] + ["FAT_LEAF=%d,NN_FAT=%d" % (l, m) for l in (16, 24, 32, 48) for m in (1, 3, 5)]
+    points = sys.argv[1:] or ["NN=0", "NN=1", "NN=5", "FAT_LEAF=12,NN=1", "FAT_LEAF=12,NN=3", "FAT_LEAF=16,NN=1", "FAT_LEAF=16,NN=3", "FAT_LEAF=24,NN=3"]
     for p in points:
         env = {}
         for kv in p.split(","):

@@ -23,6 +23,7 @@ static inline long long __double_as_longlong(double d) { long long i; std::memcp
 static inline double __longlong_as_double(long long i) { double d; std::memcpy(&d, &i, 8); return d; }
 // loads by record type (uint4 = f32 node, float4 = f32 point ...): statistics for tests/test_traverse_host.py
 static thread_local unsigned long long g_loads16 = 0, g_loads_pts = 0;
+static const uint3 threadIdx = {0, 0, 0};  // one "thread" at a time
 template <typename V>
 static inline V __ldg(const V* p) {
   ++g_loads16;
@@ -34,6 +35,30 @@ static inline float4 __ldg(const float4* p) {
 }
 
 #include "../../pico_tree_b200/csrc/traverse.cuh"
+
+// stack statistics (pushes, pops, deepest stack) for tests/test_traverse_host.py
+static thread_local unsigned long long g_push = 0, g_pop = 0, g_max_sp_sum = 0, g_sp_hist[8] = {0};
+template <typename T>
+struct CountingStack {
+  uint32_t tag[pico::kSharedSlots][1];
+  T x[pico::kSharedSlots][1], y[pico::kSharedSlots][1];
+  pico::SlotStack<T, 1> s;
+  int max_sp = 0;
+  CountingStack() {
+    s.tag = tag;
+    s.x = x;
+    s.y = y;
+  }
+  void push(int sp, uint32_t t, T a, T b) {
+    if ((t >> 30) != 3u) ++g_push;
+    if (sp + 1 > max_sp) max_sp = sp + 1;
+    s.push(sp, t, a, b);
+  }
+  void pop(int sp, uint32_t& t, T& a, T& b) const {
+    s.pop(sp, t, a, b);
+    if ((t >> 30) != 3u) ++g_pop;
+  }
+};
 
 namespace {
 
@@ -47,19 +72,27 @@ void nn_fat(const void* fat, const void* far_nodes, const void* pts4, const T* q
     T qq[DIM];
     for (int j = 0; j < DIM; ++j) qq[j] = q[i * DIM + j];
     VisitNnTie<T> vis;
-    LocalStack<T, DIM, kLocalStack> st;
-    if (nrec == 0)
-      traverse_nn_fat<T, DIM, 0>(static_cast<const NodeT*>(fat), static_cast<const NodeT*>(far_nodes),
-                                 static_cast<const V4*>(pts4), qq, st, vis);
-    else if (nrec == 1)
-      traverse_nn_fat<T, DIM, 1>(static_cast<const NodeT*>(fat), static_cast<const NodeT*>(far_nodes),
-                                 static_cast<const V4*>(pts4), qq, st, vis);
-    else
-      traverse_nn_fat<T, DIM, 3>(static_cast<const NodeT*>(fat), static_cast<const NodeT*>(far_nodes),
-                                 static_cast<const V4*>(pts4), qq, st, vis);
+    CountingStack<T> st;
+    const NodeT* f = static_cast<const NodeT*>(fat);
+    const NodeT* fr = static_cast<const NodeT*>(far_nodes);
+    const V4* p4 = static_cast<const V4*>(pts4);
+    if (f == fr && nrec >= 100) {  // no search image: the reference's own prune test and visit order
+      if (nrec == 100)
+        traverse_nn<T, DIM, 0, false>(f, fr, p4, qq, st, vis);
+      else
+        traverse_nn<T, DIM, 3, false>(f, fr, p4, qq, st, vis);
+    } else if (nrec == 0) {
+      traverse_nn<T, DIM, 0, true>(f, fr, p4, qq, st, vis);
+    } else if (nrec == 1) {
+      traverse_nn<T, DIM, 1, true>(f, fr, p4, qq, st, vis);
+    } else {
+      traverse_nn<T, DIM, 3, true>(f, fr, p4, qq, st, vis);
+    }
     idx[i] = vis.idx;
     dist[i] = vis.best;
     tie[i] = vis.tie ? 1 : 0;
+    g_max_sp_sum += st.max_sp;
+    g_sp_hist[st.max_sp < 7 ? st.max_sp : 7]++;
   }
 }
 
@@ -100,6 +133,12 @@ unsigned long long host_take_loads16() {
   const unsigned long long v = g_loads16;
   g_loads16 = 0;
   return v;
+}
+// {pushes, pops, sum of deepest stack, histogram of deepest stack 0..7+} since the last call
+void host_take_stack_stats(unsigned long long* out11) {
+  out11[0] = g_push; out11[1] = g_pop; out11[2] = g_max_sp_sum;
+  for (int i = 0; i < 8; ++i) { out11[3 + i] = g_sp_hist[i]; g_sp_hist[i] = 0; }
+  g_push = g_pop = g_max_sp_sum = 0;
 }
 unsigned long long host_take_point_loads() {
   const unsigned long long v = g_loads_pts;

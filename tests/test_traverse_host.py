@@ -105,6 +105,30 @@ def test_search_image_nn_matches_oracle(oracle, host_lib, kind, n, sdim, dtype, 
                 assert tie.sum() > len(q) // 4
             elif kind != "lidar":
                 assert tie.sum() == 0
+    # without a search image (real tree throughout, the reference's own prune test): the reference's visit
+    # order, hence its index even where several points share the minimum distance
+    for nrec in (100, 103):
+        idx, dist, _ = run_nn_fat(host_lib, flat, flat, pts4, q, nrec)
+        assert np.array_equal(dist, want["distance"][:, 0]) and np.array_equal(idx, want["index"][:, 0]), nrec
+
+
+def test_slot_stack_spills_beyond_shared_slots(oracle, host_lib):
+    """Queries far outside the cloud keep many far children pending: the slot stack goes past its four shared
+    slots into the local spill, and the restore records keep the offsets right on the way back."""
+    rng = np.random.default_rng(2)
+    pts = rng.random((30_000, 3)).astype(np.float32)
+    q = (rng.random((3_000, 3)) * 8 - 4).astype(np.float32)
+    tree = oracle.OracleTree(pts, 2)
+    flat = flat_nodes(tree.nodes, np.float32)
+    pts4 = leaf_order_points(pts, tree.indices)
+    want = tree.search_knn(q, 1)
+    st = (C.c_ulonglong * 11)()
+    host_lib.host_take_stack_stats(st)
+    for nrec in (100, 103):
+        idx, dist, _ = run_nn_fat(host_lib, flat, flat, pts4, q, nrec)
+        assert np.array_equal(dist, want["distance"][:, 0]) and np.array_equal(idx, want["index"][:, 0])
+    host_lib.host_take_stack_stats(st)
+    assert st[3 + 7] > 0 or st[3 + 5] > 0 or st[3 + 6] > 0, "no query went deeper than four slots"
 
 
 def test_tie_flag_is_complete(oracle, host_lib):
