@@ -142,7 +142,13 @@ class rows_of {
       regular = b > a && (b - a) % sizeof(scalar_type) == 0 && (b - a) / sizeof(scalar_type) >= sdim_;
       if (regular) {
         stride_ = (b - a) / sizeof(scalar_type);
-        for (size_t i = 2; i < n_ && regular; ++i) regular = at(s, i) == p0 + i * stride_;
+        if constexpr (one_block<space_type>::value) {
+          // one allocation with a fixed pitch by construction (space_map, Eigen matrices, cv::Mat, vectors of
+          // fixed-size points): the first, second and last point pin the layout — no O(n) walk per batch call
+          regular = at(s, n_ - 1) == p0 + (n_ - 1) * stride_;
+        } else {
+          for (size_t i = 2; i < n_ && regular; ++i) regular = at(s, i) == p0 + i * stride_;
+        }
       }
     }
     if (!regular) {
@@ -168,6 +174,18 @@ class rows_of {
 
  private:
   static scalar_type const* at(space_type const& s, size_t i) { return ptraits::data(traits::point_at(s, i)); }
+
+  // Spaces whose points live in ONE block at a fixed pitch: anything with a data() member that yields scalars
+  // (space_map, Eigen::Matrix / Eigen::Map) and std::vector of fixed-size points.
+  template <typename S_, typename = void>
+  struct one_block : std::false_type {};
+  template <typename S_>
+  struct one_block<S_, std::enable_if_t<std::is_convertible_v<decltype(std::declval<S_ const&>().data()),
+                                                              scalar_type const*>>> : std::true_type {};
+  template <typename P_, typename A_>
+  struct one_block<std::vector<P_, A_>, std::enable_if_t<point_traits<P_>::dim != dynamic_extent &&
+                                                          sizeof(P_) == point_traits<P_>::dim * sizeof(scalar_type)>>
+      : std::true_type {};
 
   size_t n_;
   size_t sdim_;
@@ -358,6 +376,27 @@ class kd_tree {
     knn_batch(queries, 1, 0.0, nns);
   }
 
+  // Into caller memory: queries.size() * min(k, n) records (numpy arrays of the Python binding, pinned buffers).
+  // e == 0: exact.
+  template <typename Queries_>
+  void search_knn_batch(Queries_ const& queries, size_type const k, neighbor_type* out,
+                        scalar_type const e = scalar_type(0)) const {
+    b200::rows_of<Queries_> rows(unwrap_queries(queries));
+    check_queries(rows);
+    if (k <= n_) {
+      knn_call(rows.data(), rows.size(), rows.stride(), k, static_cast<double>(e), out);
+      return;
+    }
+    // rows of k slots but only n points: like the iterator overloads, the tail of every row keeps an
+    // infinite distance (search_visitor.hpp:98-103)
+    std::vector<neighbor_type> tmp(rows.size() * n_);
+    knn_call(rows.data(), rows.size(), rows.stride(), n_, static_cast<double>(e), tmp.data());
+    for (size_type i = 0; i < rows.size(); ++i) {
+      neighbor_type* row = std::copy_n(tmp.data() + i * n_, n_, out + i * k);
+      std::fill(row, out + (i + 1) * k, neighbor_type(index_type(0), std::numeric_limits<scalar_type>::max()));
+    }
+  }
+
   // Ragged results: the neighbours of query i are flat[offsets[i] .. offsets[i + 1]).
   template <typename Queries_>
   void search_radius_batch(Queries_ const& queries, scalar_type const radius, std::vector<size_type>& offsets,
@@ -383,10 +422,7 @@ class kd_tree {
     std::vector<size_type> offsets;
     std::vector<neighbor_type> flat;
     search_radius_batch(queries, radius, offsets, flat, sort, e);
-    nns.resize(offsets.size() - 1);
-    for (size_type i = 0; i + 1 < offsets.size(); ++i)
-      nns[i].assign(flat.begin() + static_cast<std::ptrdiff_t>(offsets[i]),
-                    flat.begin() + static_cast<std::ptrdiff_t>(offsets[i + 1]));
+    split_rows(offsets, flat, nns);
   }
 
   // Box i is [mins[i], maxs[i]] (inclusive); indices of box i are flat[offsets[i] .. offsets[i+1]).
@@ -406,6 +442,34 @@ class kd_tree {
     out.p = raw;
     offsets.assign(offs.begin(), offs.end());
     flat.assign(raw, raw + offs.back());
+  }
+
+  // Same, as one vector per box.
+  template <typename Queries_>
+  void search_box_batch(Queries_ const& mins, Queries_ const& maxs, std::vector<std::vector<index_type>>& idxs) const {
+    std::vector<size_type> offsets;
+    std::vector<index_type> flat;
+    search_box_batch(mins, maxs, offsets, flat);
+    split_rows(offsets, flat, idxs);
+  }
+
+  // Boxes given as consecutive (min, max) rows of ONE space of 2 * n points — the layout of the reference's
+  // Python binding (_pyco_tree/kd_tree.hpp:245-268).
+  template <typename Queries_>
+  void search_box_batch_pairs(Queries_ const& boxes, std::vector<std::vector<index_type>>& idxs) const {
+    b200::rows_of<Queries_> rows(unwrap_queries(boxes));
+    check_queries(rows);
+    if (rows.size() % 2 != 0) throw std::invalid_argument("query min and max don't have equal size");
+    size_type const nb = rows.size() / 2;
+    std::vector<std::uint64_t> offs(nb + 1, 0);
+    b200::lib_buffer out;
+    std::int32_t* raw = nullptr;
+    b200::check(pico_b200_box(handle_.get(), rows.data(), rows.data() + rows.stride(), nb, 2 * rows.stride(),
+                              offs.data(), &raw, 0, nullptr));
+    out.p = raw;
+    std::vector<size_type> offsets(offs.begin(), offs.end());
+    idxs.resize(nb);
+    split_rows_raw(offsets, raw, idxs);
   }
 
   // ---------------------------------------------------------------- structure
@@ -530,6 +594,25 @@ class kd_tree {
       rec const* r = static_cast<rec const*>(src);
       for (size_type i = 0; i < count; ++i) dst[i] = neighbor_type(static_cast<index_type>(r[i].index), r[i].distance);
     }
+  }
+
+  // flat ragged result -> one vector per row (the filling is independent per row: OpenMP where it is enabled)
+  template <typename Item_>
+  static void split_rows(std::vector<size_type> const& offsets, std::vector<Item_> const& flat,
+                         std::vector<std::vector<Item_>>& rows) {
+    rows.resize(offsets.empty() ? 0 : offsets.size() - 1);
+    split_rows_raw(offsets, flat.data(), rows);
+  }
+  template <typename Src_, typename Item_>
+  static void split_rows_raw(std::vector<size_type> const& offsets, Src_ const* flat,
+                             std::vector<std::vector<Item_>>& rows) {
+    std::ptrdiff_t const n = static_cast<std::ptrdiff_t>(rows.size());
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+    for (std::ptrdiff_t i = 0; i < n; ++i)
+      rows[static_cast<size_type>(i)].assign(flat + offsets[static_cast<size_type>(i)],
+                                             flat + offsets[static_cast<size_type>(i) + 1]);
   }
 
   void knn_call(scalar_type const* q, size_type nq, size_type stride, size_type k, double e,

@@ -145,8 +145,8 @@ __global__ void __launch_bounds__(kThreadsPerBlock) knn_thread_kernel(KnnArgs<T>
 // Exact nn (traverse_nn): metric_l2_squared, k = 1, trees no deeper than the local stack. FAT: the first
 // descent and the second walk run over the search image (fat.cu); queries with a tie at the best distance are
 // listed for the order-exact kernel above.
-template <typename T, int DIM, int NREC, bool FAT>
-__global__ void __launch_bounds__(kThreadsPerBlock, 2048 / kThreadsPerBlock) nn_kernel(KnnArgs<T> a) {
+template <typename T, int DIM, int NREC, bool FAT, int MINB>
+__global__ void __launch_bounds__(kThreadsPerBlock, MINB) nn_kernel(KnnArgs<T> a) {
   __shared__ uint32_t s_tag[kSharedSlots][kThreadsPerBlock];
   __shared__ T s_x[kSharedSlots][kThreadsPerBlock];
   __shared__ T s_y[kSharedSlots][kThreadsPerBlock];
@@ -897,12 +897,13 @@ void launch_knn_thread(const KnnArgs<T>& a, bool fast, bool deep, unsigned block
 
 // PICO_B200_NN (tuning hook): 0 = round-1 order-exact kernel (local-memory stack); bit 0 = nn_kernel (shared slot
 // stack); bit 1 = far children are walked in the search image too (default: in the real tree); bit 2 = no
-// prefix-minimum restart records; bit 3 = ignore the search image even if the tree has one
+// prefix-minimum restart records; bit 3 = ignore the search image even if the tree has one;
+// bit 4 = let the kernel use up to 40 registers (12 resident blocks per SM instead of 16)
 int nn_mode() {
   static const int v = [] {
     const char* e = getenv("PICO_B200_NN");
     const int x = e ? atoi(e) : -1;
-    return (x >= 0 && x <= 15) ? x : 1;
+    return (x >= 0 && x <= 31) ? x : 1;
   }();
   return v;
 }
@@ -955,25 +956,34 @@ int knn_enqueue(CallCtx& c, const pico_b200_tree* t, const T* q, size_t nq, size
         a.tie_list = tie + 1;
       }
       const bool rec = !(mode & 4);
-#define PICO_LAUNCH_NN(D)                                                                  \
+      // MINB: resident blocks per SM the register allocation must allow (16 = full occupancy, 32 registers)
+#define PICO_LAUNCH_NN2(D, MINB)                                                           \
   do {                                                                                     \
     if (use_fat) {                                                                         \
       if (rec)                                                                             \
-        nn_kernel<T, D, 3, true><<<blocks, kThreadsPerBlock, 0, c.st>>>(a);                \
+        nn_kernel<T, D, 3, true, MINB><<<blocks, kThreadsPerBlock, 0, c.st>>>(a);          \
       else                                                                                 \
-        nn_kernel<T, D, 0, true><<<blocks, kThreadsPerBlock, 0, c.st>>>(a);                \
+        nn_kernel<T, D, 0, true, MINB><<<blocks, kThreadsPerBlock, 0, c.st>>>(a);          \
     } else {                                                                               \
       if (rec)                                                                             \
-        nn_kernel<T, D, 3, false><<<blocks, kThreadsPerBlock, 0, c.st>>>(a);               \
+        nn_kernel<T, D, 3, false, MINB><<<blocks, kThreadsPerBlock, 0, c.st>>>(a);         \
       else                                                                                 \
-        nn_kernel<T, D, 0, false><<<blocks, kThreadsPerBlock, 0, c.st>>>(a);               \
+        nn_kernel<T, D, 0, false, MINB><<<blocks, kThreadsPerBlock, 0, c.st>>>(a);         \
     }                                                                                      \
+  } while (0)
+#define PICO_LAUNCH_NN(D)         \
+  do {                            \
+    if (mode & 16)                \
+      PICO_LAUNCH_NN2(D, 12);     \
+    else                          \
+      PICO_LAUNCH_NN2(D, 16);     \
   } while (0)
       if (t->sdim == 2)
         PICO_LAUNCH_NN(2);
       else
         PICO_LAUNCH_NN(3);
 #undef PICO_LAUNCH_NN
+#undef PICO_LAUNCH_NN2
       PICO_CUDA(cudaGetLastError());
       if (use_fat) {
         KnnArgs<T> f = a;

@@ -631,13 +631,12 @@ __device__ __forceinline__ void traverse_nn(const typename NodeOf<T>::type* __re
   for (;;) {
     load_node(cur, node, a, b, right, sd, lb, le);
     while (sd != PICO_B200_LEAF) {
+      // (selects, not indexed stores: a run-time index would move off[] to local memory)
       T v = q[0], old = off[0];
 #pragma unroll
       for (int j = 1; j < DIM; ++j) {
-        if (sd == (uint32_t)j) {
-          v = q[j];
-          old = off[j];
-        }
+        v = (sd == (uint32_t)j) ? q[j] : v;
+        old = (sd == (uint32_t)j) ? off[j] : old;
       }
       const bool go_left = sub_rn(sub_rn(add_rn(a, b), v), v) > T(0);
       const T t = sub_rn(go_left ? b : a, v);
@@ -672,8 +671,7 @@ __device__ __forceinline__ void traverse_nn(const typename NodeOf<T>::type* __re
       const uint32_t hi = tag >> 30;
       if (hi == 3u) {  // the far subtree of this slot is done: put its offset back
 #pragma unroll
-        for (int j = 0; j < DIM; ++j)
-          if ((tag & 3u) == (uint32_t)j) off[j] = x;
+        for (int j = 0; j < DIM; ++j) off[j] = ((tag & 3u) == (uint32_t)j) ? x : off[j];
         continue;
       }
       if (reach >= x) {
@@ -681,11 +679,9 @@ __device__ __forceinline__ void traverse_nn(const typename NodeOf<T>::type* __re
         node_dist = x;
         T old = off[0];
 #pragma unroll
-        for (int j = 1; j < DIM; ++j)
-          if (hi == (uint32_t)j) old = off[j];
+        for (int j = 1; j < DIM; ++j) old = (hi == (uint32_t)j) ? off[j] : old;
 #pragma unroll
-        for (int j = 0; j < DIM; ++j)
-          if (hi == (uint32_t)j) off[j] = y;
+        for (int j = 0; j < DIM; ++j) off[j] = (hi == (uint32_t)j) ? y : off[j];
         if (sp > 0) {  // something is still pending below: it must see the offsets as they are now
           stack.push(sp, kTagRestore | hi, old, T(0));
           ++sp;
