@@ -24,6 +24,9 @@ static inline double __longlong_as_double(long long i) { double d; std::memcpy(&
 // loads by record type (uint4 = f32 node, float4 = f32 point ...): statistics for tests/test_traverse_host.py
 static thread_local unsigned long long g_loads16 = 0, g_loads_pts = 0;
 static const uint3 threadIdx = {0, 0, 0};  // one "thread" at a time
+static inline unsigned __activemask() { return 1u; }
+template <typename V>
+static inline V __shfl_sync(unsigned, V v, int) { return v; }
 template <typename V>
 static inline V __ldg(const V* p) {
   ++g_loads16;

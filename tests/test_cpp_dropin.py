@@ -120,3 +120,163 @@ def test_reference_binding_agrees_with_host_mirror(ref_binding, tmp_path):
     m.save_kd_tree(theirs, f)          # written by the reference's binding code ...
     back = pt.load_kd_tree(pts, f)     # ... read by the host mirror
     assert np.array_equal(back.search_knn(q, 4)["index"], a["index"])
+
+
+# ---------------------------------------------------------------------------------------- batch binding (f2)
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference sources only exist in the dev container")
+def test_batch_binding_builds_and_has_no_per_query_loops(tmp_path):
+    """tests/cpp/repoint_binding.py turns the five OpenMP loops of the reference's _pyco_tree/kd_tree.hpp into one
+    batch call each; the result must compile into tests/_bin/batch/_pyco_tree.so."""
+    out = tmp_path / "kd_tree.hpp"
+    subprocess.run([sys.executable, os.path.join(ROOT, "tests", "cpp", "repoint_binding.py"),
+                    os.path.join(REF, "src/pyco_tree/pico_tree/_pyco_tree/kd_tree.hpp"), str(out)], check=True)
+    text = out.read_text()
+    assert "#pragma omp parallel for" not in text
+    for call in ("search_knn_batch(query, k, output)", "search_knn_batch(query, k, output, e_b200)",
+                 "search_radius_batch(query, radius_b200, nns_data, sort)",
+                 "search_radius_batch(query, radius_b200, nns_data, sort, e_b200)",
+                 "search_box_batch_pairs(query, indices_data)"):
+        assert call in text, call
+    assert text.count("py::gil_scoped_release") == 5
+    _make("ref")
+    assert os.path.exists(os.path.join(BIN, "batch", "_pyco_tree.so"))
+
+
+BATCH_CASES = r'''
+import copy, os, sys, tempfile, time
+import numpy as np
+sys.path.insert(0, %(dir)r)
+sys.path.insert(0, %(root)r)
+import _pyco_tree as pt
+
+# ---- test/pyco_tree/kd_tree_test.py of the reference, case by case ------------------------------------
+# test_creation_kd_tree
+a = np.array([[2, 1], [4, 3], [8, 7]], dtype=np.float64, order='C')
+t = pt.KdTree(a, pt.Metric.L2Squared, 10)
+assert (a.shape[0], a.shape[1]) == (t.npts, t.sdim) and a.dtype == t.dtype_scalar
+try:
+    pt.KdTree(a[::2], pt.Metric.L2Squared, 10); raise SystemExit("non-contiguous accepted")
+except ValueError:
+    pass
+a = np.array([[2, 1], [4, 3], [8, 7]], dtype=np.float32, order='F')
+t = pt.KdTree(a, pt.Metric.L2Squared, 10)
+assert (a.shape[1], a.shape[0]) == (t.npts, t.sdim) and a.dtype == t.dtype_scalar
+a[0][0] = 42
+assert a[0][0] == memoryview(t)[0, 0]
+try:
+    pt.KdTree(np.array([[[2, 1]], [[4, 3]], [[8, 7]]], dtype=np.float32), pt.Metric.L2Squared, 10)
+    raise SystemExit("3-d array accepted")
+except ValueError:
+    pass
+# test_metric
+a = np.array([[2, 1], [4, 3], [8, 7]], dtype=np.float32)
+assert pt.KdTree(a, pt.Metric.L2Squared, 10).metric(-2.0) == 4
+assert pt.KdTree(a, pt.Metric.L1, 10).metric(-2.0) == 2
+# test_search_knn / test_search_approximate_knn
+t = pt.KdTree(a, pt.Metric.L2Squared, 10)
+for extra in ((), (1.0,)):
+    nns = t.search_knn(a, 2, *extra)
+    assert nns.shape == (3, 2)
+    for i in range(len(nns)):
+        assert nns[i][0][0] == i and abs(nns[i][0][1]) < 1e-7
+    data = copy.deepcopy(nns.ctypes.data)
+    t.search_knn(a, 2, *extra, nns)
+    assert nns.ctypes.data == data
+# test_search_radius / test_search_approximate_radius
+def addresses(nns):
+    return [copy.deepcopy(x.ctypes.data) if len(x) else 0 for x in nns]
+radius = t.metric(2.5)
+for extra in ((), (1.0,)):
+    nns = t.search_radius(a, radius, *extra)
+    assert len(nns) == 3 and nns.dtype == t.dtype_neighbor and nns
+    for i, n in enumerate(nns):
+        assert len(n) == 1 and n[0][0] == i and abs(n[0][1]) < 1e-7
+    for i in range(len(nns)):
+        assert nns[i][0][0] == i
+    datas = addresses(nns)
+    t.search_radius(a, radius, *extra, nns)
+    assert addresses(nns) == datas
+# test_search_box
+boxes = np.array([[0, 0], [3, 3], [2, 2], [3, 3], [0, 0], [9, 9], [6, 6], [9, 9]], dtype=np.float32)
+nns = t.search_box(boxes)
+assert len(nns) == 4 and nns.dtype == t.dtype_index and nns
+datas = addresses(nns)
+t.search_box(boxes, nns)
+assert addresses(nns) == datas
+assert [len(n) for n in nns] == [1, 0, 3, 1]
+part = nns[0:4:2]
+assert len(part) == 2 and [len(n) for n in part] == [1, 3] and len(part[-1]) == 3
+try:
+    t.search_box(boxes[:3]); raise SystemExit("odd number of box rows accepted")
+except ValueError:
+    pass
+# test_creation_darray
+d = pt.DArray(t.dtype_neighbor); assert d.dtype == t.dtype_neighbor and not d
+t64 = pt.KdTree(np.array([[2, 1], [4, 3], [8, 7]], dtype=np.float64), pt.Metric.L2Squared, 10)
+d = pt.DArray(dtype=t64.dtype_neighbor); assert d.dtype == t64.dtype_neighbor and not d
+assert pt.DArray(np.int32).dtype == t64.dtype_index and pt.DArray(np.dtype(np.int32)).dtype == t64.dtype_index
+# test_file_io
+a64 = np.array([[2, 1], [4, 3], [8, 7]], dtype=np.float64, order='C')
+t1 = pt.KdTree(a64, pt.Metric.L2Squared, 10)
+fn = os.path.join(tempfile.mkdtemp(), "tree.bin")
+pt.save_kd_tree(t1, fn)
+t2 = pt.load_kd_tree(a64, fn)
+assert repr(t1) == repr(t2) and t1.dtype_scalar == t2.dtype_scalar
+assert np.array_equal(t1.search_knn(a64, 2), t2.search_knn(a64, 2))
+
+# ---- against the host mirror (same engine), larger batches, every dtype x layout --------------------------
+import pico_tree_b200 as mine
+rng = np.random.default_rng(5)
+for dtype in (np.float32, np.float64):
+    pts = rng.random((30000, 3)).astype(dtype)
+    q = rng.random((5000, 3)).astype(dtype)
+    ours, theirs = mine.KdTree(pts, mine.Metric.L2Squared, 10), pt.KdTree(pts, pt.Metric.L2Squared, 10)
+    for extra in ((), (1.5,)):
+        x, y = ours.search_knn(q, 4, *extra), theirs.search_knn(q, 4, *extra)
+        assert np.array_equal(x["index"], y["index"]) and np.array_equal(x["distance"], y["distance"])
+        x, y = ours.search_radius(q, 0.002, *extra), theirs.search_radius(q, 0.002, *extra)
+        assert [len(n) for n in x] == [len(n) for n in y]
+        assert all(np.array_equal(n["index"], m["index"]) for n, m in zip(x, y))   # visit order
+    bx = np.empty((2000, 3), dtype); bx[0::2] = q[:1000] - 0.03; bx[1::2] = q[:1000] + 0.03
+    x, y = ours.search_box(bx), theirs.search_box(bx)
+    assert all(np.array_equal(n, m) for n, m in zip(x, y))
+    # column-major queries (sdim x n, the layout Eigen users pass)
+    qf = np.asfortranarray(q.T)
+    y = theirs.search_knn(qf, 2)
+    assert y.shape == (2, 5000) and np.array_equal(y.T["index"], ours.search_knn(q, 2)["index"])
+    # k larger than the point set: rows of k slots, the tail infinite
+    small = pt.KdTree(pts[:3].copy(), pt.Metric.L2Squared, 10)
+    y = small.search_knn(q[:10], 5)
+    assert y.shape == (10, 5) and np.all(np.diff(y["distance"][:, :3], axis=1) >= 0)
+
+# ---- one batch call, not a loop of device calls: 7.2M-query scale is covered by %(full)s ------------
+pts = rng.random((1_000_000, 3)).astype(np.float32)
+q = rng.random((1_000_000, 3)).astype(np.float32)
+ours, theirs = mine.KdTree(pts, mine.Metric.L2Squared, 10), pt.KdTree(pts, pt.Metric.L2Squared, 10)
+out_a, out_b = ours.search_knn(q, 1), theirs.search_knn(q, 1)
+def best(fn, n=5):
+    r = 1e9
+    for _ in range(n):
+        t0 = time.perf_counter(); fn(); r = min(r, time.perf_counter() - t0)
+    return r
+ta, tb = best(lambda: ours.search_knn(q, 1, out_a)), best(lambda: theirs.search_knn(q, 1, out_b))
+assert np.array_equal(out_a["index"], out_b["index"])
+print("BATCH_BINDING 1M queries knn=1: host mirror %%.2f ms, re-pointed reference binding %%.2f ms" %% (ta * 1e3, tb * 1e3))
+assert tb < 20 * ta + 0.05, "the binding still loops over device calls"
+'''
+
+
+@pytest.mark.gpu
+def test_batch_binding_reference_cases_and_parity():
+    """The reference's Python test-suite (test/pyco_tree/kd_tree_test.py, restated case by case) through the
+    reference's own binding code with its batch loops re-pointed; then parity with the host mirror on larger
+    batches and a check that one call answers a million queries in the time of a batch, not of a loop. Runs in a
+    process of its own (two extension modules named _pyco_tree cannot share one)."""
+    path = os.path.join(BIN, "batch", "_pyco_tree.so")
+    if not os.path.exists(path):
+        pytest.skip("tests/_bin/batch/_pyco_tree.so was not built (needs /root/reference at build time)")
+    code = BATCH_CASES % {"dir": os.path.dirname(path), "root": ROOT, "full": "profiles/binding_batch.py"}
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900)
+    sys.stdout.write(r.stdout[-2000:])
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "BATCH_BINDING" in r.stdout
