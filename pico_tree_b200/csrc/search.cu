@@ -142,51 +142,6 @@ __global__ void __launch_bounds__(kThreadsPerBlock) knn_thread_kernel(KnnArgs<T>
   }
 }
 
-// knn_thread_kernel<T, DIM, 1, FAST> with the neighbour bound (traverse_packed NB), local-memory stack
-template <typename T, int DIM>
-__global__ void __launch_bounds__(kThreadsPerBlock, 2048 / kThreadsPerBlock) nn_nb_kernel(KnnArgs<T> a) {
-  const size_t total = (size_t)gridDim.x * blockDim.x;
-  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  for (size_t slot = tid; slot < a.nq; slot += total) {
-    const uint32_t qi = a.perm ? a.perm[slot] : (uint32_t)slot;
-    T q[DIM];
-    const T* qp = a.q + (size_t)qi * a.q_stride;
-#pragma unroll
-    for (int j = 0; j < DIM; ++j) q[j] = qp[j];
-    VisitNn<T> vis;
-    LocalStack<T, DIM, kLocalStack> st;
-    traverse_packed<T, DIM, true, kPrimeFirstLeaf, true>(a.nodes, a.pts4, a.outer, q, a.metric, false, a.e_inv, st, vis);
-    Neighbor<T>* out = a.out + qi;
-    out->index = vis.idx;
-    out->distance = vis.best;
-  }
-}
-
-// The order-exact nn traversal of knn_thread_kernel (traverse_packed, first-leaf priming) with the first SLOTS stack
-// entries in shared memory (SharedSnapStack).
-template <typename T, int DIM, int SLOTS, bool NB>
-__global__ void __launch_bounds__(kThreadsPerBlock, 2048 / kThreadsPerBlock) nn_snap_kernel(KnnArgs<T> a) {
-  __shared__ uint32_t s_node[SLOTS][kThreadsPerBlock];
-  __shared__ T s_vals[SLOTS][1 + DIM][kThreadsPerBlock];
-  const size_t total = (size_t)gridDim.x * blockDim.x;
-  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  for (size_t slot = tid; slot < a.nq; slot += total) {
-    const uint32_t qi = a.perm ? a.perm[slot] : (uint32_t)slot;
-    T q[DIM];
-    const T* qp = a.q + (size_t)qi * a.q_stride;
-#pragma unroll
-    for (int j = 0; j < DIM; ++j) q[j] = qp[j];
-    VisitNn<T> vis;
-    SharedSnapStack<T, DIM, SLOTS, kThreadsPerBlock> st;
-    st.node = s_node;
-    st.vals = s_vals;
-    traverse_packed<T, DIM, true, kPrimeFirstLeaf, NB>(a.nodes, a.pts4, a.outer, q, a.metric, false, a.e_inv, st, vis);
-    Neighbor<T>* out = a.out + qi;
-    out->index = vis.idx;
-    out->distance = vis.best;
-  }
-}
-
 // Exact nn (traverse_nn): metric_l2_squared, k = 1, trees no deeper than the local stack. FAT: the first
 // descent and the second walk run over the search image (fat.cu); queries with a tie at the best distance are
 // listed for the order-exact kernel above.
@@ -270,8 +225,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock) leaf_scan_kernel(KnnArgs<T> 
     VisitNn<T> vis;
     for (int i = r.x; i < r.y; ++i) {
       const typename Vec4Of<T>::type p = ldg4(a.pts4 + i);
-      T d = T(0);
-      d = metric_fold((int)PICO_B200_METRIC_L2_SQUARED, d, q[0], p.x, 0);
+      T d = metric_first((int)PICO_B200_METRIC_L2_SQUARED, q[0], p.x);
       if (DIM > 1) d = metric_fold((int)PICO_B200_METRIC_L2_SQUARED, d, q[DIM > 1 ? 1 : 0], p.y, 1);
       if (DIM > 2) d = metric_fold((int)PICO_B200_METRIC_L2_SQUARED, d, q[DIM > 2 ? 2 : 0], p.z, 2);
       vis.visit(index_of(p), d);
@@ -940,15 +894,16 @@ void launch_knn_thread(const KnnArgs<T>& a, bool fast, bool deep, unsigned block
   }
 }
 
-// PICO_B200_NN (tuning hook): 0 = round-1 order-exact kernel (local-memory stack); bit 0 = nn_kernel (shared slot
-// stack); bit 1 = far children are walked in the search image too (default: in the real tree); bit 2 = no
-// prefix-minimum restart records; bit 3 = ignore the search image even if the tree has one;
-// bit 4 = let the kernel use up to 40 registers (12 resident blocks per SM instead of 16)
+// PICO_B200_NN (tuning hook, default 0): 0 = knn_thread_kernel (order-exact, per-thread local stack) — the fastest
+// (profiles/r2/nn_sweep_*.txt); bit 0 = nn_kernel (three-word slot stack in shared memory, restore records);
+// bit 1 = far children are walked in the search image too (default: in the real tree); bit 2 = no prefix-minimum
+// restart records; bit 3 = ignore the search image even if the tree has one (PICO_B200_FAT_LEAF);
+// bit 4 = let nn_kernel use up to 40 registers (12 resident blocks per SM instead of 16)
 int nn_mode() {
   static const int v = [] {
     const char* e = getenv("PICO_B200_NN");
     const int x = e ? atoi(e) : -1;
-    return (x >= 0 && x <= 127) ? x : 1;
+    return (x >= 0 && x <= 31) ? x : 0;
   }();
   return v;
 }
@@ -987,18 +942,7 @@ int knn_enqueue(CallCtx& c, const pico_b200_tree* t, const T* q, size_t nq, size
     PICO_TRY(thread_geometry(c, t, a, (int)t->sdim, &deep, &blocks));
     const bool fast = t->metric == PICO_B200_METRIC_L2_SQUARED && !(e > 0);
     const int mode = nn_mode();
-    if (fast && !deep && k == 1 && (mode & (32 | 64)) && t->sdim == 3) {
-      if ((mode & 96) == 96)
-        nn_nb_kernel<T, 3><<<blocks, kThreadsPerBlock, 0, c.st>>>(a);
-      else if ((mode & 32) && (mode & 1))
-        nn_snap_kernel<T, 3, 4, true><<<blocks, kThreadsPerBlock, 0, c.st>>>(a);
-      else if (mode & 32)
-        nn_snap_kernel<T, 3, 4, false><<<blocks, kThreadsPerBlock, 0, c.st>>>(a);
-      else if (mode & 1)
-        nn_snap_kernel<T, 3, 3, true><<<blocks, kThreadsPerBlock, 0, c.st>>>(a);
-      else
-        nn_snap_kernel<T, 3, 3, false><<<blocks, kThreadsPerBlock, 0, c.st>>>(a);
-    } else if (fast && !deep && k == 1 && mode && t->sdim >= 2 && t->n_nodes < ((size_t)1 << 30)) {
+    if (fast && !deep && k == 1 && mode && t->sdim >= 2 && t->n_nodes < ((size_t)1 << 30)) {
       // exact nn with the shared-memory slot stack; with a search image (fat.cu) ties at the best distance go
       // through the order-exact kernel afterwards
       const bool use_fat = t->d_fat_nodes != nullptr && !(mode & 8);

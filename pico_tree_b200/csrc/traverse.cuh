@@ -112,6 +112,22 @@ __device__ __forceinline__ T metric_fold(int metric, T d, T qj, T pj, int j) {
   }
 }
 
+// The first term of the fold (j = 0) on its own: the fold starts from metric_init (0, or the largest value for
+// metric_lninf), and 0 + x, max(0, |x|) and min(largest, |x|) are x / |x| exactly — one addition per point saved.
+template <typename T>
+__device__ __forceinline__ T metric_first(int metric, T q0, T p0) {
+  const T t = sub_rn(q0, p0);
+  switch (metric) {
+    case PICO_B200_METRIC_L2_SQUARED:
+    case PICO_B200_METRIC_SE2_SQUARED:
+      return mul_rn(t, t);
+    case PICO_B200_METRIC_SO2:
+      return s1_distance(q0, p0);
+    default:
+      return abs_t(t);
+  }
+}
+
 // search_nearest_topological::box_distance (kd_tree_search.hpp:205-229): distance of v to the
 // segment [mn, mx] on the line (segment.hpp:34-42) or on the circle (:76-100), then metric(d).
 template <typename T>
@@ -215,36 +231,6 @@ struct GlobalStack {
   }
 };
 
-// The same snapshot entries with the first SLOTS of them in shared memory, `[slot][word][thread]` (the bank of
-// an access is the thread's lane whatever its slot; per-thread local memory puts every lane's word in a line of
-// its own when lanes push at different depths). Deeper entries spill to local memory.
-template <typename T, int DIM, int SLOTS, int THREADS>
-struct SharedSnapStack {
-  uint32_t (*node)[THREADS];        // [SLOTS][THREADS]
-  T (*vals)[1 + DIM][THREADS];      // [SLOTS][1 + DIM][THREADS]: box distance, then the offsets
-  LocalStack<T, DIM, kLocalStack> spill;
-  __device__ __forceinline__ void push(int sp, uint32_t n, T d, const T (&o)[DIM]) {
-    if (sp < SLOTS) {
-      node[sp][threadIdx.x] = n;
-      vals[sp][0][threadIdx.x] = d;
-#pragma unroll
-      for (int j = 0; j < DIM; ++j) vals[sp][1 + j][threadIdx.x] = o[j];
-    } else {
-      spill.push(sp - SLOTS, n, d, o);
-    }
-  }
-  __device__ __forceinline__ void pop(int sp, uint32_t& n, T& d, T (&o)[DIM]) const {
-    if (sp < SLOTS) {
-      n = node[sp][threadIdx.x];
-      d = vals[sp][0][threadIdx.x];
-#pragma unroll
-      for (int j = 0; j < DIM; ++j) o[j] = vals[sp][1 + j][threadIdx.x];
-    } else {
-      spill.pop(sp - SLOTS, n, d, o);
-    }
-  }
-};
-
 // FAST = metric_l2_squared + exact visitors, resolved at compile time.
 //
 // PRIME (used by the single-neighbour visitors): the first root-to-leaf descent is walked
@@ -273,15 +259,7 @@ struct SharedSnapStack {
 // nor for trees deeper than the local stack (the rounding margin of the bound assumes depth < 64).
 constexpr int kPrimeNone = 0, kPrimeFirstLeaf = 1, kPrimeBound = 2;
 
-//
-// NB (with PRIME == kPrimeFirstLeaf, exact search): neighbour bound. The queries of a warp are neighbours in Z-order,
-// so the best point of the NEXT lane's first leaf is usually close to this lane's query too. Its distance to this
-// query is a valid upper bound of the final nearest distance (it is a point of the tree); the traversal then prunes
-// with min(max(), bound widened by 2^-13) exactly like PRIME == kPrimeBound does — nothing is accepted out of
-// order, every node that holds a point at the final distance is still visited in the reference's order, so the
-// result is the reference's, ties included. It only removes far children that own first leaves make look
-// promising (a query next to a cell boundary whose true neighbour sits on the other side).
-template <typename T, int DIM, bool FAST, int PRIME, bool NB = false, typename Stack, typename Visitor>
+template <typename T, int DIM, bool FAST, int PRIME, typename Stack, typename Visitor>
 __device__ __forceinline__ void traverse_packed(const typename NodeOf<T>::type* __restrict__ nodes,
                                                 const typename Vec4Of<T>::type* __restrict__ pts4,
                                                 const T* __restrict__ outer, const T (&q)[DIM], int metric_rt,
@@ -318,42 +296,15 @@ __device__ __forceinline__ void traverse_packed(const typename NodeOf<T>::type* 
       load_node(nodes, node, a, b, right, sd, lb, le);
     }
     if (PRIME == kPrimeFirstLeaf) {
-      int best_pos = lb;
-      T best_seen = Limits<T>::max();
       for (int i = lb; i < le; ++i) {
         const typename Vec4Of<T>::type p = ldg4(pts4 + i);
-        T d = metric_init<T>(metric);
-        d = metric_fold(metric, d, q[0], p.x, 0);
+        T d = metric_first(metric, q[0], p.x);
         if (DIM > 1) d = metric_fold(metric, d, q[DIM > 1 ? 1 : 0], p.y, 1);
         if (DIM > 2) d = metric_fold(metric, d, q[DIM > 2 ? 2 : 0], p.z, 2);
         if (approx) d = mul_rn(d, e_inv);
-        if (NB && d < best_seen) {
-          best_seen = d;
-          best_pos = i;
-        }
         vis.visit(index_of(p), d);
       }
       primed_leaf = node;
-      if (NB) {
-        // candidates of the two neighbouring lanes (an empty first leaf offers none)
-        const unsigned mask = __activemask();
-        const int lane = threadIdx.x & 31;
-        typename Vec4Of<T>::type c = ldg4(pts4 + (lb < le ? best_pos : 0));
-        const bool have = lb < le;
-#pragma unroll
-        for (int step = 1; step <= 2; ++step) {
-          const int other = lane ^ step;
-          const T cx = __shfl_sync(mask, c.x, other), cy = __shfl_sync(mask, c.y, other),
-                  cz = __shfl_sync(mask, c.z, other);
-          const bool ok = __shfl_sync(mask, have, other) && ((mask >> other) & 1u);
-          T d = metric_init<T>(metric);
-          d = metric_fold(metric, d, q[0], cx, 0);
-          if (DIM > 1) d = metric_fold(metric, d, q[DIM > 1 ? 1 : 0], cy, 1);
-          if (DIM > 2) d = metric_fold(metric, d, q[DIM > 2 ? 2 : 0], cz, 2);
-          d = add_rn(d, mul_rn(d, sizeof(T) == 4 ? T(1.2207031e-4) : T(2.2737368e-13)));
-          if (ok && d < bound) bound = d;
-        }
-      }
     } else {
       // k consecutive stored points centred on the first leaf
       int s = lb - (k - (le - lb)) / 2;
@@ -361,8 +312,7 @@ __device__ __forceinline__ void traverse_packed(const typename NodeOf<T>::type* 
       T far = T(0);
       for (int i = s; i < s + k; ++i) {
         const typename Vec4Of<T>::type p = ldg4(pts4 + i);
-        T d = metric_init<T>(metric);
-        d = metric_fold(metric, d, q[0], p.x, 0);
+        T d = metric_first(metric, q[0], p.x);
         if (DIM > 1) d = metric_fold(metric, d, q[DIM > 1 ? 1 : 0], p.y, 1);
         if (DIM > 2) d = metric_fold(metric, d, q[DIM > 2 ? 2 : 0], p.z, 2);
         far = d > far ? d : far;
@@ -377,7 +327,7 @@ __device__ __forceinline__ void traverse_packed(const typename NodeOf<T>::type* 
   // max() of the visitor, capped by the primed bound
   auto reach = [&]() -> T {
     const T m = vis.max();
-    return ((PRIME == kPrimeBound || NB) && bound < m) ? bound : m;
+    return (PRIME == kPrimeBound && bound < m) ? bound : m;
   };
   for (;;) {
     // ---- descend to a leaf (kd_tree_search.hpp:60-88)
@@ -416,8 +366,7 @@ __device__ __forceinline__ void traverse_packed(const typename NodeOf<T>::type* 
     if (PRIME == kPrimeFirstLeaf && node == primed_leaf) le = lb;
     for (int i = lb; i < le; ++i) {
       const typename Vec4Of<T>::type p = ldg4(pts4 + i);
-      T d = metric_init<T>(metric);
-      d = metric_fold(metric, d, q[0], p.x, 0);
+      T d = metric_first(metric, q[0], p.x);
       if (DIM > 1) d = metric_fold(metric, d, q[DIM > 1 ? 1 : 0], p.y, 1);
       if (DIM > 2) d = metric_fold(metric, d, q[DIM > 2 ? 2 : 0], p.z, 2);
       if (approx) d = mul_rn(d, e_inv);
@@ -666,8 +615,7 @@ __device__ __forceinline__ void traverse_nn(const typename NodeOf<T>::type* __re
   const uint32_t primed_leaf = node;
   for (int i = lb; i < le; ++i) {
     const typename Vec4Of<T>::type p = ldg4(pts4 + i);
-    T d = T(0);
-    d = metric_fold(metric, d, q[0], p.x, 0);
+    T d = metric_first(metric, q[0], p.x);
     if (DIM > 1) d = metric_fold(metric, d, q[DIM > 1 ? 1 : 0], p.y, 1);
     if (DIM > 2) d = metric_fold(metric, d, q[DIM > 2 ? 2 : 0], p.z, 2);
     vis.visit(index_of(p), d);
@@ -718,8 +666,7 @@ __device__ __forceinline__ void traverse_nn(const typename NodeOf<T>::type* __re
     if (lb < le) {
       for (int i = lb; i < le; ++i) {
         const typename Vec4Of<T>::type p = ldg4(pts4 + i);
-        T d = T(0);
-        d = metric_fold(metric, d, q[0], p.x, 0);
+        T d = metric_first(metric, q[0], p.x);
         if (DIM > 1) d = metric_fold(metric, d, q[DIM > 1 ? 1 : 0], p.y, 1);
         if (DIM > 2) d = metric_fold(metric, d, q[DIM > 2 ? 2 : 0], p.z, 2);
         vis.visit(index_of(p), d);

@@ -6,6 +6,7 @@
 #include <pico_tree/array_traits.hpp>
 #include <pico_tree/kd_tree.hpp>
 #include <pico_tree/vector_traits.hpp>
+#include <pico_understory/kd_forest.hpp>
 
 #include <array>
 #include <cstdio>
@@ -479,6 +480,56 @@ TEST(KdTreeDropIn, CustomSpaceTraits) {
   pico_tree::kd_tree<std::reference_wrapper<scattered_space>> tree(s, pico_tree::max_leaf_size_t(4));
   test_knn(tree, 4);
   test_box(tree, 0.2f, 0.4f);
+}
+
+// ---------------------------------------------------------------- kd_forest (examples/pico_understory)
+// examples/kd_forest/kd_forest.cpp:20-41 drives the forest with search_nn per test point and counts how often the
+// exact neighbour is found; with an unbounded leaf budget every tree is searched exhaustively, so the answer must
+// be the exact one (distances are measured in the reflected spaces: equal up to rounding).
+TEST(KdForest, UnboundedBudgetIsExactAndBatchesEqualSingles) {
+  using point_8f = std::array<float, 8>;
+  auto pts = generate_random_n<point_8f>(20000, 1.0f);
+  auto queries = generate_random_n<point_8f>(300, 0.0f, 1.0f, 7);
+  pico_tree::kd_tree<space<point_8f>> tree(pts, pico_tree::max_leaf_size_t(10));
+  pico_tree::kd_forest<space<point_8f>> forest(pts, 10, 4);
+  EXPECT_EQ(forest.info().n_trees, 4u);
+  auto const rot = forest.rotations();
+  EXPECT_EQ(rot.size(), 4u * 8u);
+  for (std::size_t t = 0; t < 4; ++t) {
+    float s = 0;
+    for (std::size_t j = 0; j < 8; ++j) s += rot[t * 8 + j] * rot[t * 8 + j];
+    EXPECT_TRUE(std::abs(s - 1.0f) < 1e-4f);
+  }
+  std::vector<pico_tree::neighbor<int, float>> batch;
+  forest.search_nn_batch(queries, std::size_t(1) << 40, batch);
+  EXPECT_EQ(batch.size(), queries.size());
+  std::size_t found_small = 0;
+  for (std::size_t i = 0; i < queries.size(); ++i) {
+    pico_tree::neighbor<int, float> exact, nn, few;
+    tree.search_nn(queries[i], exact);
+    forest.search_nn(queries[i], std::size_t(1) << 40, nn);
+    EXPECT_EQ(nn.index, exact.index);
+    EXPECT_TRUE(std::abs(nn.distance - exact.distance) <= 1e-5f * (1.0f + exact.distance));
+    EXPECT_EQ(batch[i].index, nn.index);
+    float_eq(batch[i].distance, nn.distance);
+    forest.search_nn(queries[i], 8, few);
+    found_small += few.index == exact.index;
+  }
+  EXPECT_TRUE(found_small > queries.size() / 2);  // 4 trees x 8 leaves already find most neighbours in 8-D
+  // the same forest again from its own reflection vectors: reproducible
+  pico_tree::kd_forest<space<point_8f>> again(pts, 10, 4, rot);
+  std::vector<pico_tree::neighbor<int, float>> a, b;
+  forest.search_knn_batch(queries, 5, 16, a);
+  again.search_knn_batch(queries, 5, 16, b);
+  EXPECT_EQ(a.size(), b.size());
+  for (std::size_t i = 0; i < a.size(); ++i) {
+    EXPECT_EQ(a[i].index, b[i].index);
+    float_eq(a[i].distance, b[i].distance);
+  }
+  auto moved = pico_tree::make_kd_forest(std::ref(pts), 10, 2);
+  pico_tree::neighbor<int, float> nn;
+  moved.search_nn(queries[0], 4, nn);
+  EXPECT_TRUE(nn.index >= 0);
 }
 
 int main(int argc, char** argv) { return mini_test::run_all(argc, argv); }

@@ -731,3 +731,40 @@ def test_search_image_nn_with_ties(pt, oracle, dtype, sdim):
     want = oracle.OracleTree(pts, 10).search_knn(q, 1)
     got = t.search_knn(q, 1)
     assert np.array_equal(got["distance"], want["distance"]) and np.array_equal(got["index"], want["index"])
+
+
+NN_VARIANT = r'''
+import sys, numpy as np
+sys.path.insert(0, %(root)r); sys.path.insert(0, %(root)r + "/tests")
+import pico_tree_b200 as pt
+from oracle import oracle as O
+rng = np.random.default_rng(11)
+for dtype, sdim in ((np.float32, 3), (np.float32, 2), (np.float64, 3)):
+    pts = rng.integers(0, 24, size=(60_000, sdim)).astype(dtype)                      # lattice: ties everywhere
+    q = (rng.integers(0, 24, size=(40_000, sdim)) + rng.choice([0.0, 0.5], size=(40_000, sdim))).astype(dtype)
+    want = O.OracleTree(pts, 10).search_knn(q, 1)
+    got = pt.KdTree(pts, pt.Metric.L2Squared, 10).search_knn(q, 1)
+    assert np.array_equal(got["distance"], want["distance"]) and np.array_equal(got["index"], want["index"])
+    pts = rng.random((200_000, sdim)).astype(dtype)
+    q = (rng.random((100_000, sdim)) * 3 - 1).astype(dtype)                           # many far children pending
+    want = O.OracleTree(pts, 4).search_knn(q, 1)
+    got = pt.KdTree(pts, pt.Metric.L2Squared, 4).search_knn(q, 1)
+    assert np.array_equal(got["distance"], want["distance"]) and np.array_equal(got["index"], want["index"])
+print("NN_VARIANT_OK")
+'''
+
+
+@pytest.mark.parametrize("env", [{"PICO_B200_NN": "1"}, {"PICO_B200_NN": "5"},
+                                 {"PICO_B200_NN": "1", "PICO_B200_FAT_LEAF": "16"},
+                                 {"PICO_B200_NN": "3", "PICO_B200_FAT_LEAF": "32"}],
+                         ids=["slot_stack", "slot_stack_no_restart", "search_image_16", "search_image_32_far_fat"])
+def test_nn_kernel_variants(env):
+    """The selectable k = 1 kernels (PICO_B200_NN / PICO_B200_FAT_LEAF tuning hooks, read once per process): shared
+    slot stack with restore records, prefix-minimum restart, search image with tie re-run. Same answers as the
+    oracle, ties included."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", NN_VARIANT % {"root": root}], capture_output=True, text=True,
+                       env=dict(os.environ, **env), timeout=600)
+    assert r.returncode == 0 and "NN_VARIANT_OK" in r.stdout, r.stdout[-1000:] + r.stderr[-3000:]
