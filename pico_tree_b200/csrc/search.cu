@@ -39,18 +39,23 @@ __device__ __forceinline__ uint32_t spread10(uint32_t v) {
   return v;
 }
 
+// The cell of a coordinate is computed in the tree's scalar type with one multiply-add per coordinate
+// (the order only has to be the same for every query of a batch; it never decides a result).
 template <typename T>
-__global__ void morton_kernel(const T* __restrict__ q, size_t stride, uint32_t nq, int dims, double3 lo, double3 inv,
-                              uint32_t* __restrict__ codes, uint32_t* __restrict__ ids) {
+__global__ void morton_kernel(const T* __restrict__ q, size_t stride, uint32_t nq, int dims, T lo0, T lo1, T lo2,
+                              T inv0, T inv1, T inv2, uint32_t* __restrict__ codes, uint32_t* __restrict__ ids) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nq) return;
   const T* p = q + (size_t)i * stride;
-  const double l[3] = {lo.x, lo.y, lo.z}, s[3] = {inv.x, inv.y, inv.z};
+  const T l[3] = {lo0, lo1, lo2}, s[3] = {inv0, inv1, inv2};
   uint32_t code = 0;
-  for (int j = 0; j < dims; ++j) {
-    double f = ((double)p[j] - l[j]) * s[j];
-    f = f < 0.0 ? 0.0 : (f > 1023.0 ? 1023.0 : f);
-    code |= spread10((uint32_t)f) << j;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    if (j < dims) {
+      T f = (p[j] - l[j]) * s[j];
+      f = f < T(0) ? T(0) : (f > T(1023) ? T(1023) : f);  // (a NaN coordinate converts to cell 0)
+      code |= spread10((uint32_t)f) << j;
+    }
   }
   codes[i] = code;
   ids[i] = i;
@@ -440,6 +445,31 @@ struct StreamCache {
 };
 thread_local StreamCache g_stream_cache;
 
+// One high-priority stream per host thread and device: the host pipeline orders its chunks there. The ordering
+// step of a chunk is a chain of small kernels (Morton codes, radix-sort passes); at normal priority each of
+// them queues behind the thousands of pending blocks of the previous chunks' traversal kernels and the chain
+// takes 0.4 ms instead of 0.05 ms (profiles/r1/host_pipeline_sweep.txt: order 1.83 -> 2.27 ms for the last
+// chunk). With priority its blocks are placed as soon as any block slot frees up.
+struct PriorityStream {
+  int device = -1;
+  cudaStream_t st = nullptr;
+};
+thread_local PriorityStream g_hp_stream;
+int priority_stream(int device, cudaStream_t* st) {
+  if (g_hp_stream.st && g_hp_stream.device == device) {
+    *st = g_hp_stream.st;
+    return 0;
+  }
+  int least = 0, greatest = 0;
+  PICO_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+  cudaStream_t s = nullptr;
+  PICO_CUDA(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, greatest));
+  g_hp_stream.device = device;  // (a stream of another device is leaked: a host thread rarely switches devices)
+  g_hp_stream.st = s;
+  *st = s;
+  return 0;
+}
+
 struct CallCtx {
   cudaStream_t st = nullptr;
   bool owns_stream = true;
@@ -704,38 +734,56 @@ int morton_bits(bool single_neighbour) {
   return forced ? forced : (single_neighbour ? kMortonBitsNn : kMortonBits);
 }
 
-// Z-order permutation of the batch (device). Returns nullptr in *perm for tiny batches.
+// Z-order permutation of a batch (device). Workspace: three key / value scratch arrays + CUB's temporary storage
+// (`scratch`) and the array that receives the permutation (`perm_out`, nq entries).
+struct PermPlan {
+  size_t arr = 0, tmp_bytes = 0;
+  size_t scratch_bytes() const { return 3 * arr + tmp_bytes; }
+};
+inline int plan_perm(size_t nq, int bits, PermPlan* plan) {
+  size_t tmp_bytes = 0;
+  PICO_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr,
+                                            (uint32_t*)nullptr, (int)nq, 30 - bits, 30, (cudaStream_t) nullptr));
+  plan->arr = (nq * 4 + 255) & ~(size_t)255;
+  plan->tmp_bytes = tmp_bytes;
+  return 0;
+}
+template <typename T>
+int enqueue_perm(cudaStream_t st, const pico_b200_tree* t, const T* d_q, size_t stride, size_t nq, int bits,
+                 const PermPlan& plan, char* scratch, uint32_t* perm_out) {
+  const int dims = (int)std::min<size_t>(t->sdim, 3);
+  T lo[3] = {0, 0, 0}, inv[3] = {0, 0, 0};
+  for (int j = 0; j < dims; ++j) {
+    lo[j] = (T)t->root_box_host[j];
+    const double ext = t->root_box_host[4 + j] - t->root_box_host[j];
+    inv[j] = ext > 0 ? (T)(1023.999 / ext) : T(0);
+  }
+  uint32_t* codes = reinterpret_cast<uint32_t*>(scratch);
+  uint32_t* ids = reinterpret_cast<uint32_t*>(scratch + plan.arr);
+  uint32_t* codes2 = reinterpret_cast<uint32_t*>(scratch + 2 * plan.arr);
+  void* tmp = scratch + 3 * plan.arr;
+  size_t tmp_bytes = plan.tmp_bytes;
+  morton_kernel<T><<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(d_q, stride, (uint32_t)nq, dims, lo[0], lo[1], lo[2],
+                                                                 inv[0], inv[1], inv[2], codes, ids);
+  PICO_CUDA(cudaGetLastError());
+  PICO_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, codes, codes2, ids, perm_out, (int)nq, 30 - bits, 30, st));
+  return 0;
+}
+
+// Returns nullptr in *perm for tiny batches.
 template <typename T>
 int make_perm(CallCtx& c, const pico_b200_tree* t, const T* d_q, size_t stride, size_t nq, unsigned flags,
               uint32_t** perm, bool single_neighbour = false) {
   const int bits = morton_bits(single_neighbour);
   *perm = nullptr;
   if ((flags & PICO_B200_NO_REORDER) || nq < 2048) return 0;
-  const int dims = (int)std::min<size_t>(t->sdim, 3);
-  double lo[3] = {0, 0, 0}, inv[3] = {0, 0, 0};
-  for (int j = 0; j < dims; ++j) {
-    lo[j] = t->root_box_host[j];
-    const double ext = t->root_box_host[4 + j] - t->root_box_host[j];
-    inv[j] = ext > 0 ? 1023.999 / ext : 0.0;
-  }
-  // one workspace: 4 key / value arrays + CUB's temporary storage
-  size_t tmp_bytes = 0;
-  PICO_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr,
-                                            (uint32_t*)nullptr, (int)nq, 30 - bits, 30, c.st));
-  const size_t arr = (nq * 4 + 255) & ~(size_t)255;
+  PermPlan plan;
+  PICO_TRY(plan_perm(nq, bits, &plan));
   char* ws = nullptr;
-  PICO_TRY(c.alloc(reinterpret_cast<void**>(&ws), 4 * arr + tmp_bytes));
-  uint32_t* codes = reinterpret_cast<uint32_t*>(ws);
-  uint32_t* ids = reinterpret_cast<uint32_t*>(ws + arr);
-  uint32_t* codes2 = reinterpret_cast<uint32_t*>(ws + 2 * arr);
-  uint32_t* ids2 = reinterpret_cast<uint32_t*>(ws + 3 * arr);
-  void* tmp = ws + 4 * arr;
-  morton_kernel<T><<<(unsigned)((nq + 255) / 256), 256, 0, c.st>>>(d_q, stride, (uint32_t)nq, dims,
-                                                                    make_double3(lo[0], lo[1], lo[2]),
-                                                                    make_double3(inv[0], inv[1], inv[2]), codes, ids);
-  PICO_CUDA(cudaGetLastError());
-  PICO_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, codes, codes2, ids, ids2, (int)nq, 30 - bits, 30, c.st));
-  *perm = ids2;
+  PICO_TRY(c.alloc(reinterpret_cast<void**>(&ws), plan.scratch_bytes() + plan.arr));
+  uint32_t* out = reinterpret_cast<uint32_t*>(ws + plan.scratch_bytes());
+  PICO_TRY(enqueue_perm<T>(c.st, t, d_q, stride, nq, bits, plan, ws, out));
+  *perm = out;
   return 0;
 }
 
@@ -915,9 +963,11 @@ float elapsed(cudaEvent_t a, cudaEvent_t b) {
 }
 
 // Enqueues one knn batch on c.st: stage queries (host pointers), Z-order, traverse, copy back.
+// `perm_in` (with have_perm): the batch was ordered elsewhere (host pipeline: on a high-priority stream).
 template <typename T>
 int knn_enqueue(CallCtx& c, const pico_b200_tree* t, const T* q, size_t nq, size_t stride, size_t k, double e,
-                Neighbor<T>* out, unsigned flags, bool on_device, uint64_t* launches) {
+                Neighbor<T>* out, unsigned flags, bool on_device, uint64_t* launches,
+                const uint32_t* perm_in = nullptr, bool have_perm = false) {
   PICO_TRY(c.mark(0));
   const T* d_q = nullptr;
   size_t d_stride = 0;
@@ -925,8 +975,8 @@ int knn_enqueue(CallCtx& c, const pico_b200_tree* t, const T* q, size_t nq, size
   Neighbor<T>* d_out = out;
   if (!on_device) PICO_TRY(c.alloc(reinterpret_cast<void**>(&d_out), nq * k * sizeof(Neighbor<T>)));
   PICO_TRY(c.mark(1));
-  uint32_t* perm = nullptr;
-  PICO_TRY(make_perm(c, t, d_q, d_stride, nq, flags, &perm, k == 1));
+  uint32_t* perm = const_cast<uint32_t*>(perm_in);
+  if (!have_perm) PICO_TRY(make_perm(c, t, d_q, d_stride, nq, flags, &perm, k == 1));
   PICO_TRY(c.mark(2));
   PICO_TRY(c.span_begin());
 
@@ -1086,6 +1136,14 @@ int host_ahead() {
   }();
   return v;
 }
+// Order the chunks on a high-priority stream (PICO_B200_HOST_PRIO=0 keeps the ordering on the chunk's own stream).
+bool host_priority_order() {
+  static const bool v = [] {
+    const char* e = getenv("PICO_B200_HOST_PRIO");
+    return !(e && atoi(e) == 0);
+  }();
+  return v;
+}
 constexpr size_t kHostHead = 262144;
 size_t host_head() {
   static const size_t v = [] {
@@ -1183,13 +1241,30 @@ int knn_batch(const pico_b200_tree* t, const T* q, size_t nq, size_t stride, siz
         (stage_in || stage_out || touch_out || batch_bytes > kAheadBudget) ? 0 : (size_t)host_ahead();
     T* d_q_all = nullptr;
     Neighbor<T>* d_out_all = nullptr;
-    std::vector<cudaEvent_t> ready(ahead ? n_chunks : 0);
+    std::vector<cudaEvent_t> ready(ahead ? n_chunks : 0), ordered(ahead ? n_chunks : 0);
+    // ordering of every chunk on the high-priority stream: one scratch area (the chunks are ordered one after
+    // the other there) and one permutation array for the whole batch
+    cudaStream_t hp = nullptr;
+    PermPlan perm_plan;
+    char* perm_scratch = nullptr;
+    uint32_t* perm_all = nullptr;
+    const int perm_bits = morton_bits(k == 1);
+    const bool hp_order = ahead && host_priority_order() && !(flags & PICO_B200_NO_REORDER);
     if (ahead) {
       PICO_TRY(cp.init(t->device));
       cp.timed = false;
       PICO_TRY(cp.alloc(reinterpret_cast<void**>(&d_q_all), nq * sdim * sizeof(T)));
       PICO_TRY(cp.alloc(reinterpret_cast<void**>(&d_out_all), nq * k * sizeof(Neighbor<T>)));
       for (auto& ev : ready) PICO_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      for (auto& ev : ordered) PICO_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      if (hp_order) {
+        size_t biggest = 0;
+        for (auto& pc : plan) biggest = std::max(biggest, pc.second);
+        PICO_TRY(priority_stream(t->device, &hp));
+        PICO_TRY(plan_perm(biggest, perm_bits, &perm_plan));
+        PICO_TRY(cp.alloc(reinterpret_cast<void**>(&perm_scratch), perm_plan.scratch_bytes()));
+        PICO_TRY(cp.alloc(reinterpret_cast<void**>(&perm_all), nq * sizeof(uint32_t)));
+      }
     }
     size_t uploaded = 0;  // chunks whose H2D has been issued
     auto upload_until = [&](size_t last) -> int {
@@ -1248,11 +1323,19 @@ int knn_batch(const pico_b200_tree* t, const T* q, size_t nq, size_t stride, siz
       cpu_at[2 * ci] = cpu_ms();
       if (ahead) {
         rc = upload_until(ci + ahead - 1);
-        if (!rc && cudaStreamWaitEvent(c.st, ready[ci], 0) != cudaSuccess)
+        const bool order_here = hp_order && cnt >= 2048;
+        if (!rc && order_here) {
+          if (cudaStreamWaitEvent(hp, ready[ci], 0) != cudaSuccess) rc = fail(PICO_B200_ERR_CUDA, "stream wait failed");
+          if (!rc)
+            rc = enqueue_perm<T>(hp, t, d_q_all + begin * sdim, sdim, cnt, perm_bits, perm_plan, perm_scratch,
+                                 perm_all + begin);
+          if (!rc && cudaEventRecord(ordered[ci], hp) != cudaSuccess) rc = fail(PICO_B200_ERR_CUDA, "event record failed");
+        }
+        if (!rc && cudaStreamWaitEvent(c.st, order_here ? ordered[ci] : ready[ci], 0) != cudaSuccess)
           rc = fail(PICO_B200_ERR_CUDA, "stream wait failed");
         if (!rc)
           rc = knn_enqueue<T>(c, t, d_q_all + begin * sdim, cnt, sdim, k, e, d_out_all + begin * k, flags, true,
-                              &launches);
+                              &launches, order_here ? perm_all + begin : nullptr, order_here);
         if (!rc && cudaMemcpyAsync(dst + begin * k, d_out_all + begin * k, cnt * k * sizeof(Neighbor<T>),
                                    cudaMemcpyDeviceToHost, c.st) != cudaSuccess)
           rc = fail(PICO_B200_ERR_CUDA, "result copy failed");
@@ -1276,8 +1359,11 @@ int knn_batch(const pico_b200_tree* t, const T* q, size_t nq, size_t stride, siz
     for (auto& ev : done) cudaEventDestroy(ev);
     if (rc || drain_failed.load())  // quiesce before the events the streams wait on go away
       for (int i = 0; i < n_streams; ++i) cudaStreamSynchronize(ctx[i].st);
-    if (rc || drain_failed.load())
+    if (rc || drain_failed.load()) {
+      if (hp) cudaStreamSynchronize(hp);
       for (auto& ev : ready) cudaEventDestroy(ev);
+      for (auto& ev : ordered) cudaEventDestroy(ev);
+    }
     if (!rc && drain_failed.load()) rc = fail(PICO_B200_ERR_CUDA, "copying results out of the pinned mirror failed");
     if (rc) {
       cudaEventDestroy(e0);
@@ -1286,6 +1372,7 @@ int knn_batch(const pico_b200_tree* t, const T* q, size_t nq, size_t stride, siz
     }
     for (int i = 0; i < n_streams; ++i) PICO_CUDA(cudaStreamSynchronize(ctx[i].st));
     for (auto& ev : ready) cudaEventDestroy(ev);
+    for (auto& ev : ordered) cudaEventDestroy(ev);
     PICO_CUDA(cudaEventRecord(e1, ctx[0].st));
     PICO_CUDA(cudaEventSynchronize(e1));
     if (timeline) {

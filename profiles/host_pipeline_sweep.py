@@ -74,20 +74,24 @@ if __name__ == "__main__":
     tree_pts, q = D.bench_clouds()
     np.savez(CACHE, tree=tree_pts, q=q)
     print(run(FLOOR), flush=True)
-    points = [
-        {},
-        {"ORDER": "radix", "MORTON_BITS": 16},
-        {"ORDER": "radix", "MORTON_BITS": 24},
-        {"HOST_AHEAD": 99},
-        {"HOST_AHEAD": 99, "HOST_HEAD": 262144},
-        {"HOST_AHEAD": 99, "HOST_HEAD": 262144, "HOST_STREAMS": 4},
-        {"HOST_AHEAD": 99, "HOST_HEAD": 262144, "MORTON_BITS": 18},
-        {"HOST_AHEAD": 99, "HOST_HEAD": 262144, "MORTON_BITS": 14},
-        {"HOST_AHEAD": 99, "HOST_HEAD": 262144, "HOST_CHUNK": 1572864},
-        {"HOST_AHEAD": 2, "HOST_HEAD": 262144},
-    ]
+    if len(sys.argv) > 1:   # python profiles/host_pipeline_sweep.py KEY=VAL,KEY=VAL ...   ("-" = library defaults)
+        points = [dict(kv.split("=") for kv in p.split(",") if kv and kv != "-") for p in sys.argv[1:]]
+    else:
+        points = [
+            {},
+            {"HOST_PRIO": 0},
+            {"HOST_TAPER": 131072},
+            {"HOST_TAPER": 262144},
+            {"HOST_CHUNK": 786432},
+            {"HOST_CHUNK": 524288},
+            {"HOST_CHUNK": 524288, "HOST_STREAMS": 8},
+            {"HOST_CHUNK": 1572864, "HOST_TAPER": 262144},
+            {"HOST_STREAMS": 4},
+            {"HOST_STREAMS": 8},
+            {"HOST_HEAD": 131072},
+        ]
     for env in points:
         print("%-95s %s" % (" ".join("%s=%s" % kv for kv in env.items()) or "(library defaults)", run(ONE, **env)),
               flush=True)
-    for env in ({"HOST_AHEAD": 99, "HOST_STREAMS": 8},):
+    for env in ({"HOST_STREAMS": 8}, {"HOST_STREAMS": 8, "HOST_PRIO": 0}):
         print("timeline %s\n%s" % (env, run(ONE, TIMELINE=1, **env)[-1500:]), flush=True)
