@@ -780,9 +780,10 @@ int make_perm(CallCtx& c, const pico_b200_tree* t, const T* d_q, size_t stride, 
   PermPlan plan;
   PICO_TRY(plan_perm(nq, bits, &plan));
   char* ws = nullptr;
-  PICO_TRY(c.alloc(reinterpret_cast<void**>(&ws), plan.scratch_bytes() + plan.arr));
-  uint32_t* out = reinterpret_cast<uint32_t*>(ws + plan.scratch_bytes());
-  PICO_TRY(enqueue_perm<T>(c.st, t, d_q, stride, nq, bits, plan, ws, out));
+  // (the permutation first: CUB's temporary storage at the end of the scratch area has no particular size)
+  PICO_TRY(c.alloc(reinterpret_cast<void**>(&ws), plan.arr + plan.scratch_bytes()));
+  uint32_t* out = reinterpret_cast<uint32_t*>(ws);
+  PICO_TRY(enqueue_perm<T>(c.st, t, d_q, stride, nq, bits, plan, ws + plan.arr, out));
   *perm = out;
   return 0;
 }
