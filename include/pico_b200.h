@@ -55,7 +55,14 @@ typedef enum {
   PICO_B200_METRIC_LNINF = 3,      /* metric_lninf       metric.hpp:153-180 */
   /* topological spaces (search_nearest_topological, internal/kd_tree_search.hpp:122-229): */
   PICO_B200_METRIC_SO2 = 4,        /* metric_so2         metric.hpp:197-221, sdim 1: S1 = [0,1)      */
-  PICO_B200_METRIC_SE2_SQUARED = 5 /* metric_se2_squared metric.hpp:223-257, sdim 3: R2 x S1         */
+  PICO_B200_METRIC_SE2_SQUARED = 5,/* metric_se2_squared metric.hpp:223-257, sdim 3: R2 x S1         */
+  /* A user-defined Metric_ (kd_tree.hpp:19-36 accepts any type; examples/kd_tree/kd_tree_custom_metric.cpp): the
+   * tree is built, exported, saved and loaded here — the topological flavour keeps all four bounds per node —
+   * but knn / radius need the caller's functor and are answered by the host header
+   * (include/pico_tree_b200/host_search.hpp); pico_b200_knn / pico_b200_radius return PICO_B200_ERR_UNSUPPORTED.
+   * pico_b200_box works for the euclidean flavour (a box test needs no metric). */
+  PICO_B200_METRIC_CUSTOM_TOPOLOGICAL = 6,
+  PICO_B200_METRIC_CUSTOM_EUCLIDEAN = 7
 } pico_b200_metric;
 
 /* internal/kd_tree_builder.hpp:35-75 */

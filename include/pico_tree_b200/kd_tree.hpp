@@ -5,8 +5,11 @@
 // space(), metric(), load / save, deduction guide and make_kd_tree. Where the reference runs
 // internal::build_kd_tree and the internal::search_* recursions on the calling thread, this class
 // makes ONE call into the C-ABI of include/pico_b200.h; the tree lives in HBM as a flat array of
-// nodes next to leaf-ordered points. The header holds no distance arithmetic and no tree walk,
-// and there is no CPU fallback: without a B200 every call throws std::runtime_error.
+// nodes next to leaf-ordered points. There is no CPU fallback: without a B200 every call throws
+// std::runtime_error, and every search goes to the device — except where the CALLER'S OWN CODE has to run
+// inside the search (a user-defined Metric_, a user-defined visitor passed to search_nearest) or where the
+// caller opted in with b200::single_query_on_host(true): those walk a host mirror of the device-built tree
+// (host_search.hpp).
 //
 // Additions the reference does not have (its Python binding loops over single queries,
 // src/pyco_tree/pico_tree/_pyco_tree/kd_tree.hpp:117-268): search_nn_batch, search_knn_batch,
@@ -50,6 +53,8 @@
 #else
 #include "traits.hpp"
 #endif
+
+#include "host_search.hpp"
 
 namespace pico_tree {
 
@@ -105,6 +110,18 @@ template <>
 struct metric_id<metric_so2> : std::integral_constant<int, PICO_B200_METRIC_SO2> {};
 template <>
 struct metric_id<metric_se2_squared> : std::integral_constant<int, PICO_B200_METRIC_SE2_SQUARED> {};
+
+// metric id handed to pico_b200_tree_create: a user-defined metric builds the same tree (splits only look at
+// coordinates); its category decides whether the nodes keep two bounds or four
+template <typename Metric_>
+constexpr int build_metric_id() {
+  if constexpr (metric_id<Metric_>::value >= 0)
+    return metric_id<Metric_>::value;
+  else if constexpr (std::is_same_v<typename Metric_::space_category, euclidean_space_tag>)
+    return PICO_B200_METRIC_CUSTOM_EUCLIDEAN;
+  else
+    return PICO_B200_METRIC_CUSTOM_TOPOLOGICAL;
+}
 
 template <typename Rule_>
 struct rule_id;
@@ -212,9 +229,9 @@ struct lib_buffer {
 template <typename Space_, typename Metric_ = metric_l2_squared, typename Index_ = int>
 class kd_tree {
   static_assert(std::is_same_v<std::remove_cv_t<Space_>, Space_>, "SPACE_TYPE_MUST_BE_NON-CONST_NON-VOLATILE");
-  static_assert(b200::metric_id<Metric_>::value >= 0,
-                "METRIC_HAS_NO_DEVICE_IMPLEMENTATION: libpico_b200 implements metric_l1, metric_l2_squared, "
-                "metric_lpinf, metric_lninf, metric_so2 and metric_se2_squared");
+  // metric_l1, metric_l2_squared, metric_lpinf, metric_lninf, metric_so2 and metric_se2_squared are searched on the
+  // device; any other Metric_ is the caller's code and is searched over the host mirror (host_search.hpp)
+  static constexpr bool device_metric = b200::metric_id<Metric_>::value >= 0;
   static_assert(std::is_integral_v<Index_>, "INDEX_NOT_AN_INTEGRAL_TYPE");
 
   using unwrapped_space = b200::unwrap_t<Space_>;
@@ -265,7 +282,7 @@ class kd_tree {
     }
     pico_b200_tree* h = nullptr;
     b200::check(pico_b200_tree_create(rows.data(), rows.size(), rows.sdim(), rows.stride(),
-                                      b200::scalar_id<scalar_type>::value, b200::metric_id<Metric_>::value,
+                                      b200::scalar_id<scalar_type>::value, b200::build_metric_id<Metric_>(),
                                       b200::rule_id<Rule_>::value, stop.first, stop.second, bmin, bmax,
                                       b200::default_device(), &h));
     handle_.reset(h);
@@ -279,30 +296,21 @@ class kd_tree {
   kd_tree& operator=(kd_tree&&) = default;
 
   // ---------------------------------------------------------------- single query
-  // Hands the neighbours of x to `visitor` in ascending order of distance until one lies
-  // beyond visitor.max(). The reference calls the visitor for every point of every leaf its
-  // depth-first search reaches (kd_tree.hpp:106-120, internal/kd_tree_search.hpp:52-105); a
-  // visitor therefore cannot tell which far points it will see, only that every point closer
-  // than its final max() was offered — which the ordered stream guarantees too, with max()
-  // only ever shrinking. The stream is produced by exact device knn calls with a growing k.
+  // The visitor is the caller's code: it is called for every point of every leaf the depth-first search reaches,
+  // in the reference's order (kd_tree.hpp:106-120, internal/kd_tree_search.hpp:52-105 / :122-229), over the host
+  // mirror of the device-built tree.
   template <typename P_, typename V_>
   void search_nearest(P_ const& x, V_& visitor) const {
-    scalar_type const* q = query_data(x);
-    size_type fed = 0;
-    std::vector<neighbor_type> buf;
-    for (size_type k = std::min<size_type>(n_, 32);; k = std::min(n_, k * 4)) {
-      buf.resize(k);
-      knn_call(q, 1, sdim_, k, 0.0, buf.data());
-      for (; fed < k; ++fed) {
-        if (buf[fed].distance > visitor.max()) return;
-        visitor(buf[fed].index, buf[fed].distance);
-      }
-      if (k == n_) return;
-    }
+    host_walk(query_data(x), visitor);
   }
 
   template <typename P_>
   void search_nn(P_ const& x, neighbor_type& nn) const {
+    if (on_host()) {
+      b200::visit_nn<neighbor_type> v(nn);
+      host_walk(query_data(x), v);
+      return;
+    }
     knn_call(query_data(x), 1, sdim_, 1, 0.0, &nn);
   }
 
@@ -310,6 +318,12 @@ class kd_tree {
   // distance is scaled by 1/e like the reference's (search_visitor.hpp:178-183).
   template <typename P_>
   void search_nn(P_ const& x, scalar_type const e, neighbor_type& nn) const {
+    if (on_host()) {
+      b200::visit_nn<neighbor_type> v(nn);
+      b200::visit_scaled<b200::visit_nn<neighbor_type>> a(e, v);
+      host_walk(query_data(x), a);
+      return;
+    }
     knn_call(query_data(x), 1, sdim_, 1, static_cast<double>(e), &nn);
   }
 
@@ -321,6 +335,10 @@ class kd_tree {
   template <typename P_>
   void search_knn(P_ const& x, size_type const k, std::vector<neighbor_type>& knn) const {
     knn.resize(std::min(k, n_));  // fewer points than k: all of them (kd_tree.hpp:190-195)
+    if (on_host()) {
+      host_knn(query_data(x), 0.0, knn.begin(), knn.end());
+      return;
+    }
     knn_call(query_data(x), 1, sdim_, knn.size(), 0.0, knn.data());
   }
 
@@ -332,6 +350,10 @@ class kd_tree {
   template <typename P_>
   void search_knn(P_ const& x, size_type const k, scalar_type const e, std::vector<neighbor_type>& knn) const {
     knn.resize(std::min(k, n_));
+    if (on_host()) {
+      host_knn(query_data(x), static_cast<double>(e), knn.begin(), knn.end());
+      return;
+    }
     knn_call(query_data(x), 1, sdim_, knn.size(), static_cast<double>(e), knn.data());
   }
 
@@ -384,13 +406,13 @@ class kd_tree {
     b200::rows_of<Queries_> rows(unwrap_queries(queries));
     check_queries(rows);
     if (k <= n_) {
-      knn_call(rows.data(), rows.size(), rows.stride(), k, static_cast<double>(e), out);
+      knn_rows(rows.data(), rows.size(), rows.stride(), k, static_cast<double>(e), out);
       return;
     }
     // rows of k slots but only n points: like the iterator overloads, the tail of every row keeps an
     // infinite distance (search_visitor.hpp:98-103)
     std::vector<neighbor_type> tmp(rows.size() * n_);
-    knn_call(rows.data(), rows.size(), rows.stride(), n_, static_cast<double>(e), tmp.data());
+    knn_rows(rows.data(), rows.size(), rows.stride(), n_, static_cast<double>(e), tmp.data());
     for (size_type i = 0; i < rows.size(); ++i) {
       neighbor_type* row = std::copy_n(tmp.data() + i * n_, n_, out + i * k);
       std::fill(row, out + (i + 1) * k, neighbor_type(index_type(0), std::numeric_limits<scalar_type>::max()));
@@ -404,6 +426,17 @@ class kd_tree {
                            scalar_type const e = scalar_type(0)) const {
     b200::rows_of<Queries_> rows(unwrap_queries(queries));
     check_queries(rows);
+    if constexpr (!device_metric) {
+      offsets.assign(1, 0);
+      flat.clear();
+      std::vector<neighbor_type> one;
+      for (size_type i = 0; i < rows.size(); ++i) {
+        radius_one(rows.data() + i * rows.stride(), radius, static_cast<double>(e), one, sort);
+        flat.insert(flat.end(), one.begin(), one.end());
+        offsets.push_back(flat.size());
+      }
+      return;
+    }
     std::vector<std::uint64_t> offs(rows.size() + 1, 0);
     b200::lib_buffer out;
     b200::check(pico_b200_radius(handle_.get(), rows.data(), rows.size(), rows.stride(), static_cast<double>(radius),
@@ -534,7 +567,8 @@ class kd_tree {
 
  private:
   struct host_mirror {
-    std::vector<index_type> indices;
+    b200::host_tree<scalar_type> tree;  // flat nodes, permutation, outer bounds (host_search.hpp)
+    std::vector<index_type> indices;    // the permutation as index_type (leaf_ranges)
     std::vector<std::pair<std::ptrdiff_t, std::ptrdiff_t>> leaves;
   };
   struct lazy_mirror {
@@ -547,7 +581,7 @@ class kd_tree {
     rows_type rows(unwrapped());
     pico_b200_tree* h = nullptr;
     b200::check(pico_b200_tree_load(rows.data(), rows.size(), rows.sdim(), rows.stride(),
-                                    b200::scalar_id<scalar_type>::value, b200::metric_id<Metric_>::value, bytes, size,
+                                    b200::scalar_id<scalar_type>::value, b200::build_metric_id<Metric_>(), bytes, size,
                                     b200::default_device(), &h, consumed));
     handle_.reset(h);
     n_ = rows.size();
@@ -631,6 +665,10 @@ class kd_tree {
   void knn_range(P_ const& x, double e, It_ begin, It_ end) const {
     static_assert(std::is_same_v<typename std::iterator_traits<It_>::value_type, neighbor_type>,
                   "ITERATOR_VALUE_TYPE_DOES_NOT_EQUAL_NEIGHBOR_TYPE");
+    if (on_host()) {
+      host_knn(query_data(x), e, begin, end);
+      return;
+    }
     size_type const k = static_cast<size_type>(std::distance(begin, end));
     size_type const kk = std::min(k, n_);
     std::vector<neighbor_type> tmp(kk);
@@ -647,10 +685,38 @@ class kd_tree {
     check_queries(rows);
     k = std::min(k, n_);
     knn.resize(rows.size() * k);
-    knn_call(rows.data(), rows.size(), rows.stride(), k, e, knn.data());
+    knn_rows(rows.data(), rows.size(), rows.stride(), k, e, knn.data());
+  }
+
+  // rows of queries -> rows of k neighbours: one device call, or (user-defined metric) the host descent per row
+  void knn_rows(scalar_type const* q, size_type nq, size_type stride, size_type k, double e, neighbor_type* out) const {
+    if constexpr (device_metric) {
+      knn_call(q, nq, stride, k, e, out);
+    } else {
+      mirror();  // fetch once, outside the parallel loop
+      std::ptrdiff_t const n = static_cast<std::ptrdiff_t>(nq);
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 128)
+#endif
+      for (std::ptrdiff_t i = 0; i < n; ++i)
+        host_knn(q + static_cast<size_type>(i) * stride, e, out + static_cast<size_type>(i) * k,
+                 out + (static_cast<size_type>(i) + 1) * k);
+    }
   }
 
   void radius_one(scalar_type const* q, scalar_type radius, double e, std::vector<neighbor_type>& n, bool sort) const {
+    if (on_host()) {
+      // search_approximate_radius compares against radius / e as well (search_visitor.hpp:261-267)
+      b200::visit_radius<neighbor_type> v(e > 0 ? radius * (scalar_type(1.0) / static_cast<scalar_type>(e)) : radius, n);
+      if (e > 0) {
+        b200::visit_scaled<b200::visit_radius<neighbor_type>> a(static_cast<scalar_type>(e), v);
+        host_walk(q, a);
+      } else {
+        host_walk(q, v);
+      }
+      if (sort) v.sort();
+      return;
+    }
     std::uint64_t offsets[2] = {0, 0};
     b200::lib_buffer out;
     b200::check(pico_b200_radius(handle_.get(), q, 1, sdim_, static_cast<double>(radius), e, offsets, &out.p,
@@ -662,26 +728,54 @@ class kd_tree {
   host_mirror const& mirror() const {
     std::call_once(mirror_->once, [this] {
       pico_b200_tree_info const i = info();
-      std::vector<std::int32_t> idx(i.n_points);
       host_mirror& m = mirror_->data;
-      auto collect = [&](auto const& nodes) {
-        for (auto const& nd : nodes)
-          if (nd.split_dim == PICO_B200_LEAF && nd.b.end_idx > nd.a.begin_idx)
-            m.leaves.emplace_back(static_cast<std::ptrdiff_t>(nd.a.begin_idx),
-                                  static_cast<std::ptrdiff_t>(nd.b.end_idx));
-      };
-      if constexpr (sizeof(scalar_type) == 4) {
-        std::vector<pico_b200_node_f32> nodes(i.n_nodes);
-        b200::check(pico_b200_tree_export(handle_.get(), nodes.data(), idx.data(), nullptr));
-        collect(nodes);  // pre-order == depth-first order
-      } else {
-        std::vector<pico_b200_node_f64> nodes(i.n_nodes);
-        b200::check(pico_b200_tree_export(handle_.get(), nodes.data(), idx.data(), nullptr));
-        collect(nodes);
+      m.tree.nodes.resize(i.n_nodes);
+      m.tree.indices.resize(i.n_points);
+      m.tree.root_box.resize(2 * sdim_);
+      b200::check(pico_b200_tree_export(handle_.get(), m.tree.nodes.data(), m.tree.indices.data(),
+                                        m.tree.root_box.data()));
+      if constexpr (!std::is_same_v<typename Metric_::space_category, euclidean_space_tag>) {
+        m.tree.outer.resize(2 * i.n_nodes);
+        b200::check(pico_b200_tree_export_outer_bounds(handle_.get(), m.tree.outer.data()));
       }
-      m.indices.assign(idx.begin(), idx.end());
+      for (auto const& nd : m.tree.nodes)  // pre-order == depth-first order
+        if (nd.split_dim == PICO_B200_LEAF && nd.b.end_idx > nd.a.begin_idx)
+          m.leaves.emplace_back(static_cast<std::ptrdiff_t>(nd.a.begin_idx), static_cast<std::ptrdiff_t>(nd.b.end_idx));
+      m.indices.assign(m.tree.indices.begin(), m.tree.indices.end());
     });
     return mirror_->data;
+  }
+
+  // ---- host descent (host_search.hpp): user-defined metric / visitor, or single queries on request
+  static bool on_host() {
+    if constexpr (device_metric)
+      return b200::single_query_on_host_flag();
+    else
+      return true;
+  }
+
+  template <typename V_>
+  void host_walk(scalar_type const* q, V_& visitor) const {
+    host_mirror const& m = mirror();
+    unwrapped_space const& s = unwrapped();
+    auto point_of = [&s](size_type i) {
+      return b200::point_traits_of<typename traits::point_type>::data(traits::point_at(s, i));
+    };
+    b200::host_descent<scalar_type, Metric_, decltype(point_of), V_>(m.tree, metric_, point_of, q, sdim_, visitor)();
+  }
+
+  template <typename It_>
+  void host_knn(scalar_type const* q, double e, It_ begin, It_ end) const {
+    static_assert(std::is_same_v<typename std::iterator_traits<It_>::value_type, neighbor_type>,
+                  "ITERATOR_VALUE_TYPE_DOES_NOT_EQUAL_NEIGHBOR_TYPE");
+    if (begin == end) return;
+    b200::visit_knn<It_> v(begin, end);
+    if (e > 0) {
+      b200::visit_scaled<b200::visit_knn<It_>> a(static_cast<scalar_type>(e), v);
+      host_walk(q, a);
+    } else {
+      host_walk(q, v);
+    }
   }
 
   space_type space_;

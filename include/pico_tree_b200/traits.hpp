@@ -212,6 +212,33 @@ struct space_traits<space_map<Point_>> {
 class topological_space_tag {};
 class euclidean_space_tag : public topological_space_tag {};
 
+// One-dimensional spaces a metric reports per dimension through apply_dim_space (distance.hpp:5-7 of the
+// reference), and the distance helpers user-defined metrics are written with (distance.hpp:17-48).
+class one_space_r1 {};
+class one_space_s1 {};
+
+template <typename Scalar_>
+constexpr Scalar_ r1_distance(Scalar_ x, Scalar_ y) {
+  return x > y ? x - y : y - x;
+}
+template <typename Scalar_>
+constexpr Scalar_ s1_distance(Scalar_ x, Scalar_ y) {
+  Scalar_ const d = r1_distance(x, y);
+  return d < Scalar_(1.0) - d ? d : Scalar_(1.0) - d;
+}
+template <typename Scalar_>
+constexpr Scalar_ squared(Scalar_ x) {
+  return x * x;
+}
+template <typename Scalar_>
+constexpr Scalar_ squared_r1_distance(Scalar_ x, Scalar_ y) {
+  return squared(x - y);
+}
+template <typename Scalar_>
+constexpr Scalar_ squared_s1_distance(Scalar_ x, Scalar_ y) {
+  return squared(s1_distance(x, y));
+}
+
 namespace b200_detail {
 
 template <typename It1_, typename End1_, typename It2_, typename Term_, typename Fold_, typename Scalar_>
@@ -301,6 +328,10 @@ struct metric_so2 {
   constexpr Scalar_ operator()(Scalar_ x) const {
     return x < Scalar_(0) ? -x : x;
   }
+  template <typename UnaryPredicate_>
+  void apply_dim_space(int, UnaryPredicate_ p) const {
+    p(one_space_s1{});
+  }
 };
 
 // R2 x S1: squared euclidean distance on (x, y) plus squared circle distance on the angle
@@ -317,6 +348,13 @@ struct metric_se2_squared {
   template <typename Scalar_>
   constexpr Scalar_ operator()(Scalar_ x) const {
     return x * x;
+  }
+  template <typename UnaryPredicate_>
+  void apply_dim_space(int dim, UnaryPredicate_ p) const {
+    if (dim < 2)
+      p(one_space_r1{});
+    else
+      p(one_space_s1{});
   }
 };
 

@@ -56,7 +56,7 @@ int check_common(const void* pts, size_t n, size_t sdim, size_t stride, int scal
   if (stride < sdim) return fail(PICO_B200_ERR_INVALID_ARGUMENT, "stride smaller than sdim");
   if (scalar != PICO_B200_F32 && scalar != PICO_B200_F64)
     return fail(PICO_B200_ERR_INVALID_ARGUMENT, "unknown scalar type");
-  if (metric < PICO_B200_METRIC_L1 || metric > PICO_B200_METRIC_SE2_SQUARED)
+  if (metric < PICO_B200_METRIC_L1 || metric > PICO_B200_METRIC_CUSTOM_EUCLIDEAN)
     return fail(PICO_B200_ERR_INVALID_ARGUMENT, "unknown metric");
   // metric_so2 reads coordinate 0, metric_se2_squared coordinates 0..2 (metric.hpp:203-208,229-238)
   if (metric == PICO_B200_METRIC_SO2 && sdim != 1)
@@ -232,6 +232,8 @@ int pico_b200_knn(const pico_b200_tree* t, const void* queries, size_t nq, size_
   if (nq == 0 || k == 0) return 0;
   if (!queries || !neighbors_out) return fail(PICO_B200_ERR_INVALID_ARGUMENT, "null query or output pointer");
   if (stride < t->sdim) return fail(PICO_B200_ERR_INVALID_ARGUMENT, "stride smaller than sdim");
+  if (t->custom_metric())
+    return fail(PICO_B200_ERR_UNSUPPORTED, "user-defined metric: nearest searches run in the host header, not here");
   if (t->scalar == PICO_B200_F32)
     return knn_batch<float>(t, static_cast<const float*>(queries), nq, stride, k, e,
                             static_cast<Neighbor<float>*>(neighbors_out), flags, stats);
@@ -245,6 +247,8 @@ int pico_b200_radius(const pico_b200_tree* t, const void* queries, size_t nq, si
   if (stats) memset(stats, 0, sizeof(*stats));
   if (nq && !queries) return fail(PICO_B200_ERR_INVALID_ARGUMENT, "null query pointer");
   if (stride < t->sdim) return fail(PICO_B200_ERR_INVALID_ARGUMENT, "stride smaller than sdim");
+  if (t->custom_metric())
+    return fail(PICO_B200_ERR_UNSUPPORTED, "user-defined metric: nearest searches run in the host header, not here");
   if (t->scalar == PICO_B200_F32)
     return radius_batch<float>(t, static_cast<const float*>(queries), nq, stride, radius, e, offsets_out,
                                neighbors_out, flags, stats);
@@ -258,6 +262,8 @@ int pico_b200_box(const pico_b200_tree* t, const void* mins, const void* maxs, s
   if (stats) memset(stats, 0, sizeof(*stats));
   if (nb && (!mins || !maxs)) return fail(PICO_B200_ERR_INVALID_ARGUMENT, "null box pointer");
   if (stride < t->sdim) return fail(PICO_B200_ERR_INVALID_ARGUMENT, "stride smaller than sdim");
+  if (t->metric == PICO_B200_METRIC_CUSTOM_TOPOLOGICAL)
+    return fail(PICO_B200_ERR_UNSUPPORTED, "user-defined topological metric: which dimensions wrap is only known to the caller");
   if (t->scalar == PICO_B200_F32)
     return box_batch<float>(t, static_cast<const float*>(mins), static_cast<const float*>(maxs), nb, stride,
                             offsets_out, indices_out, flags, stats);
@@ -576,7 +582,7 @@ int pico_b200_tree_load(const void* pts, size_t n, size_t sdim, size_t stride, i
   *out = nullptr;
   if (!stream) return fail(PICO_B200_ERR_INVALID_ARGUMENT, "stream is null");
   PICO_TRY(check_common(pts, n, sdim, stride, scalar, metric));
-  const bool topo = metric >= PICO_B200_METRIC_SO2;
+  const bool topo = metric >= PICO_B200_METRIC_SO2 && metric <= PICO_B200_METRIC_CUSTOM_TOPOLOGICAL;
   std::vector<int32_t> idx;
   if (scalar == PICO_B200_F32) {
     std::vector<float> box, outer;

@@ -110,7 +110,8 @@ struct pico_b200_tree {
   size_t node_size() const { return scalar == PICO_B200_F64 ? 32 : 16; }
   bool packed() const { return sdim <= (size_t)pico::kMaxPackedDim; }
   bool keep_outer = false;     // trees of a kd_forest: euclidean metric, but the priority search needs all four bounds
-  bool topological() const { return metric >= PICO_B200_METRIC_SO2; }
+  bool topological() const { return metric >= PICO_B200_METRIC_SO2 && metric <= PICO_B200_METRIC_CUSTOM_TOPOLOGICAL; }
+  bool custom_metric() const { return metric >= PICO_B200_METRIC_CUSTOM_TOPOLOGICAL; }
   size_t outer_bytes() const { return (topological() || keep_outer) ? n_nodes * 2 * scalar_size() : 0; }
   size_t spans_bytes() const { return packed() ? 0 : n_nodes * sizeof(uint2); }
   size_t pts_bytes() const { return packed() ? n * 4 * scalar_size() : n * sdim * scalar_size(); }

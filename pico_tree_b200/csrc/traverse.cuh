@@ -66,7 +66,9 @@ __device__ __forceinline__ T metric1(int metric, T x) {
   return (metric == PICO_B200_METRIC_L2_SQUARED || metric == PICO_B200_METRIC_SE2_SQUARED) ? mul_rn(x, x) : abs_t(x);
 }
 
-__device__ __forceinline__ bool is_topological(int metric) { return metric >= PICO_B200_METRIC_SO2; }
+__device__ __forceinline__ bool is_topological(int metric) {
+  return metric >= PICO_B200_METRIC_SO2 && metric <= PICO_B200_METRIC_CUSTOM_TOPOLOGICAL;
+}
 
 // s1_distance, distance.hpp:19-22: d = |x - y|; std::min(d, 1 - d)
 template <typename T>
