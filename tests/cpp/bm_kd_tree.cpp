@@ -85,7 +85,29 @@ int main(int argc, char** argv) {
                 static_cast<double>(nq) / s / 1e6, static_cast<double>(hits.size()) / static_cast<double>(nq));
   }
 
-  // the reference's loop shape: one call per query (each a one-query device batch)
+  // the reference's loop shape (bm_pico_kd_tree.cpp:63-78: one search_knn per point, the result vector resized
+  // per query), answered from the host mirror of the device-built tree: b200::single_query_on_host(true)
+  {
+    pico_tree::b200::single_query_on_host(true);
+    std::size_t const nq = std::min<std::size_t>(n_query, 1000000);
+    std::vector<neighbor_type> results;
+    std::size_t sum = 0;
+    tree.search_knn(points_test[0], 1, results);  // fetches the mirror (once per tree)
+    for (std::size_t k : {1, 4, 8, 12}) {
+      t0 = std::chrono::steady_clock::now();
+      for (std::size_t i = 0; i < nq; ++i) {
+        tree.search_knn(points_test[i], k, results);
+        sum += results.size();
+      }
+      double const s = seconds_since(t0);
+      std::printf("knn k=%-2zu single-query loop on the host mirror over %zu queries: %.3f us per call, %.2f Mq/s (1 thread)\n",
+                  k, nq, s / nq * 1e6, static_cast<double>(nq) / s / 1e6);
+    }
+    pico_tree::b200::single_query_on_host(false);
+    if (sum == 0) std::printf("?\n");
+  }
+
+  // the same loop with every call going to the device (the default): each a one-query device batch
   {
     std::size_t const nq = std::min<std::size_t>(n_query, 20000);
     std::vector<neighbor_type> results;

@@ -9,6 +9,7 @@
 #include <pico_understory/kd_forest.hpp>
 
 #include <array>
+#include <cmath>
 #include <cstdio>
 #include <numeric>
 #include <random>
@@ -399,7 +400,147 @@ TEST(KdTreeDropIn, CustomVisitor) {
   std::vector<pico_tree::neighbor<int, float>> rad;
   tree.search_radius(q, 0.01f, rad);
   EXPECT_EQ(w.hits.size(), rad.size());
-  EXPECT_GE(w.hits.size(), 100u);  // several rounds of the growing-k stream
+  EXPECT_GE(w.hits.size(), 100u);
+  // the visitor sees the points in the reference's visit order: exactly the unsorted search_radius sequence
+  for (std::size_t i = 0; i < rad.size() && i < w.hits.size(); ++i) EXPECT_EQ(w.hits[i], rad[i].index);
+}
+
+// ---------------------------------------------------------------- user-defined metrics (host_search.hpp)
+// examples/kd_tree/kd_tree_custom_metric.cpp of the reference: the L_p^p metric (euclidean) and the squared distance
+// on the torus S1 x S1 (topological). The tree is built on the device, the searches call the user's functors.
+namespace {
+template <std::size_t P_>
+struct metric_lp_p {
+  using space_category = pico_tree::euclidean_space_tag;
+  template <typename It_>
+  auto operator()(It_ b1, It_ e1, It_ b2) const {
+    using scalar = typename std::iterator_traits<It_>::value_type;
+    scalar d{};
+    for (; b1 != e1; ++b1, ++b2) d += operator()(*b1 - *b2);
+    return d;
+  }
+  template <typename S_>
+  S_ operator()(S_ x) const {
+    return std::pow(std::abs(x), static_cast<S_>(P_));
+  }
+};
+
+struct metric_t2_squared {
+  using space_category = pico_tree::topological_space_tag;
+  template <typename It_>
+  auto operator()(It_ b1, It_ e1, It_ b2) const {
+    using scalar = typename std::iterator_traits<It_>::value_type;
+    scalar d{};
+    for (; b1 != e1; ++b1, ++b2) d += pico_tree::squared_s1_distance(*b1, *b2);
+    return d;
+  }
+  template <typename S_>
+  S_ operator()(S_ x) const {
+    return x * x;
+  }
+  template <typename P_>
+  void apply_dim_space(int, P_ p) const {
+    p(pico_tree::one_space_s1{});
+  }
+};
+
+template <typename Tree_, typename Metric_>
+std::vector<typename Tree_::neighbor_type> brute_metric(Tree_ const& tree, Metric_ const& m, float const* q,
+                                                         std::size_t k) {
+  space_view<Tree_> sv(tree);
+  std::vector<typename Tree_::neighbor_type> all;
+  for (std::size_t i = 0; i < sv.size(); ++i)
+    all.emplace_back(static_cast<int>(i), m(q, q + sv.sdim(), sv[i]));
+  std::stable_sort(all.begin(), all.end(), [](auto const& a, auto const& b) { return a.distance < b.distance; });
+  all.resize(std::min(k, all.size()));
+  return all;
+}
+}  // namespace
+
+TEST(KdTreeDropIn, UserDefinedEuclideanMetric) {
+  std::vector<point_2f> pts = generate_random_n<point_2f>(50000, 10.0f);
+  pico_tree::kd_tree<space<point_2f>, metric_lp_p<3>> tree(pts, pico_tree::max_leaf_size_t(12));
+  auto queries = generate_random_n<point_2f>(200, -1.0f, 11.0f, 5);
+  for (auto const& q : queries) {
+    pico_tree::neighbor<int, float> nn;
+    tree.search_nn(q, nn);
+    auto want = brute_metric(tree, tree.metric(), q.data(), 6);
+    EXPECT_EQ(nn.index, want[0].index);
+    EXPECT_EQ(nn.distance, want[0].distance);
+    std::vector<pico_tree::neighbor<int, float>> knn;
+    tree.search_knn(q, 6, knn);
+    EXPECT_EQ(knn.size(), 6u);
+    for (std::size_t i = 0; i < knn.size(); ++i) EXPECT_EQ(knn[i].distance, want[i].distance);
+    std::vector<pico_tree::neighbor<int, float>> rad;
+    tree.search_radius(q, want[5].distance, rad, true);  // strictly inside the 6th distance
+    EXPECT_TRUE(rad.size() <= 5u);
+  }
+  // batches loop over the host descent; box search needs no metric and runs on the device
+  std::vector<pico_tree::neighbor<int, float>> flat;
+  tree.search_knn_batch(queries, 3, flat);
+  EXPECT_EQ(flat.size(), queries.size() * 3);
+  for (std::size_t i = 0; i < queries.size(); ++i) {
+    auto want = brute_metric(tree, tree.metric(), queries[i].data(), 3);
+    for (std::size_t j = 0; j < 3; ++j) EXPECT_EQ(flat[i * 3 + j].distance, want[j].distance);
+  }
+  test_box(tree, 2.0f, 4.0f);
+  // save / load keeps working (the stream does not depend on the metric)
+  std::stringstream ss;
+  pico_tree::kd_tree<space<point_2f>, metric_lp_p<3>>::save(tree, ss);
+  auto loaded = pico_tree::kd_tree<space<point_2f>, metric_lp_p<3>>::load(pts, ss);
+  pico_tree::neighbor<int, float> a, b;
+  tree.search_nn(queries[0], a);
+  loaded.search_nn(queries[0], b);
+  EXPECT_EQ(a.index, b.index);
+}
+
+TEST(KdTreeDropIn, UserDefinedTopologicalMetric) {
+  std::vector<point_2f> pts = generate_random_n<point_2f>(30000, 1.0f);
+  pico_tree::kd_tree<space<point_2f>, metric_t2_squared> tree(pts, pico_tree::max_leaf_size_t(12));
+  auto queries = generate_random_n<point_2f>(200, 0.0f, 1.0f, 6);
+  queries.push_back({1.0f, 1.0f});  // the corner: neighbours wrap around in both dimensions
+  queries.push_back({0.0f, 0.5f});
+  for (auto const& q : queries) {
+    std::array<pico_tree::neighbor<int, float>, 8> knn;
+    tree.search_knn(q, knn.begin(), knn.end());
+    auto want = brute_metric(tree, tree.metric(), q.data(), 8);
+    for (std::size_t i = 0; i < 8; ++i) EXPECT_EQ(knn[i].distance, want[i].distance);
+  }
+}
+
+// One query at a time on the host mirror when the caller asks for it: same tree, same arithmetic order, so the
+// answers are the device's bit for bit (ties included).
+TEST(KdTreeDropIn, SingleQueriesOnHostWhenAskedFor) {
+  std::vector<point_3f> pts = generate_random_n<point_3f>(80000, 1.0f);
+  for (auto& p : pts) p[2] = std::round(p[2] * 16.0f) / 16.0f;  // planes: plenty of equal distances
+  kd_tree<point_3f> tree(pts, pico_tree::max_leaf_size_t(10));
+  auto queries = generate_random_n<point_3f>(500, -0.2f, 1.2f, 11);
+  using neighbor_type = kd_tree<point_3f>::neighbor_type;
+  std::vector<neighbor_type> dev_knn, host_knn, dev_aknn, host_aknn, dev_rad, host_rad;
+  for (auto const& q : queries) {
+    neighbor_type dev_nn, host_nn;
+    pico_tree::b200::single_query_on_host(false);
+    tree.search_nn(q, dev_nn);
+    tree.search_knn(q, 7, dev_knn);
+    tree.search_knn(q, 7, 1.5f, dev_aknn);
+    tree.search_radius(q, 0.002f, dev_rad);
+    pico_tree::b200::single_query_on_host(true);
+    tree.search_nn(q, host_nn);
+    tree.search_knn(q, 7, host_knn);
+    tree.search_knn(q, 7, 1.5f, host_aknn);
+    tree.search_radius(q, 0.002f, host_rad);
+    pico_tree::b200::single_query_on_host(false);
+    EXPECT_EQ(dev_nn.index, host_nn.index);
+    EXPECT_EQ(dev_nn.distance, host_nn.distance);
+    EXPECT_EQ(dev_rad.size(), host_rad.size());
+    for (std::size_t i = 0; i < 7; ++i) {
+      EXPECT_EQ(dev_knn[i].index, host_knn[i].index);
+      EXPECT_EQ(dev_knn[i].distance, host_knn[i].distance);
+      EXPECT_EQ(dev_aknn[i].index, host_aknn[i].index);
+      EXPECT_EQ(dev_aknn[i].distance, host_aknn[i].distance);
+    }
+    for (std::size_t i = 0; i < dev_rad.size() && i < host_rad.size(); ++i) EXPECT_EQ(dev_rad[i].index, host_rad[i].index);
+  }
 }
 
 TEST(KdTreeDropIn, BatchesEqualSingles) {
