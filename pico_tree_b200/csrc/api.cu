@@ -91,6 +91,47 @@ constexpr uint64_t kMagic = 0x3030324a4f434950ull;
 
 size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
+// Structure check of an uploaded image (pico_b200_tree_deserialize, the receiving side of a broadcast): every
+// branch links forward inside the array (pre-order: left = i + 1 < right < n_nodes), split dimensions exist, leaf
+// ranges lie inside [0, n] and are ordered, indices are point numbers. flags[0] counts violations.
+template <typename NodeT>
+__global__ void validate_nodes_kernel(const NodeT* nodes, uint32_t n_nodes, uint32_t n, uint32_t sdim, uint32_t* bad) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_nodes) return;
+  const NodeT nd = nodes[i];
+  bool ok;
+  if (nd.split_dim == PICO_B200_LEAF) {
+    const long long b = (long long)nd.a.begin_idx, e = (long long)nd.b.end_idx;
+    ok = nd.right == PICO_B200_LEAF && b >= 0 && b <= e && e <= (long long)n;
+  } else {
+    ok = nd.split_dim < sdim && nd.right > i + 1 && nd.right < n_nodes && i + 1 < n_nodes;
+  }
+  if (!ok) atomicAdd(bad, 1u);
+}
+__global__ void validate_indices_kernel(const int32_t* indices, uint32_t n, uint32_t* bad) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && (indices[i] < 0 || (uint32_t)indices[i] >= n)) atomicAdd(bad, 1u);
+}
+int validate_structure(const pico_b200_tree* t) {
+  uint32_t* d_bad = nullptr;
+  PICO_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_bad), sizeof(uint32_t)));
+  cudaMemset(d_bad, 0, sizeof(uint32_t));
+  const unsigned nb = (unsigned)((t->n_nodes + 255) / 256);
+  if (t->scalar == PICO_B200_F32)
+    validate_nodes_kernel<<<nb, 256>>>(static_cast<const pico_b200_node_f32*>(t->d_nodes), (uint32_t)t->n_nodes,
+                                       (uint32_t)t->n, (uint32_t)t->sdim, d_bad);
+  else
+    validate_nodes_kernel<<<nb, 256>>>(static_cast<const pico_b200_node_f64*>(t->d_nodes), (uint32_t)t->n_nodes,
+                                       (uint32_t)t->n, (uint32_t)t->sdim, d_bad);
+  validate_indices_kernel<<<(unsigned)((t->n + 255) / 256), 256>>>(t->d_indices, (uint32_t)t->n, d_bad);
+  uint32_t bad = 0;
+  const cudaError_t e = cudaMemcpy(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost);
+  cudaFree(d_bad);
+  if (e != cudaSuccess) return fail(PICO_B200_ERR_CUDA, std::string("tree image validation: ") + cudaGetErrorString(e));
+  if (bad) return fail(PICO_B200_ERR_INVALID_ARGUMENT, "tree image: corrupt node links, leaf ranges or indices");
+  return 0;
+}
+
 size_t image_bytes(const pico_b200_tree* t) {
   return align16(sizeof(ImageHeader)) + align16(2 * t->sdim * t->scalar_size()) + align16(t->n_nodes * t->node_size()) +
          align16(t->n * 4) + align16(t->pts_bytes()) + align16(t->outer_bytes()) + align16(t->spans_bytes());
@@ -348,6 +389,13 @@ int pico_b200_tree_deserialize(const void* src, uint64_t bytes, int src_is_devic
   PICO_CUDA(cudaMemcpy(&h, src, sizeof(h), src_is_device ? cudaMemcpyDeviceToHost : cudaMemcpyHostToHost));
   if (h.magic != kMagic || h.version != PICO_B200_ABI_VERSION)
     return fail(PICO_B200_ERR_INVALID_ARGUMENT, "not a pico_b200 tree image (magic/version mismatch)");
+  // the header is data from outside: the same range checks as pico_b200_tree_create, plus the shape of a binary tree
+  if ((h.scalar != PICO_B200_F32 && h.scalar != PICO_B200_F64) || h.metric > (uint32_t)PICO_B200_METRIC_CUSTOM_EUCLIDEAN ||
+      h.sdim == 0 || h.sdim > 0x7fff || h.n == 0 || h.n >= 0x7fffffffull ||
+      (h.metric == PICO_B200_METRIC_SO2 && h.sdim != 1) || (h.metric == PICO_B200_METRIC_SE2_SQUARED && h.sdim != 3))
+    return fail(PICO_B200_ERR_INVALID_ARGUMENT, "tree image: header fields out of range");
+  if (h.n_nodes == 0 || h.n_nodes != 2 * h.n_leaves - 1 || h.n_nodes > 2 * h.n + 1 || h.height >= h.n_nodes + 1)
+    return fail(PICO_B200_ERR_INVALID_ARGUMENT, "tree image: node / leaf counts are not those of a binary tree");
   pico_b200_tree* t = new (std::nothrow) pico_b200_tree();
   if (!t) return fail(PICO_B200_ERR_OUT_OF_MEMORY, "host allocation failed");
   t->device = device;
@@ -387,6 +435,12 @@ int pico_b200_tree_deserialize(const void* src, uint64_t bytes, int src_is_devic
   t->device_bytes =
       t->pts_bytes() + t->n_nodes * t->node_size() + t->n * 4 + 2 * t->sdim * t->scalar_size() + t->outer_bytes() +
       t->spans_bytes();
+  // links, leaf ranges, split dimensions and indices are checked on the device before any search may follow them
+  rc = validate_structure(t);
+  if (rc) {
+    release(t);
+    return rc;
+  }
   rc = build_fat_nodes(t, nullptr);
   if (rc) {
     release(t);

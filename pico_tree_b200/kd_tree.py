@@ -118,10 +118,12 @@ class DArray:
         return (self._view(i) for i in range(len(self)))
 
     def _assign(self, offsets, flat):
-        """Take new results, re-using the flat buffer when it is large enough (the reference
-        re-uses its vectors' storage, kd_tree_test.py:107-118)."""
+        """Take new results. A fresh DArray adopts the library's buffer without a copy (results can be gigabytes).
+        A DArray the caller passed in again is a request to re-use its memory, like the reference re-uses its
+        vectors' storage (test/pyco_tree/kd_tree_test.py:107-118 compares addresses): the results are copied
+        into the old buffer when they fit."""
         self._items = None
-        if self._flat is not None and self._flat.dtype == flat.dtype and self._flat.size >= flat.size:
+        if self._flat is not None and self._flat.size and self._flat.dtype == flat.dtype and self._flat.size >= flat.size:
             self._flat[:flat.size] = flat
         else:
             self._flat = flat
@@ -354,14 +356,20 @@ class KdTree:
         order = "C" if row_major else "F"
         if nns is None:
             nns = np.empty(shape, dtype=self.dtype_neighbor, order=order)
+            out = nns if row_major else nns.T
         else:
+            # ensure_size of the reference binding (_pyco_tree/kd_tree.hpp:362-378): the array is only resized when
+            # its SIZE differs (to (npts,) for k == 1, else (npts, k) / (k, npts)); otherwise its memory is filled
+            # as it is, npts rows of k records one after the other, whatever its shape
             if nns.dtype != self.dtype_neighbor:
                 raise ValueError("array dtype not neighbor")
-            if nns.shape != shape or not nns.flags["C_CONTIGUOUS" if row_major else "F_CONTIGUOUS"]:
-                nns.resize(shape, refcheck=False)
-                if not row_major:
-                    nns = np.asfortranarray(nns)
-        out = nns if row_major else nns.T
+            if nns.size != nq * k:
+                nns.resize((nq,) if k == 1 else shape, refcheck=False)
+            if not (nns.flags["C_CONTIGUOUS"] or nns.flags["F_CONTIGUOUS"]):
+                raise ValueError("array not contiguous")
+            out = nns.ravel(order="K")  # a view of the dense buffer, in memory order
+            if not np.shares_memory(out, nns):
+                raise ValueError("array not contiguous")
         stats = _lib.SearchStats()
         _lib.check(_lib.lib().pico_b200_knn(self._h, _ptr(view), nq, self.sdim, k, float(e or 0.0), _ptr(out),
                                             self._flags(**kw), C.byref(stats)))

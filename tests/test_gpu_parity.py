@@ -768,3 +768,41 @@ def test_nn_kernel_variants(env):
     r = subprocess.run([sys.executable, "-c", NN_VARIANT % {"root": root}], capture_output=True, text=True,
                        env=dict(os.environ, **env), timeout=600)
     assert r.returncode == 0 and "NN_VARIANT_OK" in r.stdout, r.stdout[-1000:] + r.stderr[-3000:]
+
+
+def test_tree_image_round_trip_and_validation(pt):
+    """pico_b200_tree_serialize / _deserialize (what a replica receives): the copy answers like the original, and
+    an image with a damaged header, node link, leaf range or index is refused instead of being searched."""
+    import ctypes as C
+    from pico_tree_b200 import _lib, datasets as D
+    L = _lib.lib()
+    pts = D.lidar_shape(80_000, seed=1)
+    q = D.lidar_shape(20_000, seed=2, pose_shift=0.35)
+    t = pt.KdTree(pts, pt.Metric.L2Squared, 10)
+    image = t.serialize()
+    want = t.search_knn(q, 4)
+
+    def load(buf):
+        h = C.c_void_p()
+        rc = L.pico_b200_tree_deserialize(C.c_void_p(buf.ctypes.data), buf.size, 0, 0, C.byref(h))
+        return rc, h
+
+    rc, h = load(image)
+    assert rc == 0
+    got = np.empty_like(want)
+    _lib.check(L.pico_b200_knn(h, C.c_void_p(q.ctypes.data), len(q), 3, 4, 0.0, C.c_void_p(got.ctypes.data), 0, None))
+    assert np.array_equal(got["index"], want["index"]) and np.array_equal(got["distance"], want["distance"])
+    L.pico_b200_tree_destroy(h)
+    info = t.info()
+    header = 128  # ImageHeader padded to 16 bytes: magic, 4 x u32, 5 x u64, 8 doubles = 128 bytes
+    nodes_at = header + 32  # root box: 6 floats padded to 32 bytes
+    for what, off, value in (("scalar", 12, 7), ("metric", 16, 99), ("sdim", 32, 0), ("n_nodes", 40, 4),
+                             ("right link of the root", nodes_at + 8, 0),
+                             ("split_dim of the root", nodes_at + 12, 9),
+                             ("an index", nodes_at + ((info["n_nodes"] * 16 + 15) // 16) * 16 + 4 * 100, -5)):
+        bad = image.copy()
+        bad[off:off + 4] = np.frombuffer(np.int32(value).tobytes(), np.uint8)
+        rc, h = load(bad)
+        assert rc != 0 and not h.value, what
+    rc, h = load(image[:len(image) // 2].copy())
+    assert rc != 0
