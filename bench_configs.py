@@ -7,6 +7,9 @@
   box           (a11)       search_box, 1M boxes of 0.4 m edge centred on cfg2 queries
   cfg4_exact    configs[3]  sift-shape 1M x 128, 10k queries, knn=10, runtime-dim path
   cfg4_approx   configs[3]  the same with e = 2.25 (search_approximate_knn)
+  cfg4_forest   (f4)        kd_forest on the same data: 8 and 16 trees, max_leaf_size 32, 64 leaves per tree — the
+                            settings of the reference's examples/kd_forest/kd_forest.cpp:113-123 for SIFT — recall
+                            against the exact neighbour, q/s, and bit parity with the oracle's forest on a reduced set
 
 Every entry: `value` (device-resident, CUDA events or the device-pointer call), `e2e` (public host API, host
 buffers), `parity` against the unmodified reference (oracle/_ref; the oracle port where that is absent) — index
@@ -249,6 +252,56 @@ def box_config(ctx, tree, tree_pts, q, ref, kind, nb=1_000_000, half=0.2, sample
                               "(index read + write); kernel_ms = count + scan + fill of the host-buffer call")}
 
 
+def forest_config(ctx, pts, q, exact_index, n_trees, max_leaf_size=32, max_leaves=64, reduced=100_000):
+    """kd_forest search_nn over all queries; recall = share of queries whose exact neighbour is found."""
+    torch, O, pt = ctx["torch"], ctx["oracle"], ctx["pt"]
+    rng = np.random.default_rng(17)
+    rot = rng.normal(size=(n_trees, pts.shape[1]))
+    rot = (rot / np.linalg.norm(rot, axis=1, keepdims=True)).astype(pts.dtype)
+    t0 = time.perf_counter()
+    f = pt.KdForest(pts, max_leaf_size, n_trees, rotations=rot)
+    build_wall = time.perf_counter() - t0
+    f.search_nn(q[:256], max_leaves)
+    best = None
+    for _ in range(3):
+        t0 = time.perf_counter()
+        got = f.search_nn(q, max_leaves)
+        dt = time.perf_counter() - t0
+        if best is None or dt < best:
+            best, kernel_ms = dt, f.last_stats.kernel_ms
+    recall = float(np.mean(got["index"][:, 0] == exact_index))
+    info = f.info()
+    line = {"config": "kd_forest (f4) on configs[3] data: %d trees, max_leaf_size %d, %d leaves per tree, search_nn"
+                      % (n_trees, max_leaf_size, max_leaves),
+            "value": len(q) / best, "unit": "q/s", "ms_per_step": best * 1e3, "kernel_ms": kernel_ms, "steps": 3,
+            "n_tree": int(len(pts)), "sdim": int(pts.shape[1]), "n_query": int(len(q)), "recall_vs_exact_nn": recall,
+            "reference_precision_note": "examples/kd_forest/kd_forest.cpp:118-121 quotes ~0.884 (8 trees) / ~0.940 "
+                                        "(16 trees) on real SIFT with these settings; this is synthetic sift-shape data",
+            "build_ms_device": info["build_ms"], "build_wall_s": build_wall, "forest_device_bytes": info["device_bytes"],
+            "e2e": {"value": len(q) / best, "unit": "q/s", "ms_per_step": best * 1e3, "h2d_bytes_per_step": int(q.nbytes),
+                    "d2h_bytes_per_step": int(len(q) * 8), "note": "the timed call takes host arrays"}}
+    del f
+    # bit parity + CPU baseline on a reduced set (a CPU forest over 1M x 128 takes minutes to build)
+    rp, rq = np.ascontiguousarray(pts[:reduced]), np.ascontiguousarray(q[:512])
+    nt = min(n_trees, 4)
+    fr = pt.KdForest(rp, max_leaf_size, nt, rotations=rot[:nt])
+    t0 = time.perf_counter()
+    of = O.OracleForest(rp, rot[:nt], max_leaf_size)
+    cpu_build = time.perf_counter() - t0
+    threads = O.max_threads()
+    t0 = time.perf_counter()
+    want = of.search_knn(rq, 1, max_leaves, threads=threads)
+    cpu_s = time.perf_counter() - t0
+    gotr = fr.search_nn(rq, max_leaves)
+    line["parity"] = {"reduced_n_tree": int(reduced), "trees": nt, "queries": int(len(rq)),
+                      "indices_equal": bool(np.array_equal(gotr["index"], want["index"])),
+                      "distances_bit_equal": bool(np.array_equal(gotr["distance"], want["distance"]))}
+    line["cpu_baseline"] = {"value": len(rq) / cpu_s, "unit": "q/s", "cores": threads, "kind": "port",
+                            "sample": "oracle forest of %d trees over the first %d points (built in %.1f s on one "
+                                      "thread), %d queries" % (nt, reduced, cpu_build, len(rq))}
+    return line
+
+
 def run_all(ctx, tree, tree_pts, q, only=None):
     """ctx: {"torch", "lib" (pico_tree_b200._lib), "oracle" (oracle.oracle), "pt" (pico_tree_b200), "peak", "peak_kind"}.
     `tree` / `tree_pts` / `q` are the headline's cfg2 objects (reused: one build, one reference tree)."""
@@ -264,10 +317,10 @@ def run_all(ctx, tree, tree_pts, q, only=None):
         return cache[key]
     ctx = dict(ctx, oracle_tree=oracle_tree)
     out = {}
-    want = only or ["cfg1", "cfg3_knn16", "cfg3_radius", "box", "cfg4_exact", "cfg4_approx"]
+    want = only or ["cfg1", "cfg3_knn16", "cfg3_radius", "box", "cfg4_exact", "cfg4_approx", "cfg4_forest"]
 
     def guarded(key, fn):
-        if key not in want:
+        if key not in want and not (key.startswith("cfg4_forest") and "cfg4_forest" in want):
             return
         t0 = time.perf_counter()
         try:
@@ -297,6 +350,11 @@ def run_all(ctx, tree, tree_pts, q, only=None):
         guarded("cfg3_radius", lambda: radius_config(ctx, tree, tree_pts, q, ref, kind))
         guarded("box", lambda: box_config(ctx, tree, tree_pts, q, ref, kind))
         del ref
+    if "cfg4_forest" in want:
+        p4, q4 = D.sift_shape(1_000_000, seed=1), D.sift_shape(10_000, seed=2)
+        exact = pt.KdTree(p4, pt.Metric.L2Squared, 10).search_knn(q4, 1)["index"][:, 0]
+        for nt in (8, 16):
+            guarded("cfg4_forest_%d" % nt, lambda nt=nt: forest_config(ctx, p4, q4, exact, nt))
     if "cfg4_exact" in want or "cfg4_approx" in want:
         p4, q4 = D.sift_shape(1_000_000, seed=1), D.sift_shape(10_000, seed=2)
         t0 = time.perf_counter()

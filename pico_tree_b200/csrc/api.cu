@@ -314,7 +314,11 @@ int pico_b200_box(const pico_b200_tree* t, const void* mins, const void* maxs, s
 
 void pico_b200_free(void* p) { free(p); }
 void pico_b200_free_device(void* p) {
-  if (p) cudaFree(p);
+  // The buffers come from the stream-ordered pool and go back into it (a later call re-uses the block instead of
+  // paying a multi-gigabyte cudaMalloc). Like cudaFree, this waits for everything the device was given so far.
+  if (!p) return;
+  cudaDeviceSynchronize();
+  cudaFreeAsync(p, cudaStreamLegacy);
 }
 
 int pico_b200_set_stream(void* cuda_stream) { return set_thread_stream(cuda_stream, cuda_stream != nullptr); }
