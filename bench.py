@@ -179,9 +179,11 @@ def tree_leaf_scan(L, handle, q_dev, n_query, dev, repeats):
     return out, {"descend_ms": d_ms.value, "scan_ms": s_ms.value, "scan_bytes": int(nbytes.value)}
 
 
-def pcie_floor_ms(q_pin, out_pin, dev, reps=10):
+def pcie_floor_ms(q_pin, out_pin, dev, reps=10, barrier=None):
     """One full-size H2D of the queries and D2H of the results, issued together on two streams (PCIe is
-    full duplex): the time no host-buffer call can beat on this box."""
+    full duplex): the time no host-buffer call can beat on this box. With `barrier` (N > 1) every repetition
+    starts behind a barrier, so all ranks copy at the same time — what the shared uplinks and the one host memory
+    system allow when every GPU moves its step's bytes at once."""
     import torch
     s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
     d_in = torch.empty(q_pin.shape, dtype=q_pin.dtype, device=dev)
@@ -190,6 +192,8 @@ def pcie_floor_ms(q_pin, out_pin, dev, reps=10):
     best = None
     for _ in range(reps):
         torch.cuda.synchronize()
+        if barrier is not None:
+            barrier()
         t0 = time.perf_counter()
         with torch.cuda.stream(s_in):
             d_in.copy_(q_pin, non_blocking=True)
@@ -232,6 +236,7 @@ def run_ours(args, n_tree, n_query):
 
     # ---- tree: built on rank 0, broadcast once
     t_build0 = time.perf_counter()
+    first_build = None
     if rank == 0:
         # the first build of a process also loads the build kernels' modules (lazy loading: 130 ms inside the
         # CUDA-event span of BENCH_r01); a small throw-away build takes that out of the reported build time
@@ -255,6 +260,29 @@ def run_ours(args, n_tree, n_query):
         bcast_ms = (time.perf_counter() - t0) * 1e3
     info = _lib.TreeInfo()
     _lib.check(L.pico_b200_tree_info_get(handle, C.byref(info)))
+    # the same replication through the C-ABI's own entry (pico_b200_tree_broadcast with a plain ncclComm_t created
+    # with NCCL's API): the replica it makes must answer exactly like the one above
+    raw_nccl = None
+    if world > 1:
+        nccl_lib, comm = pd.raw_nccl_comm(local)
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        h2 = pd.replicate_tree_raw_nccl(handle if rank == 0 else None, comm, 0, local)
+        torch.cuda.synchronize()
+        raw_ms = (time.perf_counter() - t0) * 1e3
+        ns = min(n_query, 200_000)
+        qs = np.ascontiguousarray(q_host[:ns])
+        a = np.empty((ns, 2), dtype=np.dtype([("index", "<i4"), ("distance", "<f4")]))
+        b = np.empty_like(a)
+        for hh, o in ((handle, a), (h2, b)):
+            _lib.check(L.pico_b200_knn(hh, C.c_void_p(qs.ctypes.data), ns, 3, 2, 0.0, C.c_void_p(o.ctypes.data), 0, None))
+        same = torch.tensor([int(np.array_equal(a, b))], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        if rank != 0:
+            L.pico_b200_tree_destroy(h2)
+        nccl_lib.ncclCommDestroy(comm)
+        raw_nccl = {"ms": raw_ms, "replica_answers_equal_on_all_ranks": bool(same.item()), "queries_checked": ns}
 
     # ---- resident inputs / outputs
     stream = torch.cuda.Stream(device=dev)
@@ -327,6 +355,10 @@ def run_ours(args, n_tree, n_query):
     e2e_s = (time.perf_counter() - t0) / e2e_steps
 
     floor_ms = pcie_floor_ms(q_pin, out_pin, dev)
+    floor_concurrent_ms = None
+    if world > 1:  # all ranks at once: the floor of the whole job's step
+        barrier()
+        floor_concurrent_ms = pcie_floor_ms(q_pin, out_pin, dev, reps=6, barrier=dist.barrier)
     os.sched_setaffinity(0, cpus_all)
 
     # resident and host paths must agree
@@ -335,9 +367,9 @@ def run_ours(args, n_tree, n_query):
 
     # ---- max over ranks
     if world > 1:
-        tmax = torch.tensor([ms_step, e2e_s, kernel_ms], dtype=torch.float64, device=dev)
+        tmax = torch.tensor([ms_step, e2e_s, kernel_ms, floor_ms, floor_concurrent_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        ms_step, e2e_s, kernel_ms = [float(x) for x in tmax.tolist()]
+        ms_step, e2e_s, kernel_ms, floor_ms, floor_concurrent_ms = [float(x) for x in tmax.tolist()]
     total_q = n_query * world
     value = total_q / (ms_step * 1e-3) / 1e6
     e2e_value = total_q / e2e_s / 1e6
@@ -438,10 +470,13 @@ def run_ours(args, n_tree, n_query):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": config_dict(n_tree, n_query, k, world, {
             "tree_nodes": int(info.n_nodes), "tree_height": int(info.height), "build_ms_device": info.build_ms,
-            "build_wall_s": build_wall, "first_build_of_the_process": first_build, "tree_broadcast_ms": bcast_ms, "tree_device_bytes": int(info.device_bytes)}),
+            "build_wall_s": build_wall, "first_build_of_the_process": first_build, "tree_broadcast_ms": bcast_ms,
+            "tree_broadcast_raw_nccl": raw_nccl, "tree_device_bytes": int(info.device_bytes)}),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(q_host.nbytes),
                 "d2h_bytes_per_step": int(n_query * k * 8), "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
-                "pcie_floor_ms": floor_ms, "host_binding": binding,
+                "pcie_floor_ms": floor_ms, "pcie_floor_all_ranks_at_once_ms": floor_concurrent_ms,
+                "e2e_over_concurrent_floor": (floor_concurrent_ms / (e2e_s * 1e3)) if floor_concurrent_ms else None,
+                "host_binding": binding,
                 "pcie_floor_note": "one H2D of all queries + one D2H of all results issued together, best of 10"},
         "gpu_launches": int(args.steps * ((2 if k == 1 and not args.warp_per_query else 1) +
                                           (0 if args.no_reorder else 1))),

@@ -71,3 +71,57 @@ def replicate_tree(tree, src=0, device_index=0):
     _lib.check(L.pico_b200_tree_deserialize(C.c_void_p(image.data_ptr()), image.numel(), 1, device_index,
                                             C.byref(handle)))
     return handle
+
+
+# ---------------------------------------------------------------------------------- raw NCCL communicator
+class _NcclUniqueId(C.Structure):
+    _fields_ = [("internal", C.c_char * 128)]
+
+
+def _nccl():
+    """The NCCL library of this process (torch's bundled one when torch is loaded)."""
+    import glob
+    import os
+    libs = []
+    try:
+        import torch
+        libs = sorted(glob.glob(os.path.join(os.path.dirname(torch.__file__), "..", "nvidia", "nccl", "lib",
+                                             "libnccl.so*")))
+    except ImportError:
+        pass
+    lib = C.CDLL(libs[0] if libs else "libnccl.so.2", mode=C.RTLD_GLOBAL)
+    lib.ncclGetUniqueId.argtypes = [C.POINTER(_NcclUniqueId)]
+    lib.ncclCommInitRank.argtypes = [C.POINTER(C.c_void_p), C.c_int, _NcclUniqueId, C.c_int]
+    lib.ncclCommDestroy.argtypes = [C.c_void_p]
+    return lib
+
+
+def raw_nccl_comm(device_index):
+    """An ncclComm_t over all ranks of the torch.distributed job, created with NCCL's own API (the unique id
+    travels through torch.distributed). For pico_b200_tree_broadcast, which takes a plain ncclComm_t so that
+    callers without torch (the C++ header, other runtimes) can replicate a tree. Returns (lib, comm)."""
+    import torch
+    import torch.distributed as dist
+    lib = _nccl()
+    uid = _NcclUniqueId()
+    if dist.get_rank() == 0 and lib.ncclGetUniqueId(C.byref(uid)) != 0:
+        raise RuntimeError("ncclGetUniqueId failed")
+    dev = torch.device("cuda", device_index) if dist.get_backend() == "nccl" else torch.device("cpu")
+    buf = torch.frombuffer(bytearray(bytes(uid.internal)), dtype=torch.uint8).to(dev)
+    dist.broadcast(buf, 0)
+    C.memmove(C.byref(uid), bytes(buf.cpu().numpy().tobytes()), 128)
+    comm = C.c_void_p()
+    torch.cuda.set_device(device_index)
+    if lib.ncclCommInitRank(C.byref(comm), dist.get_world_size(), uid, dist.get_rank()) != 0:
+        raise RuntimeError("ncclCommInitRank failed")
+    return lib, comm
+
+
+def replicate_tree_raw_nccl(tree_handle, comm, root, device_index):
+    """pico_b200_tree_broadcast: `tree_handle` is the C handle on `root` (None elsewhere); returns a handle on
+    every rank (the root's own on the root)."""
+    import torch.distributed as dist
+    L = _lib.lib()
+    h = C.c_void_p(tree_handle.value if tree_handle is not None and dist.get_rank() == root else None)
+    _lib.check(L.pico_b200_tree_broadcast(C.byref(h), comm, dist.get_rank(), root, device_index))
+    return h
