@@ -105,6 +105,9 @@ struct WarpQueue {
         hi = mid;
     }
     const int p = lo;
+    // every lane has finished reading before any lane writes (lanes of a warp may run apart: without this, lane 0
+    // could store the new entry while a slower lane is still searching — racecheck found exactly that when p == 1)
+    __syncwarp();
     if (n == cap) {
       if (p == 0) return;  // greater than everything kept: it can never be popped within the leaf budget
       for (int b = 1; b < p; b += 32) {  // drop a[0]: a[1 .. p) move one to the left
