@@ -112,6 +112,15 @@ def run_reference(args, n_tree, n_query):
     print(json.dumps(line))
 
 
+def kernel_sources_sha16():
+    """Hash of the sources of the traversal kernels (what an ncu capture is valid for)."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("traverse.cuh", "search.cu", "common.cuh"):
+        h.update(open(os.path.join(ROOT, "pico_tree_b200", "csrc", f), "rb").read())
+    return h.hexdigest()[:16]
+
+
 # --------------------------------------------------------------------------- clocks
 class ClockSampler:
     FIELDS = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -427,14 +436,23 @@ def run_ours(args, n_tree, n_query):
     roofline = None
     if bytes_per_query is not None and kernel_ms > 0:
         achieved = bytes_per_query * n_query / (kernel_ms * 1e-3) / 1e9
-        traffic = None
+        # DRAM bytes per launch from the last ncu --set full capture of this kernel — only if it was taken with the
+        # kernel sources that are being timed now (profiles/traffic.json records their hash)
+        traffic, traffic_note = None, None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("knn1_dram_bytes_per_launch")
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            if tj.get("sources_sha16") == kernel_sources_sha16() and k == 1:
+                traffic = tj.get("knn1_dram_bytes_per_launch")
+                traffic_note = tj.get("source")
+            else:
+                traffic_note = "profiles/traffic.json was captured for other kernel sources or another k: not reported"
         except (OSError, ValueError):
             pass
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": traffic, "kernel": ("nn_fat_kernel<float,3,3>" if k == 1 else
-                                                   "knn_thread_kernel<float,3,K,FAST>") if not args.warp_per_query
+                    "traffic": traffic, "traffic_note": traffic_note,
+                    "kernel": ("knn_thread_kernel<float,3,1,FAST>" if k == 1 and os.environ.get("PICO_B200_NN", "0") == "0"
+                               else "nn_kernel<float,3,...> (PICO_B200_NN)" if k == 1 else
+                               "knn_thread_kernel<float,3,K,FAST>") if not args.warp_per_query
                     else "knn_warp_kernel<float,PACKED,REG>", "kernel_ms": kernel_ms,
                     "algorithmic_bytes_per_query": bytes_per_query,
                     "per_query_branches_leaves_points": counters, "peak_source": peak_kind}
@@ -444,8 +462,9 @@ def run_ours(args, n_tree, n_query):
         gbs = leaf_scan["scan_bytes"] / (leaf_scan["scan_ms"] * 1e-3) / 1e9
         ls_traffic = None
         try:
-            ls_traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(
-                "leaf_scan_dram_bytes_per_launch")
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            if tj.get("sources_sha16") == kernel_sources_sha16():
+                ls_traffic = tj.get("leaf_scan_dram_bytes_per_launch")
         except (OSError, ValueError):
             pass
         leaf_scan = dict(leaf_scan, kernel="leaf_scan_kernel<float,3>", achieved=gbs, peak=peak, unit="GB/s",

@@ -1096,7 +1096,7 @@ int knn_enqueue(CallCtx& c, const pico_b200_tree* t, const T* q, size_t nq, size
 
 constexpr size_t kHostChunk = (size_t)1 << 20;  // queries per pipelined chunk (host buffers)
 constexpr int kHostStreams = 6;  // profiles/r1/e2e_sweep.txt: 1 Mi queries x 6 streams is the best point
-constexpr int kMaxHostStreams = 8;
+constexpr int kMaxHostStreams = 12;
 
 // tuning hooks (profiles/r1/e2e_sweep.txt): PICO_B200_HOST_CHUNK, PICO_B200_HOST_STREAMS
 size_t host_chunk() {
