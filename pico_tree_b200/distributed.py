@@ -107,9 +107,9 @@ def raw_nccl_comm(device_index):
     if dist.get_rank() == 0 and lib.ncclGetUniqueId(C.byref(uid)) != 0:
         raise RuntimeError("ncclGetUniqueId failed")
     dev = torch.device("cuda", device_index) if dist.get_backend() == "nccl" else torch.device("cpu")
-    buf = torch.frombuffer(bytearray(bytes(uid.internal)), dtype=torch.uint8).to(dev)
+    buf = torch.frombuffer(bytearray(C.string_at(C.byref(uid), 128)), dtype=torch.uint8).to(dev)  # all 128 bytes
     dist.broadcast(buf, 0)
-    C.memmove(C.byref(uid), bytes(buf.cpu().numpy().tobytes()), 128)
+    C.memmove(C.byref(uid), buf.cpu().numpy().tobytes(), 128)
     comm = C.c_void_p()
     torch.cuda.set_device(device_index)
     if lib.ncclCommInitRank(C.byref(comm), dist.get_world_size(), uid, dist.get_rank()) != 0:
