@@ -420,6 +420,25 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) box_warp_kernel(BoxArgs<T
   }
 }
 
+// Thread-per-box (traverse_box_thread): euclidean spaces, sdim <= 3, trees no deeper than the local stack. Boxes are
+// taken in the Z-order of their lower corners so that the threads of a warp walk neighbouring cells.
+template <typename T, int DIM>
+__global__ void __launch_bounds__(kThreadsPerBlock) box_thread_kernel(BoxArgs<T> a, const uint32_t* __restrict__ perm) {
+  const size_t total = (size_t)gridDim.x * blockDim.x;
+  for (size_t slot = (size_t)blockIdx.x * blockDim.x + threadIdx.x; slot < a.nb; slot += total) {
+    const uint32_t bi = perm ? perm[slot] : (uint32_t)slot;
+    T qmin[DIM], qmax[DIM];
+#pragma unroll
+    for (int j = 0; j < DIM; ++j) {
+      qmin[j] = a.mins[(size_t)bi * a.stride + j];
+      qmax[j] = a.maxs[(size_t)bi * a.stride + j];
+    }
+    int32_t* out = a.hits ? a.hits + a.offsets[bi] : nullptr;
+    const uint32_t c = traverse_box_thread<T, DIM>(a.nodes, a.pts4, a.indices, qmin, qmax, a.root_box, out);
+    if (!a.hits) a.counts[bi] = c;
+  }
+}
+
 // ------------------------------------------------------------------ host helpers
 // per-thread call configuration (pico_b200_set_stream / pico_b200_profile_*)
 struct ThreadCfg {
@@ -1863,11 +1882,34 @@ int box_batch(const pico_b200_tree* t, const T* mins, const T* maxs, size_t nb, 
   a.offsets = nullptr;
   a.hits = nullptr;
   PICO_TRY(c.alloc(reinterpret_cast<void**>(&a.counts), nb * 4));
-  unsigned blocks;
-  size_t smem;
-  PICO_TRY(warp_geometry<T>(c, t, nb, sizeof(BoxFrame) + sizeof(T), 4 * t->sdim * sizeof(T), &a.ws, &a.ws_depth,
-                            &blocks, &smem));
+  // thread-per-box for the packed euclidean case (the warp kernel: 98 ms per 1M boxes of 541 hits each — one box
+  // per warp, frames in global memory, a __syncwarp per step; bench configs)
+  const bool thread_box = t->packed() && !t->topological() && t->height < (size_t)kLocalStack - 1 &&
+                          t->n_nodes < ((size_t)1 << 30) && !(flags & PICO_B200_WARP_PER_QUERY);
+  uint32_t* box_perm = nullptr;
+  if (thread_box) PICO_TRY(make_perm(c, t, d_min, d_stride, nb, flags, &box_perm));
+  unsigned blocks = 0;
+  size_t smem = 0;
+  if (!thread_box)
+    PICO_TRY(warp_geometry<T>(c, t, nb, sizeof(BoxFrame) + sizeof(T), 4 * t->sdim * sizeof(T), &a.ws, &a.ws_depth,
+                              &blocks, &smem));
   auto launch = [&]() -> int {
+    if (thread_box) {
+      const unsigned tb = (unsigned)((nb + kThreadsPerBlock - 1) / kThreadsPerBlock);
+      switch (t->sdim) {
+        case 1:
+          box_thread_kernel<T, 1><<<tb, kThreadsPerBlock, 0, c.st>>>(a, box_perm);
+          break;
+        case 2:
+          box_thread_kernel<T, 2><<<tb, kThreadsPerBlock, 0, c.st>>>(a, box_perm);
+          break;
+        default:
+          box_thread_kernel<T, 3><<<tb, kThreadsPerBlock, 0, c.st>>>(a, box_perm);
+          break;
+      }
+      PICO_CUDA(cudaGetLastError());
+      return 0;
+    }
     if (t->packed()) {
       box_warp_kernel<T, true><<<blocks, kWarpsPerBlock * 32, smem, c.st>>>(a);
     } else {

@@ -708,4 +708,125 @@ __device__ __forceinline__ void traverse_nn(const typename NodeOf<T>::type* __re
   }
 }
 
+// ---------------------------------------------------------------- box search, thread-per-box, sdim <= 3
+// search_box::operator() + report_node / report_left / report_right (kd_tree_search.hpp:270-372) for euclidean
+// spaces, one thread per box: the running cell box (kd_tree_search.hpp:296-306 narrows one bound before it looks
+// at a child and puts it back after) lives in registers, the recursion on a per-thread stack of
+// {node, stage, saved bound}. Reports come in the reference's depth-first order: a cell inside the query is
+// reported whole — its points are one contiguous run of the leaf-ordered arrays —, a leaf point by point
+// (box.hpp:31-47, bounds inclusive). out == nullptr: count only.
+struct BoxSlot {
+  uint32_t node_stage;  // node | stage << 30
+};
+
+template <typename T, int DIM>
+__device__ __forceinline__ uint32_t traverse_box_thread(const typename NodeOf<T>::type* __restrict__ nodes,
+                                                        const typename Vec4Of<T>::type* __restrict__ pts4,
+                                                        const int32_t* __restrict__ indices, const T (&qmin)[DIM],
+                                                        const T (&qmax)[DIM], const T* __restrict__ root_box,
+                                                        int32_t* __restrict__ out) {
+  T bmin[DIM], bmax[DIM];
+#pragma unroll
+  for (int j = 0; j < DIM; ++j) {
+    bmin[j] = root_box[j];
+    bmax[j] = root_box[DIM + j];
+  }
+  uint32_t st_node[kLocalStack];
+  T st_saved[kLocalStack];
+  uint32_t count = 0;
+  int sp = 1;
+  st_node[0] = 0;
+  while (sp > 0) {
+    const uint32_t ns = st_node[sp - 1];
+    const uint32_t node = ns & kTagNodeMask, stage = ns >> 30;
+    T a, b;
+    uint32_t right, sd;
+    int lb, le;
+    load_node(nodes, node, a, b, right, sd, lb, le);
+    if (sd == PICO_B200_LEAF) {
+      for (int i = lb; i < le; ++i) {
+        const typename Vec4Of<T>::type p = ldg4(pts4 + i);
+        bool in = !(qmin[0] > p.x || qmax[0] < p.x);
+        if (DIM > 1) in = in && !(qmin[DIM > 1 ? 1 : 0] > p.y || qmax[DIM > 1 ? 1 : 0] < p.y);
+        if (DIM > 2) in = in && !(qmin[DIM > 2 ? 2 : 0] > p.z || qmax[DIM > 2 ? 2 : 0] < p.z);
+        if (in) {
+          if (out) out[count] = index_of(p);
+          ++count;
+        }
+      }
+      --sp;
+      continue;
+    }
+    if (stage == 2u) {  // both children done: the lower bound narrowed for the right child goes back
+      const T saved = st_saved[sp - 1];
+#pragma unroll
+      for (int j = 0; j < DIM; ++j) bmin[j] = (sd == (uint32_t)j) ? saved : bmin[j];
+      --sp;
+      continue;
+    }
+    // stage 0: narrow max to left_max and look at the left child;
+    // stage 1: put max back, narrow min to right_min and look at the right child
+    const uint32_t child = stage == 0u ? node + 1 : right;
+    T keep;
+    if (stage == 0u) {
+      keep = bmax[0];
+#pragma unroll
+      for (int j = 1; j < DIM; ++j) keep = (sd == (uint32_t)j) ? bmax[j] : keep;
+#pragma unroll
+      for (int j = 0; j < DIM; ++j) bmax[j] = (sd == (uint32_t)j) ? a : bmax[j];
+    } else {
+      const T saved = st_saved[sp - 1];
+      keep = bmin[0];
+#pragma unroll
+      for (int j = 1; j < DIM; ++j) keep = (sd == (uint32_t)j) ? bmin[j] : keep;
+#pragma unroll
+      for (int j = 0; j < DIM; ++j) {
+        bmax[j] = (sd == (uint32_t)j) ? saved : bmax[j];
+        bmin[j] = (sd == (uint32_t)j) ? b : bmin[j];
+      }
+    }
+    st_saved[sp - 1] = keep;
+    st_node[sp - 1] = node | ((stage + 1u) << 30);
+    // query.contains(box_) := contains(box.min) && contains(box.max), box.hpp:44-47
+    bool contained = true;
+#pragma unroll
+    for (int j = 0; j < DIM; ++j)
+      contained = contained && !(qmin[j] > bmin[j] || qmax[j] < bmin[j]) && !(qmin[j] > bmax[j] || qmax[j] < bmax[j]);
+    if (contained) {
+      // report_node (kd_tree_search.hpp:336-372): leftmost leaf's begin .. rightmost leaf's end
+      uint32_t nl = child, nr = child, tr, tsd;
+      int rb, re, d0, d1;
+      T ta, tb;
+      load_node(nodes, nl, ta, tb, tr, tsd, rb, d0);
+      uint32_t rsd = tsd, rright = tr;
+      re = d0;
+      while (tsd != PICO_B200_LEAF) {
+        ++nl;
+        load_node(nodes, nl, ta, tb, tr, tsd, rb, d0);
+      }
+      while (rsd != PICO_B200_LEAF) {
+        nr = rright;
+        load_node(nodes, nr, ta, tb, rright, rsd, d1, re);
+      }
+      if (out)
+        for (int i = rb; i < re; ++i) out[count + (uint32_t)(i - rb)] = __ldg(indices + i);
+      count += (uint32_t)(re - rb);
+    } else {
+      // intersects_left / intersects_right, kd_tree_search.hpp:310-328
+      T lo = qmin[0], hi = qmax[0];
+#pragma unroll
+      for (int j = 1; j < DIM; ++j) {
+        lo = (sd == (uint32_t)j) ? qmin[j] : lo;
+        hi = (sd == (uint32_t)j) ? qmax[j] : hi;
+      }
+      const bool intersects = stage == 0u ? (lo <= a) : (hi >= b);
+      if (intersects) {
+        st_node[sp] = child;  // stage 0
+        ++sp;
+      }
+    }
+  }
+  return count;
+}
+
 }  // namespace pico

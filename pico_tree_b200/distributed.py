@@ -112,7 +112,19 @@ def raw_nccl_comm(device_index):
     C.memmove(C.byref(uid), buf.cpu().numpy().tobytes(), 128)
     comm = C.c_void_p()
     torch.cuda.set_device(device_index)
-    if lib.ncclCommInitRank(C.byref(comm), dist.get_world_size(), uid, dist.get_rank()) != 0:
+    # NCCL announces its version on the C stdout of the process at the first communicator it creates itself; callers
+    # such as bench.py promise exactly one JSON line there, so the announcement is sent to stderr
+    import os
+    import sys
+    sys.stdout.flush()
+    keep = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        rc = lib.ncclCommInitRank(C.byref(comm), dist.get_world_size(), uid, dist.get_rank())
+    finally:
+        os.dup2(keep, 1)
+        os.close(keep)
+    if rc != 0:
         raise RuntimeError("ncclCommInitRank failed")
     return lib, comm
 
