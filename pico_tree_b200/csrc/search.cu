@@ -521,6 +521,10 @@ struct CallCtx {
     return 0;
   }
   bool timed = true;  // record the five stage events (search stats)
+  // host pipeline: resident blocks per SM the thread-per-query traversal of a chunk may take (0 = no cap). Leaving
+  // a few block slots free lets the small ordering kernels of the next chunk start at once instead of waiting
+  // for traversal blocks to drain (profiles/r2/host_pipeline_timeline.txt)
+  int blocks_per_sm_cap = 0;
   int mark(int i) {
     if (!async && timed) PICO_CUDA(cudaEventRecord(ev[i], st));
     return 0;
@@ -1010,6 +1014,8 @@ int knn_enqueue(CallCtx& c, const pico_b200_tree* t, const T* q, size_t nq, size
     bool deep;
     unsigned blocks;
     PICO_TRY(thread_geometry(c, t, a, (int)t->sdim, &deep, &blocks));
+    if (c.blocks_per_sm_cap > 0)
+      blocks = std::min<unsigned>(blocks, (unsigned)t->sm_count * (unsigned)c.blocks_per_sm_cap);
     const bool fast = t->metric == PICO_B200_METRIC_L2_SQUARED && !(e > 0);
     const int mode = nn_mode();
     if (fast && !deep && k == 1 && mode && t->sdim >= 2 && t->n_nodes < ((size_t)1 << 30)) {
@@ -1161,6 +1167,17 @@ bool host_priority_order() {
   static const bool v = [] {
     const char* e = getenv("PICO_B200_HOST_PRIO");
     return !(e && atoi(e) == 0);
+  }();
+  return v;
+}
+// Block slots per SM a chunk's traversal may occupy while the pipeline orders the next chunks (0 = all).
+// PICO_B200_HOST_TRAV_BLOCKS is a tuning hook.
+constexpr int kHostTraversalBlocks = 0;
+int host_traversal_blocks() {
+  static const int v = [] {
+    const char* e = getenv("PICO_B200_HOST_TRAV_BLOCKS");
+    const int x = e ? atoi(e) : -1;
+    return (x >= 0 && x <= 16) ? x : kHostTraversalBlocks;
   }();
   return v;
 }
@@ -1339,6 +1356,7 @@ int knn_batch(const pico_b200_tree* t, const T* q, size_t nq, size_t stride, siz
       const size_t begin = plan[ci].first, cnt = plan[ci].second;
       CallCtx& c = ctx[ci % n_streams];
       c.timed = timeline;
+      c.blocks_per_sm_cap = hp_order ? host_traversal_blocks() : 0;
       c.release();
       cpu_at[2 * ci] = cpu_ms();
       if (ahead) {

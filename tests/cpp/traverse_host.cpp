@@ -130,7 +130,36 @@ void knn_packed(const void* nodes, const void* pts4, const T* q, size_t nq, int 
 
 }  // namespace
 
+// thread-per-box traversal: count pass, then fill pass, per box
+template <int DIM>
+static unsigned long long box_f32(const void* nodes, const void* pts4, const int32_t* indices, const float* root_box,
+                                  const float* mins, const float* maxs, size_t nb, uint64_t* offsets, int32_t* out) {
+  using namespace pico;
+  unsigned long long total = 0;
+  for (size_t i = 0; i < nb; ++i) {
+    float lo[DIM], hi[DIM];
+    for (int j = 0; j < DIM; ++j) {
+      lo[j] = mins[i * DIM + j];
+      hi[j] = maxs[i * DIM + j];
+    }
+    offsets[i] = total;
+    const uint32_t c = traverse_box_thread<float, DIM>(static_cast<const pico_b200_node_f32*>(nodes),
+                                                       static_cast<const float4*>(pts4), indices, lo, hi, root_box,
+                                                       out ? out + total : nullptr);
+    total += c;
+  }
+  offsets[nb] = total;
+  return total;
+}
+
 extern "C" {
+// search_box through traverse_box_thread; out == nullptr: offsets only. Returns the number of reported indices.
+unsigned long long host_box_f32(const void* nodes, const void* pts4, const int32_t* indices, const float* root_box,
+                                const float* mins, const float* maxs, size_t nb, int sdim, uint64_t* offsets,
+                                int32_t* out) {
+  if (sdim == 2) return box_f32<2>(nodes, pts4, indices, root_box, mins, maxs, nb, offsets, out);
+  return box_f32<3>(nodes, pts4, indices, root_box, mins, maxs, nb, offsets, out);
+}
 // node loads / f32 point loads since the last call
 unsigned long long host_take_loads16() {
   const unsigned long long v = g_loads16;

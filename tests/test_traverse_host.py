@@ -164,3 +164,36 @@ def test_order_exact_traversal_matches_oracle(oracle, host_lib, k):
     fn(flat.ctypes.data, pts4.ctypes.data, q.ctypes.data, len(q), 3, k, len(pts), idx.ctypes.data, dist.ctypes.data)
     want = tree.search_knn(q, k)
     assert np.array_equal(dist, want["distance"]) and np.array_equal(idx, want["index"])
+
+
+@pytest.mark.parametrize("sdim,leaf", [(3, 10), (2, 1), (3, 64)])
+def test_box_thread_traversal_matches_oracle(oracle, host_lib, sdim, leaf):
+    """traverse_box_thread (one thread per box): counts and indices in the reference's depth-first report order,
+    whole cells reported as one run included; boxes of every size, some empty, some covering everything."""
+    rng = np.random.default_rng(21)
+    pts = rng.random((30_000, sdim)).astype(np.float32)
+    tree = oracle.OracleTree(pts, leaf)
+    flat = flat_nodes(tree.nodes, np.float32)
+    pts4 = leaf_order_points(pts, tree.indices)
+    c = rng.random((1_500, sdim)).astype(np.float32) * 1.2 - 0.1
+    h = (rng.random((1_500, 1)) ** 3 * 0.5).astype(np.float32)
+    mins, maxs = np.ascontiguousarray(c - h), np.ascontiguousarray(c + h)
+    mins[0], maxs[0] = -1.0, 2.0            # everything
+    mins[1], maxs[1] = 5.0, 6.0             # nothing
+    mins[2], maxs[2] = pts[7], pts[7]       # a single point, bounds inclusive
+    w_offs, w_flat = tree.search_box(mins, maxs)
+    fn = host_lib.host_box_f32
+    fn.restype = C.c_ulonglong
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int,
+                   C.c_void_p, C.c_void_p]
+    root_box = np.ascontiguousarray(tree.root_box, dtype=np.float32).ravel()
+    idx = np.ascontiguousarray(tree.indices)
+    offs = np.zeros(len(mins) + 1, np.uint64)
+    total = fn(flat.ctypes.data, pts4.ctypes.data, idx.ctypes.data, root_box.ctypes.data, mins.ctypes.data,
+               maxs.ctypes.data, len(mins), sdim, offs.ctypes.data, None)
+    assert total == int(w_offs[-1]) and np.array_equal(offs, w_offs)
+    out = np.empty(int(total), np.int32)
+    fn(flat.ctypes.data, pts4.ctypes.data, idx.ctypes.data, root_box.ctypes.data, mins.ctypes.data, maxs.ctypes.data,
+       len(mins), sdim, offs.ctypes.data, out.ctypes.data)
+    assert np.array_equal(out, w_flat)
+    assert offs[1] - offs[0] == len(pts) and offs[2] == offs[1] and offs[3] - offs[2] >= 1
