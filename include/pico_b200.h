@@ -284,6 +284,14 @@ int pico_b200_forest_knn(const pico_b200_forest* forest, const void* queries, si
                          size_t max_leaves_visited, void* neighbors_out, unsigned flags, pico_b200_search_stats* stats);
 
 /*
+ * How the tree currently orders the queries of a batch before the thread-per-query kernels run (ordering never
+ * changes a result, only memory coherence): 0 = not measured yet, 1 = batches arrived locally coherent (a scan, a
+ * raster): every tile of 2048 consecutive queries is Z-ordered on its own, 2 = batches arrived in no useful order:
+ * the whole batch is Z-ordered with a device-wide radix sort. Decided from the last measured batch.
+ */
+int pico_b200_tree_order_state(const pico_b200_tree* tree, int* state);
+
+/*
  * Caller-provided CUDA stream (cudaStream_t) for the calling host thread; NULL restores the
  * default (a private stream per call). With a caller stream the searches are ordered on that
  * stream, so they compose with the caller's own kernels, events and CUDA graphs. NULL never means

@@ -28,7 +28,7 @@ EXPORTS = [
     "pico_b200_tree_save_size", "pico_b200_tree_save", "pico_b200_tree_load", "pico_b200_set_stream",
     "pico_b200_profile_begin", "pico_b200_profile_end", "pico_b200_profile_leaf_scan",
     "pico_b200_forest_create", "pico_b200_forest_destroy", "pico_b200_forest_info_get", "pico_b200_forest_rotations",
-    "pico_b200_forest_tree", "pico_b200_forest_knn",
+    "pico_b200_forest_tree", "pico_b200_forest_knn", "pico_b200_tree_order_state",
 ]
 
 
@@ -101,6 +101,7 @@ def lib():
     L.pico_b200_profile_end.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
     L.pico_b200_profile_leaf_scan.argtypes = [vp, vp, sz, sz, vp, i32, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                               C.POINTER(C.c_uint64)]
+    L.pico_b200_tree_order_state.argtypes = [vp, C.POINTER(C.c_int)]
     L.pico_b200_forest_create.argtypes = [vp, sz, sz, sz, i32, sz, vp, sz, i32, C.POINTER(vp)]
     L.pico_b200_forest_destroy.argtypes = [vp]
     L.pico_b200_forest_destroy.restype = None

@@ -77,6 +77,8 @@ void release(pico_b200_tree* t) {
   cudaFree(t->d_outer);
   cudaFree(t->d_spans);
   cudaFree(t->d_fat_nodes);
+  cudaFree(t->order_hint.d_stat);
+  if (t->order_hint.h_stat) cudaFreeHost(t->order_hint.h_stat);
   delete t;
 }
 
@@ -319,6 +321,12 @@ void pico_b200_free_device(void* p) {
   if (!p) return;
   cudaDeviceSynchronize();
   cudaFreeAsync(p, cudaStreamLegacy);
+}
+
+int pico_b200_tree_order_state(const pico_b200_tree* t, int* state) {
+  if (!t || !state) return fail(PICO_B200_ERR_INVALID_ARGUMENT, "null argument");
+  *state = order_state(t);
+  return 0;
 }
 
 int pico_b200_set_stream(void* cuda_stream) { return set_thread_stream(cuda_stream, cuda_stream != nullptr); }

@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <string>
 
 #include "../../include/pico_b200.h"
@@ -89,6 +90,15 @@ constexpr int kFatLeafPoints = 0;  // subtrees of at most this many points are o
 }  // namespace pico
 
 // ---------------------------------------------------------------- the handle
+// What the last batches looked like to the query ordering (search.cu: tile_order_kernel). Ordering never changes a
+// result, so a stale or racy hint costs time at worst.
+struct pico_b200_order_hint {
+  std::atomic<int> state{0};               // 0 unknown, 1 batches arrive locally coherent, 2 they need the global sort
+  std::atomic<unsigned> calls{0};
+  unsigned long long* h_stat = nullptr;    // pinned: tiles << 40 | distinct coarse cells summed over the tiles, last measured batch
+  unsigned long long* d_stat = nullptr;
+};
+
 struct pico_b200_tree {
   int device = 0;
   int scalar = PICO_B200_F32;
@@ -102,6 +112,7 @@ struct pico_b200_tree {
   uint2* d_spans = nullptr;    // row storage (sdim > 3): {first point, point count} below every node
   void* d_fat_nodes = nullptr; // packed trees: `nodes` with small subtrees collapsed into leaves (fat.cu), or null
   int fat_limit = 0;           // points per collapsed subtree (0 = no search image)
+  mutable pico_b200_order_hint order_hint;
   double root_box_host[2 * 4] = {0};  // first min(sdim,4) dims, as double, for query ordering
   double build_ms = 0.0;
   size_t device_bytes = 0;
@@ -131,6 +142,7 @@ int upload_tree(pico_b200_tree* t, const T* h_pts, size_t stride, const void* no
 int build_fat_nodes(pico_b200_tree* t, cudaStream_t st);
 
 // search.cu
+int order_state(const pico_b200_tree* t);  // pico_b200_order_hint::state after looking at the last measured batch
 int set_thread_stream(void* stream, bool has);
 int profile_begin();
 int profile_end(double* ms, uint64_t* launches);
