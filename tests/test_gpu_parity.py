@@ -806,3 +806,38 @@ def test_tree_image_round_trip_and_validation(pt):
         assert rc != 0 and not h.value, what
     rc, h = load(image[:len(image) // 2].copy())
     assert rc != 0
+
+
+def test_query_ordering_adapts_to_the_batch(pt, oracle):
+    """Scan-order batches are Z-ordered tile by tile (tile_order_kernel), shuffled ones with the device-wide sort;
+    the tree decides from the last measured batch (pico_b200_tree_order_state) and the answers never change."""
+    import ctypes as C
+    from pico_tree_b200 import _lib, datasets as D
+    L = _lib.lib()
+    pts = D.lidar_shape(400_000, seed=1)
+    q = D.lidar_shape(300_000, seed=2, pose_shift=0.35)
+    t = pt.KdTree(pts, pt.Metric.L2Squared, 10)
+    want = oracle.OracleTree(pts, 10).search_knn(q, 4)
+
+    def state():
+        s = C.c_int(-1)
+        _lib.check(L.pico_b200_tree_order_state(t._h, C.byref(s)))
+        return s.value
+
+    assert state() == 0
+    for _ in range(3):
+        got = t.search_knn(q, 4)
+        assert np.array_equal(got["index"], want["index"]) and np.array_equal(got["distance"], want["distance"])
+    assert state() == 1, "a scan-order batch should be ordered tile by tile"
+    perm = np.random.default_rng(0).permutation(len(q))
+    qs = np.ascontiguousarray(q[perm])
+    for _ in range(3):
+        got = t.search_knn(qs, 4)
+        assert np.array_equal(got["index"], want["index"][perm])
+    assert state() == 2, "a shuffled batch should go back to the device-wide sort"
+    for _ in range(40):  # the global path measures again every 16th call
+        t.search_knn(q, 1)
+    assert state() == 1
+    r = t.search_radius(q[:50_000], 0.01)
+    offs, flat = oracle.OracleTree(pts, 10).search_radius(q[:50_000], 0.01)
+    assert np.array_equal(r._offsets, offs) and np.array_equal(r._flat["index"][:len(flat)], flat["index"])
