@@ -525,6 +525,7 @@ struct CallCtx {
   // a few block slots free lets the small ordering kernels of the next chunk start at once instead of waiting
   // for traversal blocks to drain (profiles/r2/host_pipeline_timeline.txt)
   int blocks_per_sm_cap = 0;
+  bool pipelined = false;  // a chunk of the host pipeline: always the device-wide sort (see knn_batch)
   int mark(int i) {
     if (!async && timed) PICO_CUDA(cudaEventRecord(ev[i], st));
     return 0;
@@ -810,7 +811,7 @@ __global__ void __launch_bounds__(kTileThreads) tile_order_kernel(const T* __res
                                                                  int dims, T lo0, T lo1, T lo2, T inv0, T inv1, T inv2,
                                                                  uint32_t* __restrict__ perm,
                                                                  unsigned long long* __restrict__ stat) {
-  using Sort = cub::BlockRadixSort<uint32_t, kTileThreads, kTileItems, uint16_t>;
+  using Sort = cub::BlockRadixSort<uint32_t, kTileThreads, kTileItems, uint16_t, 6>;  // 6-bit digits: 4 passes
   __shared__ typename Sort::TempStorage sort_tmp;
   __shared__ uint32_t cells[1024];  // bitmap over the 2^15 coarse cells
   const uint32_t base = blockIdx.x * (uint32_t)kTile;
@@ -920,22 +921,22 @@ int make_perm(CallCtx& c, const pico_b200_tree* t, const T* d_q, size_t stride, 
   const int bits = morton_bits(single_neighbour);
   *perm = nullptr;
   if ((flags & PICO_B200_NO_REORDER) || nq < 2048) return 0;
-  const bool local = order_locally(t);
+  const bool local = !c.pipelined && order_locally(t);
   // every 16th call of a tree that keeps the global sort measures the batch again (one extra small kernel)
-  const bool probe = !local && order_mode() == 0 && (t->order_hint.calls.fetch_add(1, std::memory_order_relaxed) % 16 == 0);
+  const bool probe = !local && !c.pipelined && order_mode() == 0 && (t->order_hint.calls.fetch_add(1, std::memory_order_relaxed) % 16 == 0);
   PermPlan plan;
   if (!local) PICO_TRY(plan_perm(nq, bits, &plan));
   const size_t arr = (nq * 4 + 255) & ~(size_t)255;
   char* ws = nullptr;
-  // (the permutation first: CUB's temporary storage at the end of the scratch area has no particular size)
-  PICO_TRY(c.alloc(reinterpret_cast<void**>(&ws), arr + (local ? 0 : plan.scratch_bytes()) + (probe ? arr : 0)));
+  // layout: the permutation, [the probe's permutation,] the sort's scratch arrays, CUB's temporary storage last
+  // (it has no particular size, nothing may be placed behind it)
+  PICO_TRY(c.alloc(reinterpret_cast<void**>(&ws), arr + (probe ? arr : 0) + (local ? 0 : plan.scratch_bytes())));
   uint32_t* out = reinterpret_cast<uint32_t*>(ws);
   if (local) {
     PICO_TRY(enqueue_tile_order<T>(c.st, t, d_q, stride, nq, out));
   } else {
-    PICO_TRY(enqueue_perm<T>(c.st, t, d_q, stride, nq, bits, plan, ws + arr, out));
-    if (probe)
-      PICO_TRY(enqueue_tile_order<T>(c.st, t, d_q, stride, nq, reinterpret_cast<uint32_t*>(ws + arr + plan.scratch_bytes())));
+    PICO_TRY(enqueue_perm<T>(c.st, t, d_q, stride, nq, bits, plan, ws + arr + (probe ? arr : 0), out));
+    if (probe) PICO_TRY(enqueue_tile_order<T>(c.st, t, d_q, stride, nq, reinterpret_cast<uint32_t*>(ws + arr)));
   }
   *perm = out;
   return 0;
@@ -1416,8 +1417,9 @@ int knn_batch(const pico_b200_tree* t, const T* q, size_t nq, size_t stride, siz
     char* perm_scratch = nullptr;
     uint32_t* perm_all = nullptr;
     const int perm_bits = morton_bits(k == 1);
-    // (a batch that is ordered tile by tile needs one small kernel per chunk: that stays on the chunk's own stream)
-    const bool hp_order = ahead && host_priority_order() && !(flags & PICO_B200_NO_REORDER) && !order_locally(t);
+    // (the chunks always take the device-wide sort: the tile kernel's 96-register blocks wait longer for room
+    // among the traversal blocks than the sort's kernels do — 2.68 against 2.46 ms, profiles/r2/order_sweep_v1.txt)
+    const bool hp_order = ahead && host_priority_order() && !(flags & PICO_B200_NO_REORDER);
     if (ahead) {
       PICO_TRY(cp.init(t->device));
       cp.timed = false;
@@ -1488,6 +1490,7 @@ int knn_batch(const pico_b200_tree* t, const T* q, size_t nq, size_t stride, siz
       CallCtx& c = ctx[ci % n_streams];
       c.timed = timeline;
       c.blocks_per_sm_cap = hp_order ? host_traversal_blocks() : 0;
+      c.pipelined = true;
       c.release();
       cpu_at[2 * ci] = cpu_ms();
       if (ahead) {
