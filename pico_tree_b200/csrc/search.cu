@@ -811,7 +811,7 @@ __global__ void __launch_bounds__(kTileThreads) tile_order_kernel(const T* __res
                                                                  int dims, T lo0, T lo1, T lo2, T inv0, T inv1, T inv2,
                                                                  uint32_t* __restrict__ perm,
                                                                  unsigned long long* __restrict__ stat) {
-  using Sort = cub::BlockRadixSort<uint32_t, kTileThreads, kTileItems, uint16_t, 6>;  // 6-bit digits: 4 passes
+  using Sort = cub::BlockRadixSort<uint32_t, kTileThreads, kTileItems, uint16_t>;  // (6-bit digits: 124 registers, no faster)
   __shared__ typename Sort::TempStorage sort_tmp;
   __shared__ uint32_t cells[1024];  // bitmap over the 2^15 coarse cells
   const uint32_t base = blockIdx.x * (uint32_t)kTile;
@@ -921,9 +921,10 @@ int make_perm(CallCtx& c, const pico_b200_tree* t, const T* d_q, size_t stride, 
   const int bits = morton_bits(single_neighbour);
   *perm = nullptr;
   if ((flags & PICO_B200_NO_REORDER) || nq < 2048) return 0;
-  const bool local = !c.pipelined && order_locally(t);
+  // (k > 1 keeps the 24-bit device-wide order: 6.71 against 6.77 ms at k = 16, profiles/r2/order_sweep_v2.txt)
+  const bool local = !c.pipelined && single_neighbour && order_locally(t);
   // every 16th call of a tree that keeps the global sort measures the batch again (one extra small kernel)
-  const bool probe = !local && !c.pipelined && order_mode() == 0 && (t->order_hint.calls.fetch_add(1, std::memory_order_relaxed) % 16 == 0);
+  const bool probe = !local && !c.pipelined && single_neighbour && order_mode() == 0 && (t->order_hint.calls.fetch_add(1, std::memory_order_relaxed) % 16 == 0);
   PermPlan plan;
   if (!local) PICO_TRY(plan_perm(nq, bits, &plan));
   const size_t arr = (nq * 4 + 255) & ~(size_t)255;

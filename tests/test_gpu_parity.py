@@ -825,16 +825,22 @@ def test_query_ordering_adapts_to_the_batch(pt, oracle):
         return s.value
 
     assert state() == 0
-    for _ in range(3):
-        got = t.search_knn(q, 4)
-        assert np.array_equal(got["index"], want["index"]) and np.array_equal(got["distance"], want["distance"])
-    assert state() == 1, "a scan-order batch should be ordered tile by tile"
+    states = []
+    for _ in range(3):  # single-neighbour searches measure and use the tile order
+        got = t.search_knn(q, 1)
+        assert np.array_equal(got["index"], want["index"][:, :1]) and np.array_equal(got["distance"], want["distance"][:, :1])
+        states.append(state())
+    assert states[-1] == 1, ("a scan-order batch should be ordered tile by tile", states)
+    got = t.search_knn(q, 4)
+    assert np.array_equal(got["index"], want["index"]) and np.array_equal(got["distance"], want["distance"])
     perm = np.random.default_rng(0).permutation(len(q))
     qs = np.ascontiguousarray(q[perm])
+    states = []
     for _ in range(3):
-        got = t.search_knn(qs, 4)
-        assert np.array_equal(got["index"], want["index"][perm])
-    assert state() == 2, "a shuffled batch should go back to the device-wide sort"
+        got = t.search_knn(qs, 1)
+        assert np.array_equal(got["index"], want["index"][perm][:, :1])
+        states.append(state())
+    assert states[-1] == 2, ("a shuffled batch should go back to the device-wide sort", states)
     for _ in range(40):  # the global path measures again every 16th call
         t.search_knn(q, 1)
     assert state() == 1
