@@ -802,8 +802,8 @@ int enqueue_perm(cudaStream_t st, const pico_b200_tree* t, const T* d_q, size_t 
 // the Morton kernel + two device-wide radix passes): on the cfg2 scan-order batch the 32 queries of a warp then
 // share 5.7 cells of 0.25 m on average, against 9.0 after the global 16-bit sort and 5.3 after a global 24-bit
 // sort (input order: 25.8; profiles/r2/order_quality.txt). It also says how coherent the batch was: the number of
-// distinct coarse cells (top 15 code bits) per tile, summed into `stat`. A shuffled batch has ~2000 per tile and
-// gains nothing from a local sort; pico_b200_order_hint remembers that and such trees keep the global sort.
+// distinct coarse cells (top 15 code bits) that 32 consecutive sorted ranks — one traversal warp — touch, summed
+// into `stat`. A shuffled batch touches ~32 and gains nothing from a local sort; pico_b200_order_hint remembers that and such trees keep the global sort.
 constexpr int kTileItems = 16, kTileThreads = 128, kTile = kTileItems * kTileThreads;
 
 template <typename T>
@@ -813,10 +813,7 @@ __global__ void __launch_bounds__(kTileThreads) tile_order_kernel(const T* __res
                                                                  unsigned long long* __restrict__ stat) {
   using Sort = cub::BlockRadixSort<uint32_t, kTileThreads, kTileItems, uint16_t>;  // (6-bit digits: 124 registers, no faster)
   __shared__ typename Sort::TempStorage sort_tmp;
-  __shared__ uint32_t cells[1024];  // bitmap over the 2^15 coarse cells
   const uint32_t base = blockIdx.x * (uint32_t)kTile;
-  for (int i = threadIdx.x; i < 1024; i += kTileThreads) cells[i] = 0;
-  __syncthreads();
   const T l[3] = {lo0, lo1, lo2}, s[3] = {inv0, inv1, inv2};
   uint32_t keys[kTileItems];
   uint16_t vals[kTileItems];
@@ -835,29 +832,24 @@ __global__ void __launch_bounds__(kTileThreads) tile_order_kernel(const T* __res
           code |= spread10((uint32_t)f) << j;
         }
       }
-      atomicOr(&cells[code >> 20], 1u << ((code >> 15) & 31u));
     }
     keys[i] = code;
     vals[i] = (uint16_t)local;
   }
   Sort(sort_tmp).SortBlockedToStriped(keys, vals, 6, 32);  // (the arrangement going in does not matter to a sort)
+  // thread t now holds ranks t, t + 128, ...: the 32 lanes of a warp hold 32 consecutive ranks for every i —
+  // exactly the groups of queries a traversal warp will work on. Count the coarse cells such a group touches.
+  uint32_t cells = 0;
 #pragma unroll
   for (int i = 0; i < kTileItems; ++i) {
     const uint32_t rank = (uint32_t)i * kTileThreads + threadIdx.x;
     if (base + rank < nq) perm[base + rank] = base + vals[i];  // valid entries sort in front of the padding
+    const uint32_t c = keys[i] >> 15, prev = __shfl_up_sync(0xffffffffu, c, 1);
+    cells += __popc(__ballot_sync(0xffffffffu, (threadIdx.x & 31) == 0 || c != prev));
   }
-  __syncthreads();
-  uint32_t distinct = 0;
-  for (int i = threadIdx.x; i < 1024; i += kTileThreads) distinct += __popc(cells[i]);
-  for (int o = 16; o > 0; o >>= 1) distinct += __shfl_down_sync(0xffffffffu, distinct, o);
-  // one word: tiles in the top 24 bits, cells below (chunks of one call measure into the same word from several
-  // streams; a single word cannot be seen half-updated)
-  __shared__ uint32_t block_distinct;
-  if (threadIdx.x == 0) block_distinct = 0;
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0 && distinct) atomicAdd(&block_distinct, distinct);
-  __syncthreads();
-  if (threadIdx.x == 0) atomicAdd(stat, (1ull << 40) + (unsigned long long)block_distinct);
+  // one word: groups in the top 24 bits, cells below (several streams may measure into the same word; a single
+  // word cannot be seen half-updated)
+  if ((threadIdx.x & 31) == 0) atomicAdd(stat, ((unsigned long long)kTileItems << 40) + (unsigned long long)cells);
 }
 
 // PICO_B200_ORDER (tuning hook): "auto" (default: per-tree hint), "global", "local"
@@ -871,7 +863,7 @@ int order_mode() {
   return v;
 }
 
-constexpr unsigned long long kCoherentCellsPerTile = 160;  // scan-order cfg2: ~20; shuffled: ~1900
+constexpr unsigned long long kCoherentCellsPerGroup = 8;  // coarse cells per 32 consecutive ranks: a scan ~1-3, shuffled ~32
 
 // Reads what the last measured batch looked like and decides for this call: true = tile-local order.
 bool order_locally(const pico_b200_tree* t) {
@@ -881,7 +873,7 @@ bool order_locally(const pico_b200_tree* t) {
   if (h.h_stat) {
     const unsigned long long word = reinterpret_cast<volatile unsigned long long*>(h.h_stat)[0];
     const unsigned long long sum = word & ((1ull << 40) - 1), tiles = word >> 40;
-    if (tiles > 0) h.state.store(sum <= tiles * kCoherentCellsPerTile ? 1 : 2, std::memory_order_relaxed);
+    if (tiles > 0) h.state.store(sum <= tiles * kCoherentCellsPerGroup ? 1 : 2, std::memory_order_relaxed);
   }
   return h.state.load(std::memory_order_relaxed) == 1;
 }
