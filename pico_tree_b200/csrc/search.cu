@@ -798,7 +798,7 @@ int enqueue_perm(cudaStream_t st, const pico_b200_tree* t, const T* d_q, size_t 
 // Batches usually arrive in an order that is already coherent at a coarse scale (a LiDAR scan, a raster, the
 // output of a previous spatial pass): consecutive queries lie in the same region, only not next to each other.
 // Then a global sort is more than is needed. tile_order_kernel sorts every tile of 2048 consecutive queries by its
-// Morton code on its own (one block, one cub::BlockRadixSort over 24 bits, no global pass, ONE launch instead of
+// Morton code on its own (one block, one cub::BlockRadixSort over 20 bits, no global pass, ONE launch instead of
 // the Morton kernel + two device-wide radix passes): on the cfg2 scan-order batch the 32 queries of a warp then
 // share 5.7 cells of 0.25 m on average, against 9.0 after the global 16-bit sort and 5.3 after a global 24-bit
 // sort (input order: 25.8; profiles/r2/order_quality.txt). It also says how coherent the batch was: the number of
@@ -836,7 +836,13 @@ __global__ void __launch_bounds__(kTileThreads) tile_order_kernel(const T* __res
     keys[i] = code;
     vals[i] = (uint16_t)local;
   }
-  Sort(sort_tmp).SortBlockedToStriped(keys, vals, 6, 32);  // (the arrangement going in does not matter to a sort)
+  // (the arrangement going in does not matter to a sort.) 20 bits = cells of ~1/128 of the extent per dimension are
+  // as fine as a warp of 32 queries can use: five 4-bit passes. Only a partial last tile needs the two top bits,
+  // which keep its padding behind the valid entries.
+  if (base + kTile <= nq)
+    Sort(sort_tmp).SortBlockedToStriped(keys, vals, 10, 30);
+  else
+    Sort(sort_tmp).SortBlockedToStriped(keys, vals, 10, 32);
   // thread t now holds ranks t, t + 128, ...: the 32 lanes of a warp hold 32 consecutive ranks for every i —
   // exactly the groups of queries a traversal warp will work on. Count the coarse cells such a group touches.
   uint32_t cells = 0;
