@@ -59,7 +59,8 @@ def config_dict(n_tree, n_query, k, n_gpus, extra=None):
                     "tree %d pts, %d queries/GPU, knn=%d, max_leaf_size=10, metric_l2_squared, "
                     "sliding_midpoint_max_side" % (n_tree, n_query, k),
         "n_tree": n_tree, "n_query_per_gpu": n_query, "k": k, "max_leaf_size": 10,
-        "query_order": "scan order on input; Z-ordered on device inside the timed step",
+        "query_order": "scan order on input; Z-ordered on device inside the timed step (tile by tile once the tree has "
+                       "measured that batches arrive locally coherent: pico_b200_tree_order_state)",
         "parallelism": "tree replicated (NCCL broadcast once), queries sharded x%d" % n_gpus,
         "l2": "inputs exceed L2 (tree 167 MB + queries 86 MB + results 58 MB vs 126 MB L2); no flush between steps",
     }
@@ -497,11 +498,10 @@ def run_ours(args, n_tree, n_query):
                 "e2e_over_concurrent_floor": (floor_concurrent_ms / (e2e_s * 1e3)) if floor_concurrent_ms else None,
                 "host_binding": binding,
                 "pcie_floor_note": "one H2D of all queries + one D2H of all results issued together, best of 10"},
-        "gpu_launches": int(args.steps * ((2 if k == 1 and not args.warp_per_query else 1) +
-                                          (0 if args.no_reorder else 1))),
-        "gpu_launches_note": "own kernels per step: morton_kernel + the traversal (k = 1: nn_fat_kernel over the search "
-                             "image + the order-exact kernel on its tie list); CUB radix-sort passes of the Z-order "
-                             "step not counted",
+        "gpu_launches": int(args.steps * (1 + (0 if args.no_reorder else 1))),
+        "gpu_launches_note": "own kernels per step: the ordering kernel (tile_order_kernel once the tree has seen that "
+                             "batches arrive locally coherent, else morton_kernel + CUB's radix-sort passes, which are "
+                             "not counted) + the traversal kernel",
         "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "configs": configs,
     }
     print(json.dumps(line))

@@ -804,7 +804,7 @@ int enqueue_perm(cudaStream_t st, const pico_b200_tree* t, const T* d_q, size_t 
 // sort (input order: 25.8; profiles/r2/order_quality.txt). It also says how coherent the batch was: the number of
 // distinct coarse cells (top 15 code bits) that 32 consecutive sorted ranks — one traversal warp — touch, summed
 // into `stat`. A shuffled batch touches ~32 and gains nothing from a local sort; pico_b200_order_hint remembers that and such trees keep the global sort.
-constexpr int kTileItems = 16, kTileThreads = 128, kTile = kTileItems * kTileThreads;
+constexpr int kTileItems = 8, kTileThreads = 256, kTile = kTileItems * kTileThreads;
 
 template <typename T>
 __global__ void __launch_bounds__(kTileThreads) tile_order_kernel(const T* __restrict__ q, size_t stride, uint32_t nq,
@@ -1300,6 +1300,14 @@ bool host_priority_order() {
   }();
   return v;
 }
+// PICO_B200_HOST_LOCAL_ORDER=1 (tuning hook): chunks of the host pipeline may use the tile-local order too
+bool host_local_order() {
+  static const bool v = [] {
+    const char* e = getenv("PICO_B200_HOST_LOCAL_ORDER");
+    return e && atoi(e) != 0;
+  }();
+  return v;
+}
 // Block slots per SM a chunk's traversal may occupy while the pipeline orders the next chunks (0 = all).
 // PICO_B200_HOST_TRAV_BLOCKS is a tuning hook.
 constexpr int kHostTraversalBlocks = 0;
@@ -1418,7 +1426,8 @@ int knn_batch(const pico_b200_tree* t, const T* q, size_t nq, size_t stride, siz
     const int perm_bits = morton_bits(k == 1);
     // (the chunks always take the device-wide sort: the tile kernel's 96-register blocks wait longer for room
     // among the traversal blocks than the sort's kernels do — 2.68 against 2.46 ms, profiles/r2/order_sweep_v1.txt)
-    const bool hp_order = ahead && host_priority_order() && !(flags & PICO_B200_NO_REORDER);
+    const bool chunks_local = host_local_order() && k == 1 && order_locally(t);
+    const bool hp_order = ahead && host_priority_order() && !(flags & PICO_B200_NO_REORDER) && !chunks_local;
     if (ahead) {
       PICO_TRY(cp.init(t->device));
       cp.timed = false;
@@ -1489,7 +1498,7 @@ int knn_batch(const pico_b200_tree* t, const T* q, size_t nq, size_t stride, siz
       CallCtx& c = ctx[ci % n_streams];
       c.timed = timeline;
       c.blocks_per_sm_cap = hp_order ? host_traversal_blocks() : 0;
-      c.pipelined = true;
+      c.pipelined = !chunks_local;
       c.release();
       cpu_at[2 * ci] = cpu_ms();
       if (ahead) {
