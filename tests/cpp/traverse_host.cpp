@@ -40,6 +40,7 @@ static inline float4 __ldg(const float4* p) {
 #include "../../pico_tree_b200/csrc/traverse.cuh"
 
 // stack statistics (pushes, pops, deepest stack) for tests/test_traverse_host.py
+static thread_local unsigned long long g_knn_visits = 0, g_knn_inserts = 0;
 static thread_local unsigned long long g_push = 0, g_pop = 0, g_max_sp_sum = 0, g_sp_hist[8] = {0};
 template <typename T>
 struct CountingStack {
@@ -116,7 +117,13 @@ void knn_packed(const void* nodes, const void* pts4, const T* q, size_t nq, int 
       idx[i] = vis.idx;
       dist[i] = vis.best;
     } else {
-      VisitKnn<T, 16> vis;
+      struct CountingKnn : VisitKnn<T, 16> {
+        void visit(int i, T x) {
+          ++g_knn_visits;
+          if (this->d[15] > x) ++g_knn_inserts;
+          VisitKnn<T, 16>::visit(i, x);
+        }
+      } vis;
       vis.init(k);
       traverse_packed<T, DIM, true, kPrimeBound>(static_cast<const NodeT*>(nodes), static_cast<const V4*>(pts4), nullptr,
                                                  qq, 0, false, T(1), st, vis, n_points, k);
@@ -171,6 +178,11 @@ void host_take_stack_stats(unsigned long long* out11) {
   out11[0] = g_push; out11[1] = g_pop; out11[2] = g_max_sp_sum;
   for (int i = 0; i < 8; ++i) { out11[3 + i] = g_sp_hist[i]; g_sp_hist[i] = 0; }
   g_push = g_pop = g_max_sp_sum = 0;
+}
+void host_take_knn_stats(unsigned long long* out2) {
+  out2[0] = g_knn_visits;
+  out2[1] = g_knn_inserts;
+  g_knn_visits = g_knn_inserts = 0;
 }
 unsigned long long host_take_point_loads() {
   const unsigned long long v = g_loads_pts;
