@@ -526,6 +526,7 @@ struct CallCtx {
   // for traversal blocks to drain (profiles/r2/host_pipeline_timeline.txt)
   int blocks_per_sm_cap = 0;
   bool pipelined = false;  // a chunk of the host pipeline: always the device-wide sort (see knn_batch)
+  bool fused_order = false;  // exact nn may order and traverse in one kernel (nn_tile_kernel)
   int mark(int i) {
     if (!async && timed) PICO_CUDA(cudaEventRecord(ev[i], st));
     return 0;
@@ -858,6 +859,67 @@ __global__ void __launch_bounds__(kTileThreads) tile_order_kernel(const T* __res
   if ((threadIdx.x & 31) == 0) atomicAdd(stat, ((unsigned long long)kTileItems << 40) + (unsigned long long)cells);
 }
 
+// ---- order and traverse in one kernel (k = 1, metric_l2_squared, batches that arrive locally coherent)
+// Each block takes a tile of kFusedTile consecutive queries, Z-orders it in shared memory (keys = 20 code bits with the
+// local index packed below them: a keys-only block radix sort) and then walks the tree for its queries, every warp
+// over 32 consecutive ranks. No permutation array, no ordering kernel in front: in the host pipeline a chunk's
+// traversal no longer waits for a chain of small sort kernels that cannot find room among the traversal blocks of the
+// chunks before it (profiles/r2/host_pipeline_timeline.txt). The tile is smaller than tile_order_kernel's (512 against
+// 2048: a warp then touches ~9.0 cells of 0.25 m, what the device-wide 16-bit order gives, profiles/r2/order_quality.txt)
+// because every thread walks kFusedItems queries one after the other.
+constexpr int kFusedItems = 4, kFusedTile = kFusedItems * kThreadsPerBlock;
+
+template <typename T, int DIM>
+__global__ void __launch_bounds__(kThreadsPerBlock, 2048 / kThreadsPerBlock) nn_tile_kernel(KnnArgs<T> a, T lo0, T lo1, T lo2,
+                                                                                            T inv0, T inv1, T inv2) {
+  using Sort = cub::BlockRadixSort<uint32_t, kThreadsPerBlock, kFusedItems>;
+  __shared__ union {
+    typename Sort::TempStorage sort;
+    uint16_t order[kFusedTile];
+  } sm;
+  const uint32_t base = blockIdx.x * (uint32_t)kFusedTile;
+  const T l[3] = {lo0, lo1, lo2}, s[3] = {inv0, inv1, inv2};
+  uint32_t keys[kFusedItems];
+#pragma unroll
+  for (int i = 0; i < kFusedItems; ++i) {
+    const uint32_t local = (uint32_t)i * kThreadsPerBlock + threadIdx.x;
+    uint32_t key = 0xFFFFF000u | local;  // past the end of the batch: behind every valid entry
+    if (base + local < a.nq) {
+      const T* p = a.q + (size_t)(base + local) * a.q_stride;
+      uint32_t code = 0;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        if (j < DIM) {
+          T f = (p[j] - l[j]) * s[j];
+          f = f < T(0) ? T(0) : (f > T(1023) ? T(1023) : f);
+          code |= spread10((uint32_t)f) << j;
+        }
+      }
+      key = ((code >> 10) << 12) | local;
+    }
+    keys[i] = key;
+  }
+  Sort(sm.sort).SortBlockedToStriped(keys, 12, 32);
+  __syncthreads();  // the sort's storage becomes the order array
+#pragma unroll
+  for (int i = 0; i < kFusedItems; ++i) sm.order[i * kThreadsPerBlock + threadIdx.x] = (uint16_t)(keys[i] & 0xFFFu);
+  __syncthreads();
+  for (int i = 0; i < kFusedItems; ++i) {
+    const uint32_t qi = base + sm.order[i * kThreadsPerBlock + threadIdx.x];
+    if (qi >= a.nq) continue;
+    T q[DIM];
+    const T* qp = a.q + (size_t)qi * a.q_stride;
+#pragma unroll
+    for (int j = 0; j < DIM; ++j) q[j] = qp[j];
+    VisitNn<T> vis;
+    LocalStack<T, DIM, kLocalStack> st;
+    traverse_packed<T, DIM, true, kPrimeFirstLeaf>(a.nodes, a.pts4, a.outer, q, a.metric, false, a.e_inv, st, vis);
+    Neighbor<T>* out = a.out + qi;
+    out->index = vis.idx;
+    out->distance = vis.best;
+  }
+}
+
 // PICO_B200_ORDER (tuning hook): "auto" (default: per-tree hint), "global", "local"
 int order_mode() {
   static const int v = [] {
@@ -1130,9 +1192,39 @@ int knn_enqueue(CallCtx& c, const pico_b200_tree* t, const T* q, size_t nq, size
   if (!on_device) PICO_TRY(c.alloc(reinterpret_cast<void**>(&d_out), nq * k * sizeof(Neighbor<T>)));
   PICO_TRY(c.mark(1));
   uint32_t* perm = const_cast<uint32_t*>(perm_in);
-  if (!have_perm) PICO_TRY(make_perm(c, t, d_q, d_stride, nq, flags, &perm, k == 1));
+  // order-and-traverse in one kernel (nn_tile_kernel): exact nn, packed float/double points, sdim 2 or 3, a tree the
+  // local stack can hold, and a batch the tree expects to be locally coherent
+  const bool fused = c.fused_order && !have_perm && k == 1 && !(e > 0) && t->metric == PICO_B200_METRIC_L2_SQUARED &&
+                     t->packed() && t->sdim >= 2 && t->height < (size_t)kLocalStack && nq >= 2048 &&
+                     !(flags & (PICO_B200_NO_REORDER | PICO_B200_WARP_PER_QUERY)) && nn_mode() == 0;
+  if (!have_perm && !fused) PICO_TRY(make_perm(c, t, d_q, d_stride, nq, flags, &perm, k == 1));
   PICO_TRY(c.mark(2));
   PICO_TRY(c.span_begin());
+  if (fused) {
+    KnnArgs<T> a;
+    fill_base(a, t, d_q, d_stride, nq, nullptr, e);
+    a.out = d_out;
+    a.k = 1;
+    T lo[3] = {0, 0, 0}, inv[3] = {0, 0, 0};
+    for (int j = 0; j < (int)t->sdim; ++j) {
+      lo[j] = (T)t->root_box_host[j];
+      const double ext = t->root_box_host[4 + j] - t->root_box_host[j];
+      inv[j] = ext > 0 ? (T)(1023.999 / ext) : T(0);
+    }
+    const unsigned tiles = (unsigned)((nq + kFusedTile - 1) / kFusedTile);
+    if (t->sdim == 2)
+      nn_tile_kernel<T, 2><<<tiles, kThreadsPerBlock, 0, c.st>>>(a, lo[0], lo[1], lo[2], inv[0], inv[1], inv[2]);
+    else
+      nn_tile_kernel<T, 3><<<tiles, kThreadsPerBlock, 0, c.st>>>(a, lo[0], lo[1], lo[2], inv[0], inv[1], inv[2]);
+    PICO_CUDA(cudaGetLastError());
+    PICO_TRY(c.span_end());
+    *launches += 1;
+    PICO_TRY(c.mark(3));
+    if (!on_device)
+      PICO_CUDA(cudaMemcpyAsync(out, d_out, nq * k * sizeof(Neighbor<T>), cudaMemcpyDeviceToHost, c.st));
+    PICO_TRY(c.mark(4));
+    return 0;
+  }
 
   KnnArgs<T> a;
   fill_base(a, t, d_q, d_stride, nq, perm, e);
@@ -1300,6 +1392,22 @@ bool host_priority_order() {
   }();
   return v;
 }
+// PICO_B200_FUSED=1 (tuning hook): non-pipelined calls order and traverse in one kernel as well
+bool resident_fused_order() {
+  static const bool v = [] {
+    const char* e = getenv("PICO_B200_FUSED");
+    return e && atoi(e) != 0;
+  }();
+  return v;
+}
+// PICO_B200_HOST_FUSED=0 (tuning hook): chunks of the host pipeline never use nn_tile_kernel
+bool host_fused_order() {
+  static const bool v = [] {
+    const char* e = getenv("PICO_B200_HOST_FUSED");
+    return !(e && atoi(e) == 0);
+  }();
+  return v;
+}
 // PICO_B200_HOST_LOCAL_ORDER=1 (tuning hook): chunks of the host pipeline may use the tile-local order too
 bool host_local_order() {
   static const bool v = [] {
@@ -1426,8 +1534,14 @@ int knn_batch(const pico_b200_tree* t, const T* q, size_t nq, size_t stride, siz
     const int perm_bits = morton_bits(k == 1);
     // (the chunks always take the device-wide sort: the tile kernel's 96-register blocks wait longer for room
     // among the traversal blocks than the sort's kernels do — 2.68 against 2.46 ms, profiles/r2/order_sweep_v1.txt)
-    const bool chunks_local = host_local_order() && k == 1 && order_locally(t);
-    const bool hp_order = ahead && host_priority_order() && !(flags & PICO_B200_NO_REORDER) && !chunks_local;
+    // A batch the tree expects to be locally coherent (pico_b200_order_hint) is ordered INSIDE the traversal kernel,
+    // tile by tile (nn_tile_kernel): no ordering kernels between a chunk's upload and its traversal. Every 16th call
+    // (and while nothing is known yet) the first chunk is measured with tile_order_kernel on the side.
+    const bool chunks_fused = host_fused_order() && k == 1 && order_locally(t);
+    const bool chunks_local = !chunks_fused && host_local_order() && k == 1 && order_locally(t);
+    const bool hp_order = ahead && host_priority_order() && !(flags & PICO_B200_NO_REORDER) && !chunks_local && !chunks_fused;
+    const bool probe_first = ahead && k == 1 && order_mode() == 0 && !(flags & PICO_B200_NO_REORDER) && t->packed() &&
+                             (t->order_hint.calls.fetch_add(1, std::memory_order_relaxed) % 16 == 0);
     if (ahead) {
       PICO_TRY(cp.init(t->device));
       cp.timed = false;
@@ -1499,6 +1613,7 @@ int knn_batch(const pico_b200_tree* t, const T* q, size_t nq, size_t stride, siz
       c.timed = timeline;
       c.blocks_per_sm_cap = hp_order ? host_traversal_blocks() : 0;
       c.pipelined = !chunks_local;
+      c.fused_order = chunks_fused;
       c.release();
       cpu_at[2 * ci] = cpu_ms();
       if (ahead) {
@@ -1513,6 +1628,11 @@ int knn_batch(const pico_b200_tree* t, const T* q, size_t nq, size_t stride, siz
         }
         if (!rc && cudaStreamWaitEvent(c.st, order_here ? ordered[ci] : ready[ci], 0) != cudaSuccess)
           rc = fail(PICO_B200_ERR_CUDA, "stream wait failed");
+        if (!rc && probe_first && ci == 0 && cnt >= 2048) {
+          uint32_t* scratch_perm = nullptr;
+          rc = c.alloc(reinterpret_cast<void**>(&scratch_perm), cnt * sizeof(uint32_t));
+          if (!rc) rc = enqueue_tile_order<T>(c.st, t, d_q_all + begin * sdim, sdim, cnt, scratch_perm);
+        }
         if (!rc)
           rc = knn_enqueue<T>(c, t, d_q_all + begin * sdim, cnt, sdim, k, e, d_out_all + begin * k, flags, true,
                               &launches, order_here ? perm_all + begin : nullptr, order_here);
@@ -1596,6 +1716,7 @@ int knn_batch(const pico_b200_tree* t, const T* q, size_t nq, size_t stride, siz
   }
   CallCtx c;
   PICO_TRY(c.init(t->device, want_async));
+  c.fused_order = resident_fused_order() && k == 1 && order_locally(t);
   PICO_TRY(knn_enqueue<T>(c, t, q, nq, stride, k, e, out, flags, on_device, &launches));
   if (c.async) return 0;
   PICO_CUDA(cudaStreamSynchronize(c.st));
