@@ -1342,7 +1342,7 @@ int knn_enqueue(CallCtx& c, const pico_b200_tree* t, const T* q, size_t nq, size
 }
 
 constexpr size_t kHostChunk = (size_t)1 << 20;  // queries per pipelined chunk (host buffers)
-constexpr int kHostStreams = 6;  // profiles/r1/e2e_sweep.txt: 1 Mi queries x 6 streams is the best point
+constexpr int kHostStreams = 4;  // profiles/r2/host_pipeline_sweep_r2_v6.txt (round 1, before nn_tile_kernel: 6)
 constexpr int kMaxHostStreams = 12;
 
 // tuning hooks (profiles/r1/e2e_sweep.txt): PICO_B200_HOST_CHUNK, PICO_B200_HOST_STREAMS
@@ -1364,7 +1364,7 @@ int host_streams() {
 }
 // The call ends one traversal + one D2H after the last chunk's H2D, so the tail of the batch is cut
 // into halving chunks down to this many queries (0 = equal chunks). PICO_B200_HOST_TAPER is a tuning hook.
-constexpr size_t kHostTaper = 0;
+constexpr size_t kHostTaper = 262144;  // profiles/r2/host_pipeline_sweep_r2_v5.txt, _v6.txt: 2.23 -> 2.16 ms
 size_t host_taper() {
   static const size_t v = [] {
     const char* e = getenv("PICO_B200_HOST_TAPER");
@@ -1427,7 +1427,7 @@ int host_traversal_blocks() {
   }();
   return v;
 }
-constexpr size_t kHostHead = 262144;
+constexpr size_t kHostHead = 131072;
 size_t host_head() {
   static const size_t v = [] {
     const char* e = getenv("PICO_B200_HOST_HEAD");
