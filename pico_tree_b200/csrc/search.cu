@@ -527,6 +527,7 @@ struct CallCtx {
   int blocks_per_sm_cap = 0;
   bool pipelined = false;  // a chunk of the host pipeline: always the device-wide sort (see knn_batch)
   bool fused_order = false;  // exact nn may order and traverse in one kernel (nn_tile_kernel)
+  bool probe_order = false;  // measure how coherent this batch arrives (tile_order_kernel on the side)
   int mark(int i) {
     if (!async && timed) PICO_CUDA(cudaEventRecord(ev[i], st));
     return 0;
@@ -1191,6 +1192,11 @@ int knn_enqueue(CallCtx& c, const pico_b200_tree* t, const T* q, size_t nq, size
   Neighbor<T>* d_out = out;
   if (!on_device) PICO_TRY(c.alloc(reinterpret_cast<void**>(&d_out), nq * k * sizeof(Neighbor<T>)));
   PICO_TRY(c.mark(1));
+  if (c.probe_order && nq >= 2048 && t->packed()) {
+    uint32_t* scratch_perm = nullptr;
+    PICO_TRY(c.alloc(reinterpret_cast<void**>(&scratch_perm), nq * sizeof(uint32_t)));
+    PICO_TRY(enqueue_tile_order<T>(c.st, t, d_q, d_stride, nq, scratch_perm));
+  }
   uint32_t* perm = const_cast<uint32_t*>(perm_in);
   // order-and-traverse in one kernel (nn_tile_kernel): exact nn, packed float/double points, sdim 2 or 3, a tree the
   // local stack can hold, and a batch the tree expects to be locally coherent
@@ -1540,7 +1546,7 @@ int knn_batch(const pico_b200_tree* t, const T* q, size_t nq, size_t stride, siz
     const bool chunks_fused = host_fused_order() && k == 1 && order_locally(t);
     const bool chunks_local = !chunks_fused && host_local_order() && k == 1 && order_locally(t);
     const bool hp_order = ahead && host_priority_order() && !(flags & PICO_B200_NO_REORDER) && !chunks_local && !chunks_fused;
-    const bool probe_first = ahead && k == 1 && order_mode() == 0 && !(flags & PICO_B200_NO_REORDER) && t->packed() &&
+    const bool probe_first = k == 1 && order_mode() == 0 && !(flags & PICO_B200_NO_REORDER) && t->packed() &&
                              (t->order_hint.calls.fetch_add(1, std::memory_order_relaxed) % 16 == 0);
     if (ahead) {
       PICO_TRY(cp.init(t->device));
@@ -1614,6 +1620,7 @@ int knn_batch(const pico_b200_tree* t, const T* q, size_t nq, size_t stride, siz
       c.blocks_per_sm_cap = hp_order ? host_traversal_blocks() : 0;
       c.pipelined = !chunks_local;
       c.fused_order = chunks_fused;
+      c.probe_order = probe_first && ci == 0;
       c.release();
       cpu_at[2 * ci] = cpu_ms();
       if (ahead) {
@@ -1628,11 +1635,7 @@ int knn_batch(const pico_b200_tree* t, const T* q, size_t nq, size_t stride, siz
         }
         if (!rc && cudaStreamWaitEvent(c.st, order_here ? ordered[ci] : ready[ci], 0) != cudaSuccess)
           rc = fail(PICO_B200_ERR_CUDA, "stream wait failed");
-        if (!rc && probe_first && ci == 0 && cnt >= 2048) {
-          uint32_t* scratch_perm = nullptr;
-          rc = c.alloc(reinterpret_cast<void**>(&scratch_perm), cnt * sizeof(uint32_t));
-          if (!rc) rc = enqueue_tile_order<T>(c.st, t, d_q_all + begin * sdim, sdim, cnt, scratch_perm);
-        }
+
         if (!rc)
           rc = knn_enqueue<T>(c, t, d_q_all + begin * sdim, cnt, sdim, k, e, d_out_all + begin * k, flags, true,
                               &launches, order_here ? perm_all + begin : nullptr, order_here);
