@@ -847,3 +847,50 @@ def test_query_ordering_adapts_to_the_batch(pt, oracle):
     r = t.search_radius(q[:50_000], 0.01)
     offs, flat = oracle.OracleTree(pts, 10).search_radius(q[:50_000], 0.01)
     assert np.array_equal(r._offsets, offs) and np.array_equal(r._flat["index"][:len(flat)], flat["index"])
+
+
+def test_host_pipeline_orders_inside_the_traversal_for_coherent_batches(pt, oracle):
+    """A scan-order batch from host memory: after the tree has measured one such batch, the chunks of the host pipeline
+    are ordered and searched by ONE kernel each (nn_tile_kernel). Pinned, padded and pageable buffers, against the
+    oracle; then a shuffled batch, which must fall back to the device-wide sort — same answers throughout."""
+    import ctypes as C
+
+    import torch
+    from pico_tree_b200 import _lib, datasets as D
+    L = _lib.lib()
+    pts = D.lidar_shape(500_000, seed=1)
+    nq = 2_700_000
+    q = D.lidar_shape(nq, seed=2, pose_shift=0.35)
+    t = pt.KdTree(pts, pt.Metric.L2Squared, 10)
+    want = oracle.OracleTree(pts, 10).search_knn(q, 1, threads=oracle.max_threads())
+
+    def state():
+        s = C.c_int(-1)
+        _lib.check(L.pico_b200_tree_order_state(t._h, C.byref(s)))
+        return s.value
+
+    qp = torch.from_numpy(q).pin_memory()
+    out = torch.zeros((nq, 2), dtype=torch.int32).pin_memory()
+    for call in range(3):  # call 0 measures, calls 1.. use the fused kernel
+        out.zero_()
+        _lib.check(L.pico_b200_knn(t._h, C.c_void_p(qp.data_ptr()), nq, 3, 1, 0.0, C.c_void_p(out.data_ptr()), 0, None))
+        got = out.numpy()
+        assert np.array_equal(got[:, 0], want["index"][:, 0]), call
+        assert np.array_equal(got[:, 1].view(np.float32), want["distance"][:, 0]), call
+    assert state() == 1
+    q4 = torch.zeros((nq, 4), dtype=torch.float32).pin_memory()
+    q4[:, :3] = torch.from_numpy(q)
+    out.zero_()
+    _lib.check(L.pico_b200_knn(t._h, C.c_void_p(q4.data_ptr()), nq, 4, 1, 0.0, C.c_void_p(out.data_ptr()), 0, None))
+    assert np.array_equal(out.numpy()[:, 0], want["index"][:, 0])
+    for _ in range(2):  # pageable
+        got = t.search_knn(q, 1)
+        assert np.array_equal(got["index"], want["index"]) and np.array_equal(got["distance"], want["distance"])
+    perm = np.random.default_rng(1).permutation(nq)
+    qs = torch.from_numpy(np.ascontiguousarray(q[perm])).pin_memory()
+    for call in range(20):  # the pipeline measures its first chunk every 16th call
+        out.zero_()
+        _lib.check(L.pico_b200_knn(t._h, C.c_void_p(qs.data_ptr()), nq, 3, 1, 0.0, C.c_void_p(out.data_ptr()), 0, None))
+        if call in (0, 19):
+            assert np.array_equal(out.numpy()[:, 0], want["index"][perm, 0]), call
+    assert state() == 2
