@@ -528,6 +528,7 @@ struct CallCtx {
   bool pipelined = false;  // a chunk of the host pipeline: always the device-wide sort (see knn_batch)
   bool fused_order = false;  // exact nn may order and traverse in one kernel (nn_tile_kernel)
   bool probe_order = false;  // measure how coherent this batch arrives (tile_order_kernel on the side)
+  int failed = 0;            // error code of a helper that reports through the context
   int mark(int i) {
     if (!async && timed) PICO_CUDA(cudaEventRecord(ev[i], st));
     return 0;
@@ -860,6 +861,139 @@ __global__ void __launch_bounds__(kTileThreads) tile_order_kernel(const T* __res
   if ((threadIdx.x & 31) == 0) atomicAdd(stat, ((unsigned long long)kTileItems << 40) + (unsigned long long)cells);
 }
 
+// ---- exact nn with the far subtrees as work items of the block (float, sdim 2 / 3, metric_l2_squared)
+// The thread-per-query traversal spends two thirds of its warp instructions below far children at ~3 of 32 lanes:
+// after the coherent part (first descent, first leaf, second walk — 29 lanes) every lane is left with 0..4 far
+// subtrees of its own, and a warp runs until its slowest lane is done. Here the coherent part only EMITS the far
+// children that can matter ({owner thread, node | split_dim << 30, offset}: on the first path the box distance is the
+// offset itself) into the block's slice of a global item array; after a barrier the 128 threads of the block take the
+// items one each, whoever emitted them, walk the subtree in the reference's order and fold what they find into the
+// owner's result with a 64-bit atomicMin on {index, distance} (distance in the high word: non-negative floats order
+// like unsigned integers). The subtrees of one query are then searched side by side against the best of the first
+// leaf instead of one after the other against a shrinking bound (more nodes visited, at four times the lanes), and
+// "first visited wins" is no longer decided by the traversal: a query whose best distance is attained twice — inside
+// one item (VisitNnTie), or across items (the atomicMin returns what it replaced) — is flagged in `redo` and re-run
+// by the order-exact kernel. So is a query of a block whose item slice overflowed.
+constexpr int kItemsPerBlock = 4 * kThreadsPerBlock;
+
+template <int DIM>
+__global__ void __launch_bounds__(kThreadsPerBlock, 2048 / kThreadsPerBlock) nn_split_kernel(KnnArgs<float> a,
+                                                                                             uint32_t* __restrict__ items,
+                                                                                             uint8_t* __restrict__ redo) {
+  using T = float;
+  constexpr int metric = PICO_B200_METRIC_L2_SQUARED;
+  __shared__ uint32_t n_items;
+  if (threadIdx.x == 0) n_items = 0;
+  __syncthreads();
+  uint32_t* my_items = items + (size_t)blockIdx.x * kItemsPerBlock * 3;
+  const uint32_t slot = blockIdx.x * kThreadsPerBlock + threadIdx.x;
+  if (slot < a.nq) {
+    const uint32_t qi = a.perm ? a.perm[slot] : slot;
+    T q[DIM];
+    const T* qp = a.q + (size_t)qi * a.q_stride;
+#pragma unroll
+    for (int j = 0; j < DIM; ++j) q[j] = qp[j];
+    // first descent, first leaf
+    T na, nb;
+    uint32_t right, sd, node = 0;
+    int lb, le;
+    load_node(a.nodes, node, na, nb, right, sd, lb, le);
+    while (sd != PICO_B200_LEAF) {
+      T v = q[0];
+#pragma unroll
+      for (int j = 1; j < DIM; ++j) v = (sd == (uint32_t)j) ? q[j] : v;
+      node = sub_rn(sub_rn(add_rn(na, nb), v), v) > T(0) ? node + 1 : right;
+      load_node(a.nodes, node, na, nb, right, sd, lb, le);
+    }
+    VisitNnTie<T> vis;
+    for (int i = lb; i < le; ++i) {
+      const float4 p = ldg4(a.pts4 + i);
+      T d = metric_first(metric, q[0], p.x);
+      if (DIM > 1) d = metric_fold(metric, d, q[DIM > 1 ? 1 : 0], p.y, 1);
+      if (DIM > 2) d = metric_fold(metric, d, q[DIM > 2 ? 2 : 0], p.z, 2);
+      vis.visit(index_of(p), d);
+    }
+    const T reach = add_rn(vis.best, mul_rn(vis.best, T(1.2207031e-4)));
+    // second walk: far children of the first path within reach become items (deepest last; the order is free now)
+    bool overflow = false;
+    node = 0;
+    load_node(a.nodes, node, na, nb, right, sd, lb, le);
+    while (sd != PICO_B200_LEAF) {
+      T v = q[0];
+#pragma unroll
+      for (int j = 1; j < DIM; ++j) v = (sd == (uint32_t)j) ? q[j] : v;
+      const bool go_left = sub_rn(sub_rn(add_rn(na, nb), v), v) > T(0);
+      const T t = sub_rn(go_left ? nb : na, v);
+      const T new_off = mul_rn(t, t);
+      if (reach >= new_off) {
+        const uint32_t pos = atomicAdd(&n_items, 1u);
+        if (pos < (uint32_t)kItemsPerBlock) {
+          my_items[3 * pos] = threadIdx.x;
+          my_items[3 * pos + 1] = (go_left ? right : node + 1) | (sd << 30);
+          my_items[3 * pos + 2] = __float_as_uint(new_off);
+        } else {
+          overflow = true;
+        }
+      }
+      node = go_left ? node + 1 : right;
+      load_node(a.nodes, node, na, nb, right, sd, lb, le);
+    }
+    Neighbor<T>* out = a.out + qi;
+    out->index = vis.idx;
+    out->distance = vis.best;
+    if (vis.tie || overflow) redo[qi] = 1;
+  }
+  __syncthreads();
+  const uint32_t n = min(n_items, (uint32_t)kItemsPerBlock);
+  for (uint32_t j = threadIdx.x; j < n; j += kThreadsPerBlock) {
+    const uint32_t owner = my_items[3 * j], tag = my_items[3 * j + 1];
+    const T new_off = __uint_as_float(my_items[3 * j + 2]);
+    const uint32_t oslot = blockIdx.x * kThreadsPerBlock + owner;
+    const uint32_t qi = a.perm ? a.perm[oslot] : oslot;
+    T q[DIM];
+    const T* qp = a.q + (size_t)qi * a.q_stride;
+#pragma unroll
+    for (int jj = 0; jj < DIM; ++jj) q[jj] = qp[jj];
+    unsigned long long* cell = reinterpret_cast<unsigned long long*>(a.out + qi);
+    const unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(cell);
+    VisitNnTie<T> vis;
+    vis.best = __uint_as_float((uint32_t)(cur >> 32));
+    vis.idx = (int)(uint32_t)cur;
+    const T start_best = vis.best;
+    T off[DIM];
+    const uint32_t sd = tag >> 30;
+#pragma unroll
+    for (int jj = 0; jj < DIM; ++jj) off[jj] = (sd == (uint32_t)jj) ? new_off : T(0);
+    LocalStack<T, DIM, kLocalStack> st;
+    traverse_subtree<T, DIM>(a.nodes, a.pts4, q, tag & kTagNodeMask, new_off, off, mul_rn(vis.best, T(1.2207031e-4)), st,
+                             vis);
+    bool tie = vis.tie;
+    if (vis.best < start_best) {
+      const unsigned long long mine = ((unsigned long long)__float_as_uint(vis.best) << 32) | (uint32_t)vis.idx;
+      const unsigned long long old = atomicMin(cell, mine);
+      tie = tie || ((uint32_t)(old >> 32) == __float_as_uint(vis.best) && (uint32_t)old != (uint32_t)vis.idx);
+    }
+    if (tie) redo[qi] = 1;
+  }
+}
+
+// The flagged queries of nn_split_kernel, once more through the order-exact traversal.
+template <int DIM>
+__global__ void __launch_bounds__(kThreadsPerBlock) nn_redo_kernel(KnnArgs<float> a, const uint8_t* __restrict__ redo) {
+  using T = float;
+  const uint32_t qi = blockIdx.x * kThreadsPerBlock + threadIdx.x;
+  if (qi >= a.nq || !redo[qi]) return;
+  T q[DIM];
+  const T* qp = a.q + (size_t)qi * a.q_stride;
+#pragma unroll
+  for (int j = 0; j < DIM; ++j) q[j] = qp[j];
+  VisitNn<T> vis;
+  LocalStack<T, DIM, kLocalStack> st;
+  traverse_packed<T, DIM, true, kPrimeFirstLeaf>(a.nodes, a.pts4, a.outer, q, a.metric, false, a.e_inv, st, vis);
+  a.out[qi].index = vis.idx;
+  a.out[qi].distance = vis.best;
+}
+
 // ---- order and traverse in one kernel (k = 1, metric_l2_squared, batches that arrive locally coherent)
 // Each block takes a tile of kFusedTile consecutive queries, Z-orders it in shared memory (keys = 20 code bits with the
 // local index packed below them: a keys-only block radix sort) and then walks the tree for its queries, every warp
@@ -1163,14 +1297,45 @@ void launch_knn_thread(const KnnArgs<T>& a, bool fast, bool deep, unsigned block
 // (profiles/r2/nn_sweep_*.txt); bit 0 = nn_kernel (three-word slot stack in shared memory, restore records);
 // bit 1 = far children are walked in the search image too (default: in the real tree); bit 2 = no prefix-minimum
 // restart records; bit 3 = ignore the search image even if the tree has one (PICO_B200_FAT_LEAF);
-// bit 4 = let nn_kernel use up to 40 registers (12 resident blocks per SM instead of 16)
+// bit 4 = let nn_kernel use up to 40 registers (12 resident blocks per SM instead of 16);
+// bit 5 = nn_split_kernel (far subtrees as work items of the block, float only)
 int nn_mode() {
   static const int v = [] {
     const char* e = getenv("PICO_B200_NN");
     const int x = e ? atoi(e) : -1;
-    return (x >= 0 && x <= 31) ? x : 0;
+    return (x >= 0 && x <= 63) ? x : 0;
   }();
   return v;
+}
+
+// nn_split_kernel + nn_redo_kernel (PICO_B200_NN bit 5). Returns false if the call is not of that kind.
+template <typename T>
+bool launch_nn_split(CallCtx&, const pico_b200_tree*, KnnArgs<T>&, bool, bool, size_t, int, uint64_t*) {
+  return false;
+}
+template <>
+bool launch_nn_split<float>(CallCtx& c, const pico_b200_tree* t, KnnArgs<float>& a, bool fast, bool deep, size_t k,
+                            int mode, uint64_t* launches) {
+  if (!(mode & 32) || !fast || deep || k != 1 || t->sdim < 2 || t->n_nodes >= ((size_t)1 << 30) ||
+      (reinterpret_cast<uintptr_t>(a.out) & 7u) != 0)
+    return false;
+  const unsigned blocks = (a.nq + kThreadsPerBlock - 1) / kThreadsPerBlock;
+  uint32_t* items = nullptr;
+  uint8_t* redo = nullptr;
+  c.failed = c.alloc(reinterpret_cast<void**>(&items), (size_t)blocks * kItemsPerBlock * 3 * sizeof(uint32_t));
+  if (!c.failed) c.failed = c.alloc(reinterpret_cast<void**>(&redo), a.nq);
+  if (!c.failed && cudaMemsetAsync(redo, 0, a.nq, c.st) != cudaSuccess) c.failed = fail(PICO_B200_ERR_CUDA, "memset failed");
+  if (c.failed) return true;
+  if (t->sdim == 2) {
+    nn_split_kernel<2><<<blocks, kThreadsPerBlock, 0, c.st>>>(a, items, redo);
+    nn_redo_kernel<2><<<blocks, kThreadsPerBlock, 0, c.st>>>(a, redo);
+  } else {
+    nn_split_kernel<3><<<blocks, kThreadsPerBlock, 0, c.st>>>(a, items, redo);
+    nn_redo_kernel<3><<<blocks, kThreadsPerBlock, 0, c.st>>>(a, redo);
+  }
+  if (cudaGetLastError() != cudaSuccess) c.failed = fail(PICO_B200_ERR_CUDA, "nn_split_kernel launch failed");
+  *launches += 1;
+  return true;
 }
 
 float elapsed(cudaEvent_t a, cudaEvent_t b) {
@@ -1246,7 +1411,9 @@ int knn_enqueue(CallCtx& c, const pico_b200_tree* t, const T* q, size_t nq, size
       blocks = std::min<unsigned>(blocks, (unsigned)t->sm_count * (unsigned)c.blocks_per_sm_cap);
     const bool fast = t->metric == PICO_B200_METRIC_L2_SQUARED && !(e > 0);
     const int mode = nn_mode();
-    if (fast && !deep && k == 1 && mode && t->sdim >= 2 && t->n_nodes < ((size_t)1 << 30)) {
+    if (launch_nn_split(c, t, a, fast, deep, k, mode, launches)) {
+      if (c.failed) return c.failed;
+    } else if (fast && !deep && k == 1 && (mode & 31) && t->sdim >= 2 && t->n_nodes < ((size_t)1 << 30)) {
       // exact nn with the shared-memory slot stack; with a search image (fat.cu) ties at the best distance go
       // through the order-exact kernel afterwards
       const bool use_fat = t->d_fat_nodes != nullptr && !(mode & 8);

@@ -708,6 +708,74 @@ __device__ __forceinline__ void traverse_nn(const typename NodeOf<T>::type* __re
   }
 }
 
+// ---------------------------------------------------------------- far subtrees as work items (nn_split_kernel)
+// The order-exact traversal below one far child: the main loop of traverse_packed started at `node` with the box
+// distance and the offsets that hold there. reach = best widened by `margin` (see VisitNnTie: ties must be seen).
+template <typename T, int DIM, typename Stack>
+__device__ __forceinline__ void traverse_subtree(const typename NodeOf<T>::type* __restrict__ nodes,
+                                                 const typename Vec4Of<T>::type* __restrict__ pts4, const T (&q)[DIM],
+                                                 uint32_t node, T node_dist, T (&off)[DIM], T margin, Stack& stack,
+                                                 VisitNnTie<T>& vis) {
+  constexpr int metric = PICO_B200_METRIC_L2_SQUARED;
+  T reach = add_rn(vis.best, margin);
+  int sp = 0;
+  for (;;) {
+    T a, b;
+    uint32_t right, sd;
+    int lb, le;
+    load_node(nodes, node, a, b, right, sd, lb, le);
+    while (sd != PICO_B200_LEAF) {
+      T v = q[0], old = off[0];
+#pragma unroll
+      for (int j = 1; j < DIM; ++j) {
+        v = (sd == (uint32_t)j) ? q[j] : v;
+        old = (sd == (uint32_t)j) ? off[j] : old;
+      }
+      const bool go_left = sub_rn(sub_rn(add_rn(a, b), v), v) > T(0);
+      const T t = sub_rn(go_left ? b : a, v);
+      const T new_off = mul_rn(t, t);
+      const uint32_t far = go_left ? right : node + 1;
+      node = go_left ? node + 1 : right;
+      const T far_dist = add_rn(sub_rn(node_dist, old), new_off);
+      if (reach >= far_dist) {
+        T snap[DIM];
+#pragma unroll
+        for (int j = 0; j < DIM; ++j) snap[j] = (sd == (uint32_t)j) ? new_off : off[j];
+        stack.push(sp, far, far_dist, snap);
+        ++sp;
+      }
+      load_node(nodes, node, a, b, right, sd, lb, le);
+    }
+    if (lb < le) {
+      for (int i = lb; i < le; ++i) {
+        const typename Vec4Of<T>::type p = ldg4(pts4 + i);
+        T d = metric_first(metric, q[0], p.x);
+        if (DIM > 1) d = metric_fold(metric, d, q[DIM > 1 ? 1 : 0], p.y, 1);
+        if (DIM > 2) d = metric_fold(metric, d, q[DIM > 2 ? 2 : 0], p.z, 2);
+        vis.visit(index_of(p), d);
+      }
+      reach = add_rn(vis.best, margin);
+    }
+    bool found = false;
+    while (sp > 0) {
+      --sp;
+      T d;
+      uint32_t n;
+      T snap[DIM];
+      stack.pop(sp, n, d, snap);
+      if (reach >= d) {
+        node = n;
+        node_dist = d;
+#pragma unroll
+        for (int j = 0; j < DIM; ++j) off[j] = snap[j];
+        found = true;
+        break;
+      }
+    }
+    if (!found) return;
+  }
+}
+
 // ---------------------------------------------------------------- box search, thread-per-box, sdim <= 3
 // search_box::operator() + report_node / report_left / report_right (kd_tree_search.hpp:270-372) for euclidean
 // spaces, one thread per box: the running cell box (kd_tree_search.hpp:296-306 narrows one bound before it looks

@@ -756,8 +756,9 @@ print("NN_VARIANT_OK")
 
 @pytest.mark.parametrize("env", [{"PICO_B200_NN": "1"}, {"PICO_B200_NN": "5"},
                                  {"PICO_B200_NN": "1", "PICO_B200_FAT_LEAF": "16"},
-                                 {"PICO_B200_NN": "3", "PICO_B200_FAT_LEAF": "32"}],
-                         ids=["slot_stack", "slot_stack_no_restart", "search_image_16", "search_image_32_far_fat"])
+                                 {"PICO_B200_NN": "3", "PICO_B200_FAT_LEAF": "32"}, {"PICO_B200_NN": "32"}],
+                         ids=["slot_stack", "slot_stack_no_restart", "search_image_16", "search_image_32_far_fat",
+                              "far_subtrees_as_items"])
 def test_nn_kernel_variants(env):
     """The selectable k = 1 kernels (PICO_B200_NN / PICO_B200_FAT_LEAF tuning hooks, read once per process): shared
     slot stack with restore records, prefix-minimum restart, search image with tie re-run. Same answers as the
