@@ -9,6 +9,7 @@
 //   * warp-per-query for everything else (any sdim, any k), also selectable with
 //     PICO_B200_WARP_PER_QUERY for comparison.
 #include <cub/cub.cuh>
+#include <sys/mman.h>
 
 #include <algorithm>
 #include <atomic>
@@ -618,6 +619,21 @@ void parallel_pack_rows(char* dst, const char* src, size_t rows, size_t row_byte
     if (i * per < rows) th.emplace_back(work, i * per, std::min(rows, (i + 1) * per));
   work(0, std::min(rows, per));
   for (auto& t : th) t.join();
+}
+
+// Ragged results can be gigabytes of fresh host memory (cfg3 radius: 6.1 GB). Large buffers are aligned to 2 MiB and
+// offered to the kernel as transparent huge pages: the copy out of the pinned staging buffers then takes one page
+// fault per 2 MiB instead of one per 4 KiB. free() releases them like any malloc'd block (pico_b200_free).
+void* alloc_result(size_t bytes) {
+  constexpr size_t kHuge = (size_t)2 << 20;
+  if (bytes >= 32 * kHuge) {
+    void* p = nullptr;
+    if (posix_memalign(&p, kHuge, (bytes + kHuge - 1) / kHuge * kHuge) == 0) {
+      madvise(p, (bytes + kHuge - 1) / kHuge * kHuge, MADV_HUGEPAGE);
+      return p;
+    }
+  }
+  return malloc(bytes);
 }
 
 // Touches every page of a freshly allocated (never written) pageable output buffer with several host
@@ -2154,7 +2170,7 @@ int radius_batch(const pico_b200_tree* t, const T* q, size_t nq, size_t stride, 
     // call cost more than both traversal passes together (bench configs: 78 ms per call, 20 ms of kernels)
     PICO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_hits), bytes, c.st));
   } else {
-    h_hits = static_cast<Neighbor<T>*>(malloc(bytes));
+    h_hits = static_cast<Neighbor<T>*>(alloc_result(bytes));
     if (!h_hits) return fail(PICO_B200_ERR_OUT_OF_MEMORY, "host allocation of radius results failed");
   }
   auto give_up = [&](int rc) {
@@ -2390,7 +2406,7 @@ int box_batch(const pico_b200_tree* t, const T* mins, const T* maxs, size_t nb, 
   if (on_device) {
     PICO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_hits), bytes, c.st));
   } else {
-    h_hits = static_cast<int32_t*>(malloc(bytes));
+    h_hits = static_cast<int32_t*>(alloc_result(bytes));
     if (!h_hits) return fail(PICO_B200_ERR_OUT_OF_MEMORY, "host allocation of box results failed");
   }
   auto give_up = [&](int rc) {
