@@ -430,20 +430,29 @@ struct VisitKnn {
     }
   }
   __device__ __forceinline__ T max() const { return d[KMAX - 1]; }
+  // The network runs from the tail in segments of four slots and stops at the first segment boundary whose lower
+  // neighbour is not greater than x: everything below stays as it is. Candidates accepted late in a search land
+  // near the tail of the list, so most insertions touch one or two segments instead of all KMAX slots.
   __device__ __forceinline__ void visit(int i_new, T x) {
     if (!(d[KMAX - 1] > x)) return;
+    constexpr int SEG = KMAX >= 8 ? 4 : KMAX;
 #pragma unroll
-    for (int i = KMAX - 1; i >= 1; --i) {
-      const bool shift = d[i - 1] > x;
-      const bool here = !shift && (d[i] > x);
-      const T nd = shift ? d[i - 1] : (here ? x : d[i]);
-      const int ni = shift ? id[i - 1] : (here ? i_new : id[i]);
-      d[i] = nd;
-      id[i] = ni;
-    }
-    if (d[0] > x) {
-      d[0] = x;
-      id[0] = i_new;
+    for (int hi = KMAX - 1; hi >= 0; hi -= SEG) {
+#pragma unroll
+      for (int i = hi; i > hi - SEG; --i) {
+        if (i >= 1) {
+          const bool shift = d[i - 1] > x;
+          const bool here = !shift && (d[i] > x);
+          const T nd = shift ? d[i - 1] : (here ? x : d[i]);
+          const int ni = shift ? id[i - 1] : (here ? i_new : id[i]);
+          d[i] = nd;
+          id[i] = ni;
+        } else if (d[0] > x) {
+          d[0] = x;
+          id[0] = i_new;
+        }
+      }
+      if (hi - SEG >= 0 && !(d[hi - SEG] > x)) return;
     }
   }
   // row = k neighbour records, ascending
