@@ -25,6 +25,7 @@
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <chrono>
 #include <vector>
 
 #include "common.cuh"
@@ -272,8 +273,7 @@ __device__ void emit_children(const BuildState<T>& s, uint32_t node_id, int sd, 
     l.split_dim = r.split_dim = -1;
     const int cnts[2] = {split - begin, end - split};
     for (int k = 0; k < 2; ++k) {
-      const bool huge = cnts[k] > s.huge_min && s.rule != PICO_B200_RULE_MEDIAN_MAX_SIDE &&
-                        !will_be_leaf(s, cnts[k], depth + 1);
+      const bool huge = cnts[k] > s.huge_min && !will_be_leaf(s, cnts[k], depth + 1);
       if (huge)
         s.huge_next[atomicAdd(&s.counters[3], 1u)] = c + k;
       else if (cnts[k] > kWarpNodeMax)
@@ -304,23 +304,27 @@ __device__ void emit_children(const BuildState<T>& s, uint32_t node_id, int sd, 
 // than the right one; the cut follows from the two position lists (tests/test_oracle_golden.py
 // holds the sequential restatement this was checked against; tests/test_gpu_parity.py compares the
 // resulting permutations with the reference's fixtures).
-template <typename T>
+// CG: the index array is read past L1 (ld.cg) — for the multi-CTA flavour, where other CTAs exchange entries
+// between two barriers of the same kernel.
+template <typename T, bool CG = false>
 struct NthCtx {
+  using scalar = T;
   const T* col;  // coordinate `split_dim` of point p is col[p * sdim]
   int32_t* idx;
   int sdim;
-  __device__ __forceinline__ T at(int pos) const { return col[(size_t)idx[pos] * sdim]; }
+  __device__ __forceinline__ int32_t id(int pos) const { return CG ? __ldcg(idx + pos) : idx[pos]; }
+  __device__ __forceinline__ T at(int pos) const { return col[(size_t)id(pos) * sdim]; }
   __device__ __forceinline__ bool less(int a, int b) const { return at(a) < at(b); }  // positions
   __device__ __forceinline__ void swap(int a, int b) const {
-    const int32_t t = idx[a];
-    idx[a] = idx[b];
+    const int32_t t = id(a), u = id(b);
+    idx[a] = u;
     idx[b] = t;
   }
 };
 
 // sequential pieces (one thread): std::__move_median_to_first, std::__insertion_sort, std::__heap_select
-template <typename T>
-__device__ void seq_move_median_to_first(const NthCtx<T>& c, int result, int a, int b, int cc) {
+template <typename Ctx>
+__device__ void seq_move_median_to_first(const Ctx& c, int result, int a, int b, int cc) {
   int pick;
   if (c.less(a, b)) {
     if (c.less(b, cc))
@@ -401,14 +405,15 @@ __device__ void seq_heap_select(const NthCtx<T>& c, int first, int middle, int l
 }
 
 // std::nth_element(first, nth, last) on positions of s.idx, by the whole group
+// (depth_limit < 0: a fresh call; otherwise the introselect loop is resumed with that many levels left)
 template <typename T, int G>
-__device__ void group_nth_element(const BuildState<T>& s, int sd, int first, int nth, int last) {
+__device__ void group_nth_element(const BuildState<T>& s, int sd, int first, int nth, int last, int depth_limit = -1) {
   if (first == last || nth == last) return;
   const int tid = Grp<G>::tid();
   NthCtx<T> c{s.raw + sd, s.idx, s.sdim};
   int32_t* lst_l = s.tmp;   // positions of elements >= pivot, ascending, at [lo, lo + n_l)
   int32_t* lst_r = s.tmp2;  // positions of elements <= pivot, descending, at (hi - 1 - n_r, hi - 1]
-  int depth_limit = 2 * (31 - __clz(last - first));
+  if (depth_limit < 0) depth_limit = 2 * (31 - __clz(last - first));
   while (last - first > 3) {
     if (depth_limit == 0) {
       if (tid == 0) {
@@ -766,7 +771,7 @@ __global__ void __launch_bounds__(kChunkThreads) huge_swap(BuildState<T> s, int 
 // the value is the coordinate that ends up there; group_nth_element leaves the indices exactly
 // where libstdc++ would.
 template <typename T, int G>
-__device__ void median_node(const BuildState<T>& s, uint32_t node_id) {
+__device__ void median_node(const BuildState<T>& s, uint32_t node_id, bool selected = false) {
   BNode<T>& nd = s.nodes[node_id];
   const int tid = Grp<G>::tid();
   const int begin = nd.begin, end = nd.end, cnt = end - begin, depth = nd.depth;
@@ -791,7 +796,7 @@ __device__ void median_node(const BuildState<T>& s, uint32_t node_id) {
   int32_t* idx = s.idx;
   // std::nth_element at the middle (kd_tree_builder.hpp:165-175), emulated exactly
   const int split = begin + cnt / 2;
-  group_nth_element<T, G>(s, sd, begin, split, end);
+  if (!selected) group_nth_element<T, G>(s, sd, begin, split, end);
   const T split_val = col[(size_t)idx[split] * sdim];
   Grp<G>::sync();
   emit_children<T, G>(s, node_id, sd, split, split_val);
@@ -808,6 +813,150 @@ __global__ void __launch_bounds__(256) median_level_warp(BuildState<T> s, uint32
 template <typename T>
 __global__ void __launch_bounds__(kBigThreads) median_level_block(BuildState<T> s, const uint32_t* big_list) {
   median_node<T, kBigThreads>(s, big_list[blockIdx.x]);
+}
+
+// Huge nodes of the median rule (the first ~8 levels of a multi-million point tree): one CTA per node would leave
+// the GPU to 1, 2, 4 ... CTAs, each walking millions of indices (142-200 ms per 7.7 M points, profiles/r1). Here the
+// CTAs of ONE co-resident grid (cooperative launch) are dealt out in equal groups over the level's huge nodes — the
+// median rule keeps the nodes of a level within one point of each other — and a group runs the introselect
+// iterations of its node together: the range is cut into one slice per CTA, every iteration takes
+//   pivot (CTA 0)  |  count both flag kinds per slice  |  write the two position lists  |  exchange the pairs
+// with a barrier of the group (a counter in global memory) after each step. The lists are what group_nth_element
+// builds, so the exchanges and the cut are the same; once the range is short (or the depth limit is used up) CTA 0
+// resumes the loop alone with the remaining depth limit. Everything the CTAs tell each other goes through L2
+// (ld.cg / plain stores + __threadfence at the barrier).
+__device__ __forceinline__ void group_barrier(unsigned* bar, unsigned& epoch, int ctas) {
+  __syncthreads();
+  if (ctas == 1) return;
+  epoch += (unsigned)ctas;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1u);
+    while (*reinterpret_cast<volatile unsigned*>(bar) < epoch) {
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+template <typename T>
+__device__ void multi_nth_element(const BuildState<T>& s, int sd, int first, int nth, int last, int c, int ctas,
+                                  unsigned* bar, unsigned& epoch, int32_t* cnt /* [2 * ctas] of this group */) {
+  constexpr int B = kBigThreads;
+  const int tid = threadIdx.x;
+  NthCtx<T, true> ctx{s.raw + sd, s.idx, s.sdim};
+  int32_t* lst_l = s.tmp;
+  int32_t* lst_r = s.tmp2;
+  const int multi_min = s.huge_min / 4;
+  int depth_limit = 2 * (31 - __clz(last - first));
+  while (last - first > multi_min && depth_limit > 0) {
+    --depth_limit;
+    if (c == 0 && tid == 0) seq_move_median_to_first(ctx, first, first + 1, first + (last - first) / 2, last - 1);
+    group_barrier(bar, epoch, ctas);
+    const T pv = ctx.at(first);
+    const int lo = first + 1, hi = last;
+    const int per = (hi - lo + ctas - 1) / ctas;
+    const int my_lo = min(hi, lo + c * per), my_hi = min(hi, my_lo + per);
+    // how many of each kind this slice holds
+    {
+      int nl = 0, nr = 0;
+      for (int i = my_lo + tid; i < my_hi; i += B) {
+        const T v = ctx.at(i);
+        nl += !(v < pv);
+        nr += !(pv < v);
+      }
+      nl = Grp<B>::sum(nl);
+      nr = Grp<B>::sum(nr);
+      if (tid == 0) {
+        __stcg(cnt + c, nl);
+        __stcg(cnt + ctas + c, nr);
+      }
+    }
+    group_barrier(bar, epoch, ctas);
+    int off_l = 0, off_r = 0, n_l = 0, n_r = 0;
+    for (int o = 0; o < ctas; ++o) {
+      const int a = __ldcg(cnt + o), b = __ldcg(cnt + ctas + o);
+      if (o < c) off_l += a;
+      if (o > c) off_r += b;
+      n_l += a;
+      n_r += b;
+    }
+    {
+      int n = 0;
+      for (int base = my_lo; base < my_hi; base += B) {
+        const int i = base + tid;
+        const int f = (i < my_hi) && !(ctx.at(i) < pv);
+        int tot;
+        const int ex = Grp<B>::excl(f, tot);
+        if (f) lst_l[lo + off_l + n + ex] = i;
+        n += tot;
+      }
+      n = 0;
+      for (int base = 0; base < my_hi - my_lo; base += B) {
+        const int i = my_hi - 1 - (base + tid);
+        const int f = (i >= my_lo) && !(pv < ctx.at(i));
+        int tot;
+        const int ex = Grp<B>::excl(f, tot);
+        if (f) lst_r[hi - 1 - (off_r + n + ex)] = i;
+        n += tot;
+      }
+    }
+    group_barrier(bar, epoch, ctas);
+    // pairs j with lst_l[j] < lst_r[j]: the left positions ascend and the right ones descend, so they are a prefix
+    const int pairs = n_l < n_r ? n_l : n_r;
+    int m = 0;
+    {
+      int a = 0, b = pairs;  // first j in [0, pairs] that fails
+      while (a < b) {
+        const int j = (a + b) >> 1;
+        if (__ldcg(lst_l + lo + j) < __ldcg(lst_r + hi - 1 - j))
+          a = j + 1;
+        else
+          b = j;
+      }
+      m = a;
+    }
+    for (int j = c * B + tid; j < m; j += ctas * B) ctx.swap(__ldcg(lst_l + lo + j), __ldcg(lst_r + hi - 1 - j));
+    int cut;
+    if (m < n_l && (m == 0 || __ldcg(lst_l + lo + m) < __ldcg(lst_r + hi - 1 - (m - 1))))
+      cut = __ldcg(lst_l + lo + m);
+    else
+      cut = __ldcg(lst_r + hi - 1 - (m - 1));
+    group_barrier(bar, epoch, ctas);
+    if (cut <= nth)
+      first = cut;
+    else
+      last = cut;
+  }
+  if (c == 0) group_nth_element<T, B>(s, sd, first, nth, last, depth_limit);
+}
+
+// blockDim.x == kBigThreads; gridDim.x co-resident CTAs (cooperative launch); `ctas` CTAs per node
+template <typename T>
+__global__ void __launch_bounds__(kBigThreads) median_huge_level(BuildState<T> s, const uint32_t* huge_list,
+                                                                 int n_huge, int ctas, unsigned* bars, int32_t* cnts) {
+  const int groups = gridDim.x / ctas;
+  const int g = blockIdx.x / ctas, c = blockIdx.x % ctas;
+  if (g >= groups) return;
+  unsigned epoch = 0;
+  for (int h = g; h < n_huge; h += groups) {
+    const uint32_t node_id = huge_list[h];
+    const BNode<T>& nd = s.nodes[node_id];
+    const int begin = nd.begin, end = nd.end, sdim = s.sdim;
+    const T* box = s.boxes + (size_t)node_id * 2 * sdim;
+    int sd = 0;
+    T max_delta = -Limits<T>::max();
+    for (int d = 0; d < sdim; ++d) {
+      const T delta = box[sdim + d] - box[d];
+      if (delta > max_delta) {
+        max_delta = delta;
+        sd = d;
+      }
+    }
+    multi_nth_element<T>(s, sd, begin, begin + (end - begin) / 2, end, c, ctas, bars + g, epoch,
+                         cnts + (size_t)g * 2 * ctas);
+    if (c == 0) median_node<T, kBigThreads>(s, node_id, true);
+  }
 }
 
 // ------------------------------------------------------------------ small kernels
@@ -986,11 +1135,15 @@ int stage_points(const T* h_pts, size_t n, size_t sdim, size_t stride, T* d_raw,
   return 0;
 }
 
+// The tree's own arrays come from the stream-ordered pool as well (its release threshold is raised in api.cu): a
+// rebuild — one per LiDAR frame in the reference's use — gets the blocks of the tree it replaces back within
+// microseconds, where cudaMalloc spent 4.5 of a 13 ms build mapping fresh memory (profiles/r2/build_timeline_*.txt).
+// pico_b200_tree_destroy releases them with cudaFree, which accepts pool allocations and waits for the device.
 template <typename T>
 int finalize_storage(pico_b200_tree* t, const T* d_raw, cudaStream_t st) {
   const size_t n = t->n;
   const int sdim = (int)t->sdim;
-  PICO_CUDA(cudaMalloc(&t->d_pts, t->pts_bytes() ? t->pts_bytes() : 16));
+  PICO_CUDA(cudaMallocAsync(&t->d_pts, t->pts_bytes() ? t->pts_bytes() : 16, st));
   if (t->packed()) {
     pack_points4<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_raw, t->d_indices, n, sdim,
                                                                   static_cast<typename Vec4Of<T>::type*>(t->d_pts));
@@ -1006,6 +1159,53 @@ int finalize_storage(pico_b200_tree* t, const T* d_raw, cudaStream_t st) {
 
 }  // namespace
 
+// Pinned host scratch of the calling thread, kept for the life of the thread: the per-level counters and the root
+// box are read back through it. (A cudaMallocHost per build sat inside the timed region and cost 3-10 ms, now and
+// then 30 — profiles/r2/build_timeline_median3.txt.)
+void* pinned_scratch(size_t bytes) {
+  struct Pin {
+    void* p = nullptr;
+    size_t cap = 0;
+    ~Pin() {
+      if (p) cudaFreeHost(p);
+    }
+  };
+  thread_local Pin pin;
+  if (bytes > pin.cap) {
+    if (pin.p) cudaFreeHost(pin.p);
+    pin.p = nullptr;
+    pin.cap = 0;
+    const size_t want = std::max<size_t>(bytes, 4096);
+    if (cudaMallocHost(&pin.p, want) != cudaSuccess) {
+      cudaGetLastError();
+      pin.p = nullptr;
+      return nullptr;
+    }
+    pin.cap = want;
+  }
+  return pin.p;
+}
+
+// root node, counters and empty lists in one launch (instead of five small copies out of pageable memory)
+template <typename T>
+__global__ void init_root(BuildState<T> s, int32_t n, const T* root_box, uint32_t* big, uint32_t* huge) {
+  if (threadIdx.x == 0) {
+    BNode<T> root;
+    memset(&root, 0, sizeof(root));
+    root.begin = 0;
+    root.end = n;
+    root.left = root.right = -1;
+    root.split_dim = -1;
+    root.depth = 0;
+    root.preorder = 0;
+    s.nodes[0] = root;
+    for (int i = 0; i < 8; ++i) s.counters[i] = i == 0 ? 1u : 0u;
+    big[0] = 0;
+    huge[0] = 0;
+  }
+  for (int d = threadIdx.x; d < 2 * s.sdim; d += blockDim.x) s.boxes[d] = root_box[d];
+}
+
 // ------------------------------------------------------------------ host driver
 template <typename T>
 int build_tree(pico_b200_tree* t, const T* h_pts, size_t stride, int rule, int stop_kind, size_t stop_value,
@@ -1013,6 +1213,10 @@ int build_tree(pico_b200_tree* t, const T* h_pts, size_t stride, int rule, int s
   const size_t n = t->n;
   const int sdim = (int)t->sdim;
   if (n >= (size_t)0x7fffffff) return fail(PICO_B200_ERR_UNSUPPORTED, "more than 2^31-2 points");
+  // PICO_B200_BUILD_TIMELINE=1: host clock at the stages of the build and after every level's round trip, to stderr
+  const bool timeline = getenv("PICO_B200_BUILD_TIMELINE") != nullptr;
+  const auto tl0 = std::chrono::steady_clock::now();
+  auto tl_ms = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tl0).count(); };
   cudaStream_t st;
   PICO_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   struct StreamGuard {
@@ -1023,8 +1227,8 @@ int build_tree(pico_b200_tree* t, const T* h_pts, size_t stride, int rule, int s
   DevBuf raw, tmp, tmp2, nodes, boxes, counters, big_a, big_b, partial, huge_a, huge_b, huge_nodes, chunk_stats;
   PICO_TRY(alloc(raw, n * sdim * sizeof(T), st));
   PICO_TRY(stage_points(h_pts, n, sdim, stride, raw.as<T>(), st));
-  PICO_CUDA(cudaMalloc(&t->d_indices, n * sizeof(int32_t)));
-  PICO_CUDA(cudaMalloc(&t->d_root_box, 2 * sdim * sizeof(T)));
+  PICO_CUDA(cudaMallocAsync(&t->d_indices, n * sizeof(int32_t), st));
+  PICO_CUDA(cudaMallocAsync(&t->d_root_box, 2 * sdim * sizeof(T), st));
   PICO_TRY(alloc(tmp, n * sizeof(int32_t), st));
   PICO_TRY(alloc(tmp2, n * sizeof(int32_t), st));
 
@@ -1045,15 +1249,35 @@ int build_tree(pico_b200_tree* t, const T* h_pts, size_t stride, int rule, int s
   PICO_TRY(alloc(huge_nodes, huge_cap * sizeof(HugeNode<T>), st));
   PICO_TRY(alloc(chunk_stats, chunk_cap * sizeof(ChunkStat<T>), st));
 
+  // median rule: the grid of the cooperative kernel that takes the huge nodes, its barrier counters and slice counts
+  int coop_grid = 0;
+  DevBuf coop;
+  if (rule == PICO_B200_RULE_MEDIAN_MAX_SIDE && n > (size_t)huge_min) {
+    int per_sm = 0;
+    PICO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, median_huge_level<T>, kBigThreads, 0));
+    coop_grid = per_sm * t->sm_count;
+    if (coop_grid < 1) return fail(PICO_B200_ERR_CUDA, "median_huge_level does not fit an SM");
+    PICO_TRY(alloc(coop, (size_t)coop_grid * 3 * sizeof(int32_t), st));
+  }
+
   // build_ms covers the kernels and the per-level round trips, not the allocations above
   cudaEvent_t ev0, ev1;
   PICO_CUDA(cudaEventCreate(&ev0));
   PICO_CUDA(cudaEventCreate(&ev1));
+  if (timeline) {
+    fprintf(stderr, "points staged, workspaces allocated (host) at %.3f ms\n", tl_ms());
+    cudaStreamSynchronize(st);
+    fprintf(stderr, "... and done on the device at %.3f ms\n", tl_ms());
+  }
   PICO_CUDA(cudaEventRecord(ev0, st));
 
   // --- root box
   T* d_root = static_cast<T*>(t->d_root_box);
-  std::vector<T> h_root(2 * sdim);
+  // [0, 64): the per-level counters; then the root box
+  char* pinned = static_cast<char*>(pinned_scratch(64 + 2 * sdim * sizeof(T)));
+  if (!pinned) return fail(PICO_B200_ERR_CUDA, "no pinned host memory for the build's read-backs");
+  uint32_t* h_counters = reinterpret_cast<uint32_t*>(pinned);
+  T* h_root = reinterpret_cast<T*>(pinned + 64);
   if (bounds_min && bounds_max) {
     // bbox.fit(min); bbox.fit(max)  kd_tree_builder.hpp:502-511
     for (int d = 0; d < sdim; ++d) {
@@ -1066,14 +1290,14 @@ int build_tree(pico_b200_tree* t, const T* h_pts, size_t stride, int rule, int s
       h_root[d] = mn;
       h_root[sdim + d] = mx;
     }
-    PICO_CUDA(cudaMemcpyAsync(d_root, h_root.data(), 2 * sdim * sizeof(T), cudaMemcpyHostToDevice, st));
+    PICO_CUDA(cudaMemcpyAsync(d_root, h_root, 2 * sdim * sizeof(T), cudaMemcpyHostToDevice, st));
   } else {
     const int parts = (int)std::min<size_t>((n + 1023) / 1024, (size_t)t->sm_count * 4);
     PICO_TRY(alloc(partial, (size_t)parts * 2 * sdim * sizeof(T), st));
     root_box_kernel<T><<<parts, 1024, 0, st>>>(raw.as<T>(), n, sdim, partial.as<T>());
     root_box_final<T><<<(sdim + 127) / 128, 128, 0, st>>>(partial.as<T>(), parts, sdim, d_root);
     PICO_CUDA(cudaGetLastError());
-    PICO_CUDA(cudaMemcpyAsync(h_root.data(), d_root, 2 * sdim * sizeof(T), cudaMemcpyDeviceToHost, st));
+    PICO_CUDA(cudaMemcpyAsync(h_root, d_root, 2 * sdim * sizeof(T), cudaMemcpyDeviceToHost, st));
     PICO_CUDA(cudaStreamSynchronize(st));
   }
   for (int d = 0; d < sdim && d < 4; ++d) {
@@ -1099,23 +1323,8 @@ int build_tree(pico_b200_tree* t, const T* h_pts, size_t stride, int rule, int s
   s.stop_kind = stop_kind;
   s.stop_value = (int32_t)std::min<size_t>(stop_value, 0x7fffffff);
 
-  {
-    BNode<T> root;
-    memset(&root, 0, sizeof(root));
-    root.begin = 0;
-    root.end = (int32_t)n;
-    root.left = root.right = -1;
-    root.split_dim = -1;
-    root.depth = 0;
-    root.preorder = 0;
-    PICO_CUDA(cudaMemcpyAsync(s.nodes, &root, sizeof(root), cudaMemcpyHostToDevice, st));
-    PICO_CUDA(cudaMemcpyAsync(s.boxes, d_root, 2 * sdim * sizeof(T), cudaMemcpyDeviceToDevice, st));
-    const uint32_t h_cnt[8] = {1u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-    PICO_CUDA(cudaMemcpyAsync(s.counters, h_cnt, sizeof(h_cnt), cudaMemcpyHostToDevice, st));
-    const uint32_t zero = 0;
-    PICO_CUDA(cudaMemcpyAsync(big_a.p, &zero, sizeof(zero), cudaMemcpyHostToDevice, st));
-    PICO_CUDA(cudaMemcpyAsync(huge_a.p, &zero, sizeof(zero), cudaMemcpyHostToDevice, st));
-  }
+  init_root<T><<<1, 128, 0, st>>>(s, (int32_t)n, d_root, big_a.as<uint32_t>(), huge_a.as<uint32_t>());
+  PICO_CUDA(cudaGetLastError());
 
   std::vector<uint32_t> level_start;  // BFS id of the first node of each level
   level_start.push_back(0);
@@ -1123,19 +1332,14 @@ int build_tree(pico_b200_tree* t, const T* h_pts, size_t stride, int rule, int s
   // the root: leaf / warp / CTA / chunked passes
   const bool root_leaf = (stop_kind == PICO_B200_STOP_MAX_LEAF_SIZE) ? (n <= (size_t)s.stop_value)
                                                                      : (s.stop_value == 0 || n <= 1);
-  uint32_t n_huge = (n > (size_t)huge_min && rule != PICO_B200_RULE_MEDIAN_MAX_SIDE && !root_leaf) ? 1u : 0u;
+  uint32_t n_huge = (n > (size_t)huge_min && !root_leaf) ? 1u : 0u;
   uint32_t n_big = (!n_huge && n > (size_t)kWarpNodeMax) ? 1u : 0u;
   uint32_t* big_cur = big_a.as<uint32_t>();
   uint32_t* big_nxt = big_b.as<uint32_t>();
   uint32_t* huge_cur = huge_a.as<uint32_t>();
   uint32_t* huge_nxt = huge_b.as<uint32_t>();
-  uint32_t* h_counters = nullptr;
-  PICO_CUDA(cudaMallocHost(&h_counters, 8 * sizeof(uint32_t)));
-  struct PinGuard {
-    uint32_t* p;
-    ~PinGuard() { cudaFreeHost(p); }
-  } pin_guard{h_counters};
 
+  if (timeline) fprintf(stderr, "root box, root node: level loop starts at %.3f ms\n", tl_ms());
   while (level_begin < level_end) {
     const uint32_t width = level_end - level_begin;
     if ((size_t)level_end + 2 * (size_t)width > cap) {
@@ -1164,7 +1368,18 @@ int build_tree(pico_b200_tree* t, const T* h_pts, size_t stride, int rule, int s
     s.huge_next = huge_nxt;
     PICO_CUDA(cudaMemsetAsync(s.counters + 1, 0, sizeof(uint32_t), st));
     PICO_CUDA(cudaMemsetAsync(s.counters + 3, 0, 2 * sizeof(uint32_t), st));
-    if (n_huge) {
+    if (n_huge && rule == PICO_B200_RULE_MEDIAN_MAX_SIDE) {
+      // equal groups of co-resident CTAs, one per huge node (as many nodes at a time as there are groups)
+      const int ctas = std::max(1, coop_grid / (int)std::min<uint32_t>(n_huge, (uint32_t)coop_grid));
+      PICO_CUDA(cudaMemsetAsync(coop.p, 0, (size_t)coop_grid * sizeof(unsigned), st));
+      const uint32_t* list = huge_cur;
+      int nh = (int)n_huge;
+      unsigned* bars = coop.as<unsigned>();
+      int32_t* cnts = coop.as<int32_t>() + coop_grid;
+      void* args[] = {&s, &list, &nh, const_cast<int*>(&ctas), &bars, &cnts};
+      PICO_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(&median_huge_level<T>), dim3(coop_grid),
+                                            dim3(kBigThreads), args, 0, st));
+    } else if (n_huge) {
       // every chunk kernel is launched over an upper bound of the level's chunk count
       const unsigned chunk_grid = (unsigned)std::min<size_t>(n / kChunk + n_huge + 1, chunk_cap);
       huge_plan<T><<<1, 256, 0, st>>>(s, huge_cur, (int)n_huge);
@@ -1185,6 +1400,9 @@ int build_tree(pico_b200_tree* t, const T* h_pts, size_t stride, int rule, int s
     PICO_CUDA(cudaGetLastError());
     PICO_CUDA(cudaMemcpyAsync(h_counters, s.counters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     PICO_CUDA(cudaStreamSynchronize(st));
+    if (timeline)
+      fprintf(stderr, "level %zu: %u nodes (%u big, %u huge) done at %.3f ms\n", level_start.size() - 1, width, n_big,
+              n_huge, tl_ms());
     level_begin = level_end;
     level_end = h_counters[0];
     n_big = h_counters[1];
@@ -1213,17 +1431,19 @@ int build_tree(pico_b200_tree* t, const T* h_pts, size_t stride, int rule, int s
     const uint32_t lb = level_start[l], le = level_start[l + 1];
     number_level<T><<<(le - lb + 127) / 128, 128, 0, st>>>(s.nodes, lb, le);
   }
-  PICO_CUDA(cudaMalloc(&t->d_nodes, (size_t)n_nodes * t->node_size()));
-  if (t->outer_bytes()) PICO_CUDA(cudaMalloc(&t->d_outer, t->outer_bytes()));
-  if (!t->packed()) PICO_CUDA(cudaMalloc(reinterpret_cast<void**>(&t->d_spans), t->spans_bytes()));
+  PICO_CUDA(cudaMallocAsync(&t->d_nodes, (size_t)n_nodes * t->node_size(), st));
+  if (t->outer_bytes()) PICO_CUDA(cudaMallocAsync(&t->d_outer, t->outer_bytes(), st));
+  if (!t->packed()) PICO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&t->d_spans), t->spans_bytes(), st));
   emit_nodes<T><<<(n_nodes + 255) / 256, 256, 0, st>>>(s.nodes, n_nodes,
                                                         static_cast<typename NodeOf<T>::type*>(t->d_nodes),
                                                         static_cast<T*>(t->d_outer), t->d_spans);
   PICO_CUDA(cudaGetLastError());
   PICO_TRY(finalize_storage<T>(t, raw.as<T>(), st));
   PICO_TRY(build_fat_nodes(t, st));
+  if (timeline) fprintf(stderr, "bottom-up, numbering, emit, point packing enqueued at %.3f ms\n", tl_ms());
   PICO_CUDA(cudaEventRecord(ev1, st));
   PICO_CUDA(cudaStreamSynchronize(st));
+  if (timeline) fprintf(stderr, "build finished at %.3f ms\n", tl_ms());
   float ms = 0;
   PICO_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
   t->build_ms = ms;
@@ -1280,9 +1500,9 @@ int upload_tree(pico_b200_tree* t, const T* h_pts, size_t stride, const void* h_
   DevBuf raw;
   PICO_TRY(alloc(raw, n * sdim * sizeof(T), st));
   PICO_TRY(stage_points(h_pts, n, sdim, stride, raw.as<T>(), st));
-  PICO_CUDA(cudaMalloc(&t->d_indices, n * sizeof(int32_t)));
-  PICO_CUDA(cudaMalloc(&t->d_root_box, 2 * sdim * sizeof(T)));
-  PICO_CUDA(cudaMalloc(&t->d_nodes, n_nodes * sizeof(NodeT)));
+  PICO_CUDA(cudaMallocAsync(&t->d_indices, n * sizeof(int32_t), st));
+  PICO_CUDA(cudaMallocAsync(&t->d_root_box, 2 * sdim * sizeof(T), st));
+  PICO_CUDA(cudaMallocAsync(&t->d_nodes, n_nodes * sizeof(NodeT), st));
   PICO_CUDA(cudaMemcpyAsync(t->d_indices, indices, n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   PICO_CUDA(cudaMemcpyAsync(t->d_root_box, root_box, 2 * sdim * sizeof(T), cudaMemcpyHostToDevice, st));
   PICO_CUDA(cudaMemcpyAsync(t->d_nodes, nodes, n_nodes * sizeof(NodeT), cudaMemcpyHostToDevice, st));
@@ -1297,13 +1517,13 @@ int upload_tree(pico_b200_tree* t, const T* h_pts, size_t stride, const void* h_
         spans[i] = make_uint2(l.x, l.y + r.y);
       }
     }
-    PICO_CUDA(cudaMalloc(reinterpret_cast<void**>(&t->d_spans), t->spans_bytes()));
+    PICO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&t->d_spans), t->spans_bytes(), st));
     PICO_CUDA(cudaMemcpyAsync(t->d_spans, spans.data(), t->spans_bytes(), cudaMemcpyHostToDevice, st));
     PICO_CUDA(cudaStreamSynchronize(st));
   }
   if (t->topological()) {
     if (!outer_bounds) return fail(PICO_B200_ERR_INVALID_ARGUMENT, "topological metric needs the outer bounds");
-    PICO_CUDA(cudaMalloc(&t->d_outer, t->outer_bytes()));
+    PICO_CUDA(cudaMallocAsync(&t->d_outer, t->outer_bytes(), st));
     PICO_CUDA(cudaMemcpyAsync(t->d_outer, outer_bounds, t->outer_bytes(), cudaMemcpyHostToDevice, st));
   }
   for (int d = 0; d < sdim && d < 4; ++d) {

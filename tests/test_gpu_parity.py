@@ -518,6 +518,34 @@ def test_nth_element_heap_select_fallback(pt, oracle):
         assert_same_structure(nodes_from_export(nodes, pts.dtype), o.nodes)
 
 
+def test_median_rule_huge_nodes_match_oracle(pt, oracle, monkeypatch):
+    """Median rule above the one-CTA threshold (build.cu median_huge_level: several CTAs per node, barriers in
+    global memory): node table and index permutation equal to the oracle's std::nth_element build — at the
+    default threshold, with a low one (many iterations by many groups), and on the introselect killers, whose
+    depth limit runs out while the range is still in the multi-CTA phase."""
+    from pico_tree_b200 import datasets as D
+    pts = D.lidar_shape(400_000, seed=11)
+    o = oracle.OracleTree(pts, 10, rule="median")
+    for huge_min in (None, "2048"):
+        if huge_min:
+            monkeypatch.setenv("PICO_B200_HUGE_MIN", huge_min)
+        t = pt.KdTree(pts, pt.Metric.L2Squared, 10, rule=pt.kd_tree.Rule.MedianMaxSide)
+        nodes, indices, _ = t.export()
+        assert np.array_equal(indices, o.indices), huge_min
+        assert_same_structure(nodes_from_export(nodes, pts.dtype), o.nodes)
+    data = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "introselect_killers.npz"))
+    monkeypatch.setenv("PICO_B200_HUGE_MIN", "1024")
+    for key in data.files:
+        v = data[key]
+        pts = np.ascontiguousarray(np.stack([v, np.zeros_like(v)], axis=1))
+        o = oracle.OracleTree(pts, 10, rule="median")
+        t = pt.KdTree(pts, pt.Metric.L2Squared, 10, rule=pt.kd_tree.Rule.MedianMaxSide)
+        nodes, indices, _ = t.export()
+        assert np.array_equal(indices, o.indices), key
+        assert_same_structure(nodes_from_export(nodes, pts.dtype), o.nodes)
+    monkeypatch.delenv("PICO_B200_HUGE_MIN")
+
+
 def test_build_paths_agree(pt, monkeypatch):
     """The three ways a node can be split on the device — one warp, one CTA, grid-wide chunked passes
     (build.cu, PICO_B200_HUGE_MIN is the test hook for the threshold) — must leave the very same
@@ -535,6 +563,10 @@ def test_build_paths_agree(pt, monkeypatch):
         (D.uniform(100_000, 3, seed=9), {"rule": pt.kd_tree.Rule.MidpointMaxSide}),
         (D.uniform(90_000, 3, seed=9), {"max_leaf_depth": 6}),
         (D.sift_shape(40_000, 16, seed=4), {}),
+        # median rule: one CTA per node against groups of CTAs running introselect together (median_huge_level)
+        (D.lidar_shape(300_000, seed=5), {"rule": pt.kd_tree.Rule.MedianMaxSide}),
+        (clustered, {"rule": pt.kd_tree.Rule.MedianMaxSide}),
+        (rng.random((120_000, 2)), {"rule": pt.kd_tree.Rule.MedianMaxSide}),
     ]
     for pts, kw in cases:
         got = []
