@@ -314,7 +314,7 @@ int pico_b200_box(const pico_b200_tree* t, const void* mins, const void* maxs, s
                            offsets_out, indices_out, flags, stats);
 }
 
-void pico_b200_free(void* p) { free(p); }
+void pico_b200_free(void* p) { pico::release_result(p); }
 void pico_b200_free_device(void* p) {
   // The buffers come from the stream-ordered pool and go back into it (a later call re-uses the block instead of
   // paying a multi-gigabyte cudaMalloc). Like cudaFree, this waits for everything the device was given so far.

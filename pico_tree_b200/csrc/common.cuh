@@ -140,6 +140,8 @@ int upload_tree(pico_b200_tree* t, const T* h_pts, size_t stride, const void* no
 
 // fat.cu: (re)builds t->d_fat_nodes from t->d_nodes; every way of making a tree ends with it
 int build_fat_nodes(pico_b200_tree* t, cudaStream_t st);
+// search.cu: frees a host result of the ragged searches (one big block is kept for the next call)
+void release_result(void* p);
 
 // search.cu
 int order_state(const pico_b200_tree* t);  // pico_b200_order_hint::state after looking at the last measured batch

@@ -589,8 +589,28 @@ struct Staging {
 };
 Staging g_staging;
 
-void parallel_memcpy(char* dst, const char* src, size_t bytes) {
-  unsigned nt = std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+// host threads of the big copies (PICO_B200_COPY_THREADS overrides; tuning hook)
+unsigned copy_threads() {
+  static const unsigned v = [] {
+    const char* e = getenv("PICO_B200_COPY_THREADS");
+    const int x = e ? atoi(e) : 0;
+    if (x >= 1 && x <= 64) return (unsigned)x;
+    return std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+  }();
+  return v;
+}
+
+// ... and of the copy of a multi-gigabyte ragged result out of the staging buffers, where nothing else keeps the
+// host busy: into fresh pages 16 threads move 6.1 GB in 255 ms against 300 ms with 8; into the cached block both
+// take 200 ms (profiles/r2/radius_e2e_v1.txt)
+unsigned result_copy_threads() {
+  static const unsigned v = getenv("PICO_B200_COPY_THREADS")
+                                ? copy_threads()
+                                : std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+  return v;
+}
+
+void parallel_memcpy(char* dst, const char* src, size_t bytes, unsigned nt = copy_threads()) {
   if (bytes < ((size_t)4 << 20)) nt = 1;
   const size_t per = (bytes / nt + 4095) & ~(size_t)4095;
   std::vector<std::thread> th;
@@ -608,7 +628,7 @@ void parallel_pack_rows(char* dst, const char* src, size_t rows, size_t row_byte
     parallel_memcpy(dst, src, rows * row_bytes);
     return;
   }
-  unsigned nt = std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+  unsigned nt = copy_threads();
   if (rows * row_bytes < ((size_t)4 << 20)) nt = 1;
   const size_t per = (rows + nt - 1) / nt;
   auto work = [=](size_t b, size_t e) {
@@ -624,12 +644,45 @@ void parallel_pack_rows(char* dst, const char* src, size_t rows, size_t row_byte
 // Ragged results can be gigabytes of fresh host memory (cfg3 radius: 6.1 GB). Large buffers are aligned to 2 MiB and
 // offered to the kernel as transparent huge pages: the copy out of the pinned staging buffers then takes one page
 // fault per 2 MiB instead of one per 4 KiB. free() releases them like any malloc'd block (pico_b200_free).
+//
+// One such block is kept when the caller frees it (release_result, behind pico_b200_free) and handed to the next
+// big result that fits: its pages are already mapped, so the copy is not slowed by the kernel zeroing 2 MiB at
+// every first touch — the reference's users run the same radius search frame after frame. At most
+// PICO_B200_RESULT_CACHE_MB (default 8192, 0 = off) stay cached.
+struct ResultCache {
+  std::mutex mu;
+  std::vector<std::pair<void*, size_t>> big;  // every live huge-page block this library handed out (or caches)
+  void* spare = nullptr;
+  size_t spare_cap = 0;
+};
+ResultCache g_results;
+
+size_t result_cache_budget() {
+  static const size_t v = [] {
+    const char* e = getenv("PICO_B200_RESULT_CACHE_MB");
+    return (size_t)(e ? std::max(0L, atol(e)) : 8192L) << 20;
+  }();
+  return v;
+}
+
 void* alloc_result(size_t bytes) {
   constexpr size_t kHuge = (size_t)2 << 20;
   if (bytes >= 32 * kHuge) {
+    const size_t cap = (bytes + kHuge - 1) / kHuge * kHuge;
+    {
+      std::lock_guard<std::mutex> lock(g_results.mu);
+      if (g_results.spare && g_results.spare_cap >= cap && g_results.spare_cap / 2 <= cap) {
+        void* p = g_results.spare;
+        g_results.spare = nullptr;
+        g_results.spare_cap = 0;
+        return p;  // (still listed in `big`)
+      }
+    }
     void* p = nullptr;
-    if (posix_memalign(&p, kHuge, (bytes + kHuge - 1) / kHuge * kHuge) == 0) {
-      madvise(p, (bytes + kHuge - 1) / kHuge * kHuge, MADV_HUGEPAGE);
+    if (posix_memalign(&p, kHuge, cap) == 0) {
+      madvise(p, cap, MADV_HUGEPAGE);
+      std::lock_guard<std::mutex> lock(g_results.mu);
+      g_results.big.emplace_back(p, cap);
       return p;
     }
   }
@@ -640,7 +693,7 @@ void* alloc_result(size_t bytes) {
 // threads: a device-to-host copy into untouched pages otherwise takes its page faults one at a time
 // inside the driver (np.empty results: 160 MB took 200 ms).
 void parallel_touch(char* p, size_t bytes) {
-  const unsigned nt = std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+  const unsigned nt = copy_threads();
   const size_t per = ((bytes / nt) + 4095) & ~(size_t)4095;
   std::vector<std::thread> th;
   for (unsigned i = 0; i < nt; ++i) {
@@ -725,14 +778,14 @@ int copy_out(cudaStream_t st, void* h_dst, const void* d_src, size_t bytes) {
       rc = fail(PICO_B200_ERR_CUDA, "staged device-to-host copy failed");
     if (prev_len && !rc) {
       if (cudaEventSynchronize(ev[slot ^ 1]) != cudaSuccess) rc = fail(PICO_B200_ERR_CUDA, "staged copy sync failed");
-      if (!rc) parallel_memcpy(dst + prev_off, static_cast<const char*>(g_staging.buf[slot ^ 1]), prev_len);
+      if (!rc) parallel_memcpy(dst + prev_off, static_cast<const char*>(g_staging.buf[slot ^ 1]), prev_len, result_copy_threads());
     }
     prev_off = off;
     prev_len = len;
   }
   if (!rc && prev_len) {
     if (cudaEventSynchronize(ev[slot ^ 1]) != cudaSuccess) rc = fail(PICO_B200_ERR_CUDA, "staged copy sync failed");
-    if (!rc) parallel_memcpy(dst + prev_off, static_cast<const char*>(g_staging.buf[slot ^ 1]), prev_len);
+    if (!rc) parallel_memcpy(dst + prev_off, static_cast<const char*>(g_staging.buf[slot ^ 1]), prev_len, result_copy_threads());
   }
   cudaEventDestroy(ev[0]);
   cudaEventDestroy(ev[1]);
@@ -1655,6 +1708,31 @@ std::vector<std::pair<size_t, size_t>> host_chunk_plan(size_t nq, size_t chunk, 
 }
 
 }  // namespace
+
+// pico_b200_free: a huge-page result block is kept for the next big result instead of going back to the OS
+void release_result(void* p) {
+  if (!p) return;
+  void* drop = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(g_results.mu);
+    auto& big = g_results.big;
+    auto it = std::find_if(big.begin(), big.end(), [p](const std::pair<void*, size_t>& b) { return b.first == p; });
+    if (it == big.end()) {
+      drop = p;
+    } else if (it->second <= result_cache_budget() && it->second > g_results.spare_cap) {
+      drop = g_results.spare;  // the smaller spare goes
+      if (drop) big.erase(std::find_if(big.begin(), big.end(), [drop](const std::pair<void*, size_t>& b) { return b.first == drop; }));
+      // (`it` may have moved: look the block up again)
+      it = std::find_if(big.begin(), big.end(), [p](const std::pair<void*, size_t>& b) { return b.first == p; });
+      g_results.spare = p;
+      g_results.spare_cap = it->second;
+    } else {
+      big.erase(it);
+      drop = p;
+    }
+  }
+  free(drop);
+}
 
 // ------------------------------------------------------------------ knn
 template <typename T>

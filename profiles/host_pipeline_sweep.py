@@ -74,8 +74,12 @@ if __name__ == "__main__":
     tree_pts, q = D.bench_clouds()
     np.savez(CACHE, tree=tree_pts, q=q)
     print(run(FLOOR), flush=True)
+    timelines = ({"HOST_STREAMS": 8}, {"HOST_STREAMS": 8, "HOST_PRIO": 0})
     if len(sys.argv) > 1:   # python profiles/host_pipeline_sweep.py KEY=VAL,KEY=VAL ...   ("-" = library defaults)
-        points = [dict(kv.split("=") for kv in p.split(",") if kv and kv != "-") for p in sys.argv[1:]]
+        # (an argument that starts with "T:" asks for the per-chunk timeline of that point instead of its timing)
+        parse = lambda p: dict(kv.split("=") for kv in p.split(",") if kv and kv != "-")
+        points = [parse(p) for p in sys.argv[1:] if not p.startswith("T:")]
+        timelines = [parse(p[2:]) for p in sys.argv[1:] if p.startswith("T:")]
     else:
         points = [
             {},
@@ -93,5 +97,5 @@ if __name__ == "__main__":
     for env in points:
         print("%-95s %s" % (" ".join("%s=%s" % kv for kv in env.items()) or "(library defaults)", run(ONE, **env)),
               flush=True)
-    for env in ({"HOST_STREAMS": 8}, {"HOST_STREAMS": 8, "HOST_PRIO": 0}):
-        print("timeline %s\n%s" % (env, run(ONE, TIMELINE=1, **env)[-1500:]), flush=True)
+    for env in timelines:
+        print("timeline %s\n%s" % (env, run(ONE, TIMELINE=1, **env)[-2600:]), flush=True)

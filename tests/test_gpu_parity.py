@@ -518,6 +518,34 @@ def test_nth_element_heap_select_fallback(pt, oracle):
         assert_same_structure(nodes_from_export(nodes, pts.dtype), o.nodes)
 
 
+def test_big_ragged_result_block_is_reused_correctly(pt):
+    """A ragged host result of 64 MiB or more lives in a huge-page block that pico_b200_free keeps for the next big
+    result (search.cu alloc_result / release_result). Results written into a reused block — bigger than, equal
+    to and smaller than what the next call needs — must equal the ones written into fresh memory."""
+    import gc
+    from pico_tree_b200 import datasets as D
+    pts = D.lidar_shape(400_000, seed=2)
+    q = D.lidar_shape(300_000, seed=3, pose_shift=0.2)
+    t = pt.KdTree(pts, pt.Metric.L2Squared, 10)
+
+    def snapshot(r2):
+        res = t.search_radius(q, r2)
+        off, flat = res._offsets.copy(), res._flat[:int(res._offsets[-1])].copy()
+        del res
+        gc.collect()  # the block goes back to the library here
+        return off, flat
+
+    r2s = (0.25, 0.25, 0.16, 0.25, 0.36, 0.25)
+    first = {}
+    for r2 in r2s:
+        off, flat = snapshot(r2)
+        assert flat.nbytes >= 64 << 20, "the case must reach the huge-page path"
+        if r2 in first:
+            assert np.array_equal(off, first[r2][0]) and np.array_equal(flat, first[r2][1]), r2
+        else:
+            first[r2] = (off, flat)
+
+
 def test_median_rule_huge_nodes_match_oracle(pt, oracle, monkeypatch):
     """Median rule above the one-CTA threshold (build.cu median_huge_level: several CTAs per node, barriers in
     global memory): node table and index permutation equal to the oracle's std::nth_element build — at the
