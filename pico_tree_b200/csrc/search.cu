@@ -622,25 +622,6 @@ void parallel_memcpy(char* dst, const char* src, size_t bytes, unsigned nt = cop
   for (auto& t : th) t.join();
 }
 
-// rows of `row_bytes` lying `src_stride_bytes` apart -> packed rows
-void parallel_pack_rows(char* dst, const char* src, size_t rows, size_t row_bytes, size_t src_stride_bytes) {
-  if (src_stride_bytes == row_bytes) {
-    parallel_memcpy(dst, src, rows * row_bytes);
-    return;
-  }
-  unsigned nt = copy_threads();
-  if (rows * row_bytes < ((size_t)4 << 20)) nt = 1;
-  const size_t per = (rows + nt - 1) / nt;
-  auto work = [=](size_t b, size_t e) {
-    for (size_t r = b; r < e; ++r) memcpy(dst + r * row_bytes, src + r * src_stride_bytes, row_bytes);
-  };
-  std::vector<std::thread> th;
-  for (unsigned i = 1; i < nt; ++i)
-    if (i * per < rows) th.emplace_back(work, i * per, std::min(rows, (i + 1) * per));
-  work(0, std::min(rows, per));
-  for (auto& t : th) t.join();
-}
-
 // Ragged results can be gigabytes of fresh host memory (cfg3 radius: 6.1 GB). Large buffers are aligned to 2 MiB and
 // offered to the kernel as transparent huge pages: the copy out of the pinned staging buffers then takes one page
 // fault per 2 MiB instead of one per 4 KiB. free() releases them like any malloc'd block (pico_b200_free).
@@ -1852,25 +1833,107 @@ int knn_batch(const pico_b200_tree* t, const T* q, size_t nq, size_t stride, siz
     // feeding chunks
     std::atomic<size_t> enqueued{0};
     std::atomic<bool> failed{false}, drain_failed{false};
-    std::thread drain;
+    // Pageable buffers: ONE team of host threads that lives for the whole call. A single core of the host moves
+    // ~7 GB/s, so the 86 MB of queries and 58 MB of results of the headline batch are 20 ms of one thread's time:
+    // every worker PACKS query blocks into the pinned mirror while there are any (in chunk order, ahead of the chunk
+    // loop, which waits for a chunk's blocks and lends a hand while it does) and otherwise DRAINS result blocks of
+    // chunks whose device-to-host copy has completed, so the last chunk's results are moved by all of them.
+    // (One team per chunk, spawned and joined around every chunk, kept the enqueueing thread busy 0.6-0.9 ms per
+    // 1 Mi-query chunk: 6.5 ms per 7.2 M queries; a drain thread count sweep is in profiles/r2/pageable_pipeline.txt.)
+    struct Block {
+      uint32_t chunk;
+      size_t begin, count;  // rows of the batch (packing) / bytes of the result (draining)
+    };
+    std::vector<Block> pack_blocks, drain_blocks;
+    std::vector<std::atomic<uint32_t>> pack_left(stage_in ? n_chunks : 0);
+    std::vector<std::atomic<uint8_t>> chunk_out(stage_out ? n_chunks : 0);  // 1: the chunk's results are in the mirror
+    std::atomic<size_t> next_pack{0}, next_drain{0};
+    if (stage_in) {
+      const size_t rows_per_block = std::max<size_t>(1, ((size_t)768 << 10) / (sdim * sizeof(T)));
+      for (size_t ci = 0; ci < n_chunks; ++ci) {
+        uint32_t blocks = 0;
+        for (size_t r = 0; r < plan[ci].second; r += rows_per_block, ++blocks)
+          pack_blocks.push_back({(uint32_t)ci, plan[ci].first + r, std::min(rows_per_block, plan[ci].second - r)});
+        pack_left[ci].store(blocks, std::memory_order_relaxed);
+      }
+    }
     if (stage_out) {
+      const size_t bytes_per_block = (size_t)1 << 20;
+      for (size_t ci = 0; ci < n_chunks; ++ci) {
+        chunk_out[ci].store(0, std::memory_order_relaxed);
+        const size_t first = plan[ci].first * k * sizeof(Neighbor<T>), bytes = plan[ci].second * k * sizeof(Neighbor<T>);
+        for (size_t o = 0; o < bytes; o += bytes_per_block)
+          drain_blocks.push_back({(uint32_t)ci, first + o, std::min(bytes_per_block, bytes - o)});
+      }
+    }
+    auto pack_one = [&]() -> bool {
+      if (next_pack.load(std::memory_order_relaxed) >= pack_blocks.size()) return false;
+      const size_t b = next_pack.fetch_add(1, std::memory_order_relaxed);
+      if (b >= pack_blocks.size()) return false;
+      const Block& blk = pack_blocks[b];
+      char* to = reinterpret_cast<char*>(const_cast<T*>(src) + blk.begin * sdim);
+      const char* from = reinterpret_cast<const char*>(q + blk.begin * stride);
+      if (stride == sdim)
+        memcpy(to, from, blk.count * sdim * sizeof(T));
+      else
+        for (size_t r = 0; r < blk.count; ++r)
+          memcpy(to + r * sdim * sizeof(T), from + r * stride * sizeof(T), sdim * sizeof(T));
+      pack_left[blk.chunk].fetch_sub(1, std::memory_order_release);
+      return true;
+    };
+    // has the chunk's device-to-host copy completed? (asked of the driver until it has, then remembered)
+    auto chunk_ready = [&](uint32_t ci) -> bool {
+      if (chunk_out[ci].load(std::memory_order_acquire)) return true;
+      if (enqueued.load(std::memory_order_acquire) <= ci) return false;
+      const cudaError_t st = cudaEventQuery(done[ci]);
+      if (st == cudaSuccess) {
+        chunk_out[ci].store(1, std::memory_order_release);
+        return true;
+      }
+      if (st != cudaErrorNotReady) drain_failed.store(true);
+      cudaGetLastError();
+      return false;
+    };
+    // 1: moved a block; 0: the next block's chunk is not there yet; -1: nothing left to drain
+    auto drain_one = [&]() -> int {
+      const size_t peek = next_drain.load(std::memory_order_relaxed);
+      if (peek >= drain_blocks.size()) return -1;
+      if (!chunk_ready(drain_blocks[peek].chunk)) return 0;
+      const size_t b = next_drain.fetch_add(1, std::memory_order_relaxed);
+      if (b >= drain_blocks.size()) return -1;
+      const Block& blk = drain_blocks[b];
+      while (!chunk_ready(blk.chunk)) {  // (another worker took the block peeked at; this one belongs to a later chunk)
+        if (failed.load() || drain_failed.load()) return -1;
+        std::this_thread::yield();
+      }
+      memcpy(reinterpret_cast<char*>(out) + blk.begin, reinterpret_cast<const char*>(dst) + blk.begin, blk.count);
+      return 1;
+    };
+    auto work = [&] {
+      for (;;) {
+        if (failed.load(std::memory_order_relaxed) || drain_failed.load(std::memory_order_relaxed)) return;
+        if (stage_in && pack_one()) continue;
+        if (!stage_out) return;
+        const int d = drain_one();
+        if (d < 0) return;
+        if (d == 0) std::this_thread::yield();
+      }
+    };
+    std::vector<std::thread> team;
+    if (stage_in || stage_out) {
+      static const unsigned workers = [] {
+        const char* e = getenv("PICO_B200_HOST_WORKERS");  // tuning hook
+        const int x = e ? atoi(e) : 0;
+        if (x >= 1 && x <= 64) return (unsigned)x;
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        return std::max(1u, std::min(14u, hw > 2 ? hw - 2 : 1u));
+      }();
       const int device = t->device;
-      drain = std::thread([&, device] {
-        cudaSetDevice(device);
-        for (size_t ci = 0; ci < n_chunks; ++ci) {
-          while (enqueued.load(std::memory_order_acquire) <= ci) {
-            if (failed.load()) return;
-            std::this_thread::yield();
-          }
-          if (cudaEventSynchronize(done[ci]) != cudaSuccess) {
-            drain_failed.store(true);
-            return;
-          }
-          const size_t begin = plan[ci].first, cnt = plan[ci].second;
-          parallel_memcpy(reinterpret_cast<char*>(out + begin * k), reinterpret_cast<const char*>(dst + begin * k),
-                          cnt * k * sizeof(Neighbor<T>));
-        }
-      });
+      for (unsigned i = 0; i < workers; ++i)
+        team.emplace_back([&, device] {
+          cudaSetDevice(device);
+          work();
+        });
     }
     int rc = 0;
     const bool timeline = host_timeline() && n_chunks <= (size_t)n_streams;
@@ -1905,10 +1968,9 @@ int knn_batch(const pico_b200_tree* t, const T* q, size_t nq, size_t stride, siz
           rc = fail(PICO_B200_ERR_CUDA, "result copy failed");
         if (!rc) rc = c.mark(4);
       } else {
-        if (stage_in)
-          parallel_pack_rows(reinterpret_cast<char*>(const_cast<T*>(src) + begin * sdim),
-                             reinterpret_cast<const char*>(q + begin * stride), cnt, sdim * sizeof(T),
-                             stride * sizeof(T));
+        if (stage_in)  // the chunk's queries must be in the mirror; pack blocks (of any chunk) while waiting
+          while (pack_left[ci].load(std::memory_order_acquire) != 0)
+            if (!pack_one()) std::this_thread::yield();
         if (touch_out) parallel_touch(reinterpret_cast<char*>(out + begin * k), cnt * k * sizeof(Neighbor<T>));
         rc = knn_enqueue<T>(c, t, src + begin * src_stride, cnt, src_stride, k, e, dst + begin * k, flags, false,
                             &launches);
@@ -1919,7 +1981,8 @@ int knn_batch(const pico_b200_tree* t, const T* q, size_t nq, size_t stride, siz
       enqueued.store(ci + 1, std::memory_order_release);
       cpu_at[2 * ci + 1] = cpu_ms();
     }
-    if (drain.joinable()) drain.join();
+    if (!team.empty()) work();  // the enqueueing thread helps with what is left
+    for (auto& th : team) th.join();
     for (auto& ev : done) cudaEventDestroy(ev);
     if (rc || drain_failed.load())  // quiesce before the events the streams wait on go away
       for (int i = 0; i < n_streams; ++i) cudaStreamSynchronize(ctx[i].st);
