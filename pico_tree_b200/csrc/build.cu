@@ -1135,15 +1135,32 @@ int stage_points(const T* h_pts, size_t n, size_t sdim, size_t stride, T* d_raw,
   return 0;
 }
 
-// The tree's own arrays come from the stream-ordered pool as well (its release threshold is raised in api.cu): a
-// rebuild — one per LiDAR frame in the reference's use — gets the blocks of the tree it replaces back within
-// microseconds, where cudaMalloc spent 4.5 of a 13 ms build mapping fresh memory (profiles/r2/build_timeline_*.txt).
-// pico_b200_tree_destroy releases them with cudaFree, which accepts pool allocations and waits for the device.
+// The tree's own arrays are plain cudaMalloc blocks. Taking them from the stream-ordered pool like the workspaces
+// makes a REBUILD marginally cheaper (9.4 against 9.8 ms) but leaves long-lived blocks inside the pool, and the
+// multi-gigabyte result arrays of the ragged searches then cost 8-17 ms more per call to place (resident radius
+// 21 -> 29-38 ms per call after other trees had been built and searched, profiles/r2/tree_pool.txt); the first
+// full-size build of a process pays the pool's growth inside its timed region as well (13.5 -> 30-42 ms).
+int tree_alloc(void** p, size_t bytes, cudaStream_t st) {
+  static const bool pooled = [] {
+    const char* e = getenv("PICO_B200_TREE_POOL");  // 1: from the stream-ordered pool (measurement hook)
+    return e && atoi(e) == 1;
+  }();
+  if (pooled)
+    PICO_CUDA(cudaMallocAsync(p, bytes ? bytes : 16, st));
+  else
+    PICO_CUDA(cudaMalloc(p, bytes ? bytes : 16));
+  return 0;
+}
+template <typename P>
+int tree_alloc(P** p, size_t bytes, cudaStream_t st) {
+  return tree_alloc(reinterpret_cast<void**>(p), bytes, st);
+}
+
 template <typename T>
 int finalize_storage(pico_b200_tree* t, const T* d_raw, cudaStream_t st) {
   const size_t n = t->n;
   const int sdim = (int)t->sdim;
-  PICO_CUDA(cudaMallocAsync(&t->d_pts, t->pts_bytes() ? t->pts_bytes() : 16, st));
+  PICO_TRY(tree_alloc(&t->d_pts, t->pts_bytes() ? t->pts_bytes() : 16, st));
   if (t->packed()) {
     pack_points4<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_raw, t->d_indices, n, sdim,
                                                                   static_cast<typename Vec4Of<T>::type*>(t->d_pts));
@@ -1227,8 +1244,8 @@ int build_tree(pico_b200_tree* t, const T* h_pts, size_t stride, int rule, int s
   DevBuf raw, tmp, tmp2, nodes, boxes, counters, big_a, big_b, partial, huge_a, huge_b, huge_nodes, chunk_stats;
   PICO_TRY(alloc(raw, n * sdim * sizeof(T), st));
   PICO_TRY(stage_points(h_pts, n, sdim, stride, raw.as<T>(), st));
-  PICO_CUDA(cudaMallocAsync(&t->d_indices, n * sizeof(int32_t), st));
-  PICO_CUDA(cudaMallocAsync(&t->d_root_box, 2 * sdim * sizeof(T), st));
+  PICO_TRY(tree_alloc(&t->d_indices, n * sizeof(int32_t), st));
+  PICO_TRY(tree_alloc(&t->d_root_box, 2 * sdim * sizeof(T), st));
   PICO_TRY(alloc(tmp, n * sizeof(int32_t), st));
   PICO_TRY(alloc(tmp2, n * sizeof(int32_t), st));
 
@@ -1431,9 +1448,9 @@ int build_tree(pico_b200_tree* t, const T* h_pts, size_t stride, int rule, int s
     const uint32_t lb = level_start[l], le = level_start[l + 1];
     number_level<T><<<(le - lb + 127) / 128, 128, 0, st>>>(s.nodes, lb, le);
   }
-  PICO_CUDA(cudaMallocAsync(&t->d_nodes, (size_t)n_nodes * t->node_size(), st));
-  if (t->outer_bytes()) PICO_CUDA(cudaMallocAsync(&t->d_outer, t->outer_bytes(), st));
-  if (!t->packed()) PICO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&t->d_spans), t->spans_bytes(), st));
+  PICO_TRY(tree_alloc(&t->d_nodes, (size_t)n_nodes * t->node_size(), st));
+  if (t->outer_bytes()) PICO_TRY(tree_alloc(&t->d_outer, t->outer_bytes(), st));
+  if (!t->packed()) PICO_TRY(tree_alloc(reinterpret_cast<void**>(&t->d_spans), t->spans_bytes(), st));
   emit_nodes<T><<<(n_nodes + 255) / 256, 256, 0, st>>>(s.nodes, n_nodes,
                                                         static_cast<typename NodeOf<T>::type*>(t->d_nodes),
                                                         static_cast<T*>(t->d_outer), t->d_spans);
@@ -1500,9 +1517,9 @@ int upload_tree(pico_b200_tree* t, const T* h_pts, size_t stride, const void* h_
   DevBuf raw;
   PICO_TRY(alloc(raw, n * sdim * sizeof(T), st));
   PICO_TRY(stage_points(h_pts, n, sdim, stride, raw.as<T>(), st));
-  PICO_CUDA(cudaMallocAsync(&t->d_indices, n * sizeof(int32_t), st));
-  PICO_CUDA(cudaMallocAsync(&t->d_root_box, 2 * sdim * sizeof(T), st));
-  PICO_CUDA(cudaMallocAsync(&t->d_nodes, n_nodes * sizeof(NodeT), st));
+  PICO_TRY(tree_alloc(&t->d_indices, n * sizeof(int32_t), st));
+  PICO_TRY(tree_alloc(&t->d_root_box, 2 * sdim * sizeof(T), st));
+  PICO_TRY(tree_alloc(&t->d_nodes, n_nodes * sizeof(NodeT), st));
   PICO_CUDA(cudaMemcpyAsync(t->d_indices, indices, n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   PICO_CUDA(cudaMemcpyAsync(t->d_root_box, root_box, 2 * sdim * sizeof(T), cudaMemcpyHostToDevice, st));
   PICO_CUDA(cudaMemcpyAsync(t->d_nodes, nodes, n_nodes * sizeof(NodeT), cudaMemcpyHostToDevice, st));
@@ -1517,13 +1534,13 @@ int upload_tree(pico_b200_tree* t, const T* h_pts, size_t stride, const void* h_
         spans[i] = make_uint2(l.x, l.y + r.y);
       }
     }
-    PICO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&t->d_spans), t->spans_bytes(), st));
+    PICO_TRY(tree_alloc(reinterpret_cast<void**>(&t->d_spans), t->spans_bytes(), st));
     PICO_CUDA(cudaMemcpyAsync(t->d_spans, spans.data(), t->spans_bytes(), cudaMemcpyHostToDevice, st));
     PICO_CUDA(cudaStreamSynchronize(st));
   }
   if (t->topological()) {
     if (!outer_bounds) return fail(PICO_B200_ERR_INVALID_ARGUMENT, "topological metric needs the outer bounds");
-    PICO_CUDA(cudaMallocAsync(&t->d_outer, t->outer_bytes(), st));
+    PICO_TRY(tree_alloc(&t->d_outer, t->outer_bytes(), st));
     PICO_CUDA(cudaMemcpyAsync(t->d_outer, outer_bounds, t->outer_bytes(), cudaMemcpyHostToDevice, st));
   }
   for (int d = 0; d < sdim && d < 4; ++d) {
