@@ -94,6 +94,61 @@ struct scalar_id<float> : std::integral_constant<int, PICO_B200_F32> {};
 template <>
 struct scalar_id<double> : std::integral_constant<int, PICO_B200_F64> {};
 
+// Re-encodes the index width of a reference tree stream (kd_tree_data.hpp:89-135): [sdim u64][n u64][n indices]
+// [root box][nodes in pre-order: a leaf flag byte, then {begin, end} as indices for a leaf or a branch record of
+// `branch_bytes`]. `consumed` receives the bytes of the INPUT stream that belong to the tree.
+template <typename From_, typename To_>
+inline std::vector<char> recode_stream_index(char const* src, std::size_t size, std::size_t branch_bytes,
+                                             std::size_t scalar_bytes, std::uint64_t* consumed) {
+  char const* p = src;
+  char const* const end = src + size;
+  std::vector<char> out;
+  auto need = [&](std::size_t n) {
+    if (static_cast<std::size_t>(end - p) < n) throw std::runtime_error("tree stream ends early");
+  };
+  auto copy = [&](std::size_t n) {
+    need(n);
+    out.insert(out.end(), p, p + n);
+    p += n;
+  };
+  auto index = [&] {
+    need(sizeof(From_));
+    From_ v;
+    std::memcpy(&v, p, sizeof(From_));
+    p += sizeof(From_);
+    To_ const w = static_cast<To_>(v);
+    if (static_cast<From_>(w) != v || ((v < From_(0)) != (w < To_(0))))
+      throw std::runtime_error("tree stream holds an index the other index type cannot represent");
+    char b[sizeof(To_)];
+    std::memcpy(b, &w, sizeof(To_));
+    out.insert(out.end(), b, b + sizeof(To_));
+  };
+  need(16);
+  std::uint64_t sdim = 0, n = 0;
+  std::memcpy(&sdim, p, 8);
+  std::memcpy(&n, p + 8, 8);
+  copy(16);
+  if (n > size / sizeof(From_)) throw std::runtime_error("tree stream ends early");
+  out.reserve(size / sizeof(From_) * sizeof(To_) + 64);
+  for (std::uint64_t i = 0; i < n; ++i) index();
+  copy(2 * sdim * scalar_bytes);  // the root box: min, then max
+  for (std::uint64_t pending = 1; pending > 0;) {
+    need(1);
+    bool const leaf = *p != 0;
+    copy(1);
+    if (leaf) {
+      index();
+      index();
+      --pending;
+    } else {
+      copy(branch_bytes);
+      ++pending;
+    }
+  }
+  if (consumed) *consumed = static_cast<std::uint64_t>(p - src);
+  return out;
+}
+
 // Metrics the device implements. A user-defined metric type has no device functor: the
 // static_assert in kd_tree points here.
 template <typename Metric_>
@@ -540,14 +595,25 @@ class kd_tree {
   }
 
   static kd_tree load(space_type space, std::iostream& stream) {
-    static_assert(sizeof(index_type) == 4, "LOAD_AND_SAVE_NEED_A_32_BIT_INDEX_TYPE");
     auto const pos = stream.tellg();
     std::vector<char> bytes((std::istreambuf_iterator<char>(stream)), std::istreambuf_iterator<char>());
     std::uint64_t consumed = 0;
-    kd_tree tree(std::move(space), bytes.data(), bytes.size(), &consumed);
-    stream.clear();
-    stream.seekg(pos + static_cast<std::streamoff>(consumed));
-    return tree;
+    if constexpr (sizeof(index_type) == 4) {
+      kd_tree tree(std::move(space), bytes.data(), bytes.size(), &consumed);
+      stream.clear();
+      stream.seekg(pos + static_cast<std::streamoff>(consumed));
+      return tree;
+    } else {
+      // the reference writes the permutation and the leaf ranges as Index_ (kd_tree_data.hpp:89-135); the device
+      // keeps 32-bit indices, so a stream of another index width is re-encoded on the way in and out
+      std::vector<char> const narrow =
+          b200::recode_stream_index<index_type, std::int32_t>(bytes.data(), bytes.size(), branch_record_bytes(),
+                                                              sizeof(scalar_type), &consumed);
+      kd_tree tree(std::move(space), narrow.data(), narrow.size(), nullptr);
+      stream.clear();
+      stream.seekg(pos + static_cast<std::streamoff>(consumed));
+      return tree;
+    }
   }
 
   static void save(kd_tree const& tree, std::string const& filename) {
@@ -557,15 +623,25 @@ class kd_tree {
   }
 
   static void save(kd_tree const& tree, std::iostream& stream) {
-    static_assert(sizeof(index_type) == 4, "LOAD_AND_SAVE_NEED_A_32_BIT_INDEX_TYPE");
     std::uint64_t bytes = 0;
     b200::check(pico_b200_tree_save_size(tree.handle_.get(), &bytes));
     std::vector<char> buf(bytes);
     b200::check(pico_b200_tree_save(tree.handle_.get(), buf.data()));
+    if constexpr (sizeof(index_type) != 4)
+      buf = b200::recode_stream_index<std::int32_t, index_type>(buf.data(), buf.size(), branch_record_bytes(),
+                                                                sizeof(scalar_type), nullptr);
     stream.write(buf.data(), static_cast<std::streamsize>(buf.size()));
   }
 
  private:
+  // bytes of one branch record of the reference's stream: kd_tree_branch_split (euclidean) or
+  // kd_tree_branch_double (topological spaces) of kd_tree_node.hpp:28-60, written as the struct lies in memory
+  static constexpr std::size_t branch_record_bytes() {
+    struct split { int split_dim; scalar_type left_max, right_min; };
+    struct twice { int split_dim; scalar_type left_min, left_max, right_min, right_max; };
+    return std::is_same_v<typename Metric_::space_category, euclidean_space_tag> ? sizeof(split) : sizeof(twice);
+  }
+
   struct host_mirror {
     b200::host_tree<scalar_type> tree;  // flat nodes, permutation, outer bounds (host_search.hpp)
     std::vector<index_type> indices;    // the permutation as index_type (leaf_ranges)

@@ -1272,9 +1272,11 @@ int build_tree(pico_b200_tree* t, const T* h_pts, size_t stride, int rule, int s
   if (rule == PICO_B200_RULE_MEDIAN_MAX_SIDE && n > (size_t)huge_min) {
     int per_sm = 0;
     PICO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, median_huge_level<T>, kBigThreads, 0));
-    coop_grid = per_sm * t->sm_count;
-    if (coop_grid < 1) return fail(PICO_B200_ERR_CUDA, "median_huge_level does not fit an SM");
-    PICO_TRY(alloc(coop, (size_t)coop_grid * 3 * sizeof(int32_t), st));
+    int can_cooperate = 0;
+    cudaDeviceGetAttribute(&can_cooperate, cudaDevAttrCooperativeLaunch, t->device);
+    coop_grid = can_cooperate ? per_sm * t->sm_count : 0;
+    if (const char* e = getenv("PICO_B200_MEDIAN_COOP")) coop_grid = atoi(e) == 0 ? 0 : coop_grid;  // test hook
+    PICO_TRY(alloc(coop, (size_t)std::max(coop_grid, 1) * 3 * sizeof(int32_t), st));
   }
 
   // build_ms covers the kernels and the per-level round trips, not the allocations above
@@ -1385,7 +1387,7 @@ int build_tree(pico_b200_tree* t, const T* h_pts, size_t stride, int rule, int s
     s.huge_next = huge_nxt;
     PICO_CUDA(cudaMemsetAsync(s.counters + 1, 0, sizeof(uint32_t), st));
     PICO_CUDA(cudaMemsetAsync(s.counters + 3, 0, 2 * sizeof(uint32_t), st));
-    if (n_huge && rule == PICO_B200_RULE_MEDIAN_MAX_SIDE) {
+    if (n_huge && rule == PICO_B200_RULE_MEDIAN_MAX_SIDE && coop_grid > 0) {
       // equal groups of co-resident CTAs, one per huge node (as many nodes at a time as there are groups)
       const int ctas = std::max(1, coop_grid / (int)std::min<uint32_t>(n_huge, (uint32_t)coop_grid));
       PICO_CUDA(cudaMemsetAsync(coop.p, 0, (size_t)coop_grid * sizeof(unsigned), st));
@@ -1394,8 +1396,16 @@ int build_tree(pico_b200_tree* t, const T* h_pts, size_t stride, int rule, int s
       unsigned* bars = coop.as<unsigned>();
       int32_t* cnts = coop.as<int32_t>() + coop_grid;
       void* args[] = {&s, &list, &nh, const_cast<int*>(&ctas), &bars, &cnts};
-      PICO_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(&median_huge_level<T>), dim3(coop_grid),
-                                            dim3(kBigThreads), args, 0, st));
+      if (cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(&median_huge_level<T>), dim3(coop_grid),
+                                      dim3(kBigThreads), args, 0, st) != cudaSuccess) {
+        // a device that cannot keep the grid resident (a partitioned or shared GPU): one CTA per huge node, the
+        // slow but equivalent way
+        cudaGetLastError();
+        coop_grid = 0;
+        median_level_block<T><<<n_huge, kBigThreads, 0, st>>>(s, huge_cur);
+      }
+    } else if (n_huge && rule == PICO_B200_RULE_MEDIAN_MAX_SIDE) {
+      median_level_block<T><<<n_huge, kBigThreads, 0, st>>>(s, huge_cur);
     } else if (n_huge) {
       // every chunk kernel is launched over an upper bound of the level's chunk count
       const unsigned chunk_grid = (unsigned)std::min<size_t>(n / kChunk + n_huge + 1, chunk_cap);

@@ -11,6 +11,7 @@
 #include <array>
 #include <cmath>
 #include <cstdio>
+#include <fstream>
 #include <numeric>
 #include <random>
 #include <sstream>
@@ -358,6 +359,66 @@ TEST(KdTreeDropIn, IteratorOverloadsAndWideIndex) {
   tree.search_knn(q, 6000, all);
   EXPECT_EQ(all.size(), pts.size());
   EXPECT_TRUE(std::is_sorted(all.begin(), all.end()));
+}
+
+// save / load with an index type that is not 32 bits wide: the stream must be the one the reference writes for that
+// Index_ (golden files made by tests/golden/make_wide_index_streams.cpp from the unmodified reference headers), and a
+// stream written by the reference must load.
+namespace {
+template <typename Metric_>
+void wide_index_round_trip(char const* file) {
+  std::ifstream in(std::string(GOLDEN_DIR) + "/" + file, std::ios::binary);
+  ASSERT_EQ(in.is_open(), true);
+  auto u64 = [&] {
+    std::uint64_t v = 0;
+    in.read(reinterpret_cast<char*>(&v), 8);
+    return v;
+  };
+  std::uint64_t const n = u64(), dim = u64();
+  ASSERT_EQ(dim, std::uint64_t(3));
+  std::vector<point_3f> pts(n);
+  in.read(reinterpret_cast<char*>(pts.data()), static_cast<std::streamsize>(n * sizeof(point_3f)));
+  std::string s_int(u64(), '\0');
+  in.read(s_int.data(), static_cast<std::streamsize>(s_int.size()));
+  std::string s_long(u64(), '\0');
+  in.read(s_long.data(), static_cast<std::streamsize>(s_long.size()));
+
+  using tree_long = pico_tree::kd_tree<space<point_3f>, Metric_, long>;
+  using tree_int = pico_tree::kd_tree<space<point_3f>, Metric_, int>;
+  tree_long built(pts, pico_tree::max_leaf_size_t(8));
+  std::stringstream ours;
+  tree_long::save(built, ours);
+  EXPECT_TRUE(ours.str() == s_long);
+  std::stringstream ours_int;
+  tree_int built_int(pts, pico_tree::max_leaf_size_t(8));
+  tree_int::save(built_int, ours_int);
+  EXPECT_TRUE(ours_int.str() == s_int);
+
+  std::stringstream theirs;
+  theirs.write("xy", 2);
+  theirs.write(s_long.data(), static_cast<std::streamsize>(s_long.size()));
+  theirs.write("z", 1);
+  theirs.seekg(2);
+  tree_long loaded = tree_long::load(pts, theirs);
+  char z = 0;
+  theirs.read(&z, 1);
+  EXPECT_EQ(z, 'z');
+  std::vector<typename tree_long::neighbor_type> a, b;
+  for (std::size_t i = 0; i < 50; ++i) {
+    built.search_knn(pts[i * 7], 5, a);
+    loaded.search_knn(pts[i * 7], 5, b);
+    ASSERT_EQ(a.size(), b.size());
+    for (std::size_t j = 0; j < a.size(); ++j) {
+      EXPECT_EQ(a[j].index, b[j].index);
+      EXPECT_EQ(a[j].distance, b[j].distance);
+    }
+  }
+}
+}  // namespace
+
+TEST(KdTreeDropIn, SaveLoadWithWideIndexMatchesReferenceStream) {
+  wide_index_round_trip<pico_tree::metric_l2_squared>("l2.bin");
+  wide_index_round_trip<pico_tree::metric_se2_squared>("se2.bin");
 }
 
 namespace {

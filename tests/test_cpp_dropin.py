@@ -30,6 +30,16 @@ def test_cpp_suite_builds():
     assert os.access(os.path.join(BIN, "kd_tree_test"), os.X_OK)
 
 
+def test_stream_index_width_recoding_matches_reference_streams():
+    """kd_tree::save / load with an Index_ that is not 32 bits wide re-encode the stream on the host
+    (kd_tree.hpp recode_stream_index): int -> long and long -> int must reproduce, byte for byte, what the unmodified
+    reference saves for either index type over the same points (tests/golden/wide_index, euclidean and topological
+    branch records). Host code only."""
+    _make(os.path.join(BIN, "stream_index_test"))
+    r = subprocess.run([os.path.join(BIN, "stream_index_test")], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and " 0 failed" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+
+
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference sources only exist in the dev container")
 def test_reference_examples_compile_against_dropin(tmp_path):
     """examples/kd_tree/*.cpp of the reference, unmodified, against our kd_tree.hpp + the reference's own

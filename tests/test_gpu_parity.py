@@ -554,13 +554,17 @@ def test_median_rule_huge_nodes_match_oracle(pt, oracle, monkeypatch):
     from pico_tree_b200 import datasets as D
     pts = D.lidar_shape(400_000, seed=11)
     o = oracle.OracleTree(pts, 10, rule="median")
-    for huge_min in (None, "2048"):
+    for huge_min, coop in ((None, None), ("2048", None), (None, "0")):
         if huge_min:
             monkeypatch.setenv("PICO_B200_HUGE_MIN", huge_min)
+        if coop:  # the fallback of a device that cannot hold the cooperative grid: one CTA per huge node
+            monkeypatch.setenv("PICO_B200_MEDIAN_COOP", coop)
         t = pt.KdTree(pts, pt.Metric.L2Squared, 10, rule=pt.kd_tree.Rule.MedianMaxSide)
         nodes, indices, _ = t.export()
-        assert np.array_equal(indices, o.indices), huge_min
+        assert np.array_equal(indices, o.indices), (huge_min, coop)
         assert_same_structure(nodes_from_export(nodes, pts.dtype), o.nodes)
+        monkeypatch.delenv("PICO_B200_HUGE_MIN", raising=False)
+        monkeypatch.delenv("PICO_B200_MEDIAN_COOP", raising=False)
     data = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "introselect_killers.npz"))
     monkeypatch.setenv("PICO_B200_HUGE_MIN", "1024")
     for key in data.files:
