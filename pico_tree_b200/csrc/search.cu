@@ -125,8 +125,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock) knn_thread_kernel(KnnArgs<T>
         traverse_packed<T, DIM, FAST, kPrimeFirstLeaf>(a.nodes, a.pts4, a.outer, q, a.metric, a.approx != 0, a.e_inv, st,
                                                        vis);
       }
-      out->index = vis.idx;
-      out->distance = vis.best;
+      store_neighbor(out, vis.idx, vis.best);
     } else {
       VisitKnn<T, KMAX> vis;
       vis.init(a.k);
@@ -171,8 +170,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, MINB) nn_kernel(KnnArgs<T> a
     st.y = s_y;
     traverse_nn<T, DIM, NREC, FAT>(a.fat, a.far_nodes, a.pts4, q, st, vis);
     Neighbor<T>* out = a.out + qi;
-    out->index = vis.idx;
-    out->distance = vis.best;
+    store_neighbor(out, vis.idx, vis.best);
     if (FAT && vis.tie) a.tie_list[atomicAdd(a.tie_count, 1u)] = qi;
   }
 }
@@ -236,8 +234,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock) leaf_scan_kernel(KnnArgs<T> 
       if (DIM > 2) d = metric_fold((int)PICO_B200_METRIC_L2_SQUARED, d, q[DIM > 2 ? 2 : 0], p.z, 2);
       vis.visit(index_of(p), d);
     }
-    a.out[qi].index = vis.idx;
-    a.out[qi].distance = vis.best;
+    store_neighbor(a.out + qi, vis.idx, vis.best);
   }
 }
 
@@ -251,7 +248,7 @@ struct RadiusArgs {
 };
 
 template <typename T, int DIM, bool FILL, bool DEEP>
-__global__ void __launch_bounds__(kThreadsPerBlock) radius_thread_kernel(RadiusArgs<T> r) {
+__global__ void __launch_bounds__(kThreadsPerBlock, 16) radius_thread_kernel(RadiusArgs<T> r) {
   const KnnArgs<T>& a = r.base;
   const size_t total = (size_t)gridDim.x * blockDim.x;
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -273,11 +270,12 @@ __global__ void __launch_bounds__(kThreadsPerBlock) radius_thread_kernel(RadiusA
     if (FILL) {
       VisitRadiusFill<T> vis;
       vis.radius = r.radius;
-      vis.out = r.hits + r.offsets[qi];
+      vis.begin(r.hits + r.offsets[qi]);
       if (DEEP)
         traverse_packed<T, DIM, false, kPrimeNone>(a.nodes, a.pts4, a.outer, q, a.metric, a.approx != 0, a.e_inv, gst, vis);
       else
         traverse_packed<T, DIM, false, kPrimeNone>(a.nodes, a.pts4, a.outer, q, a.metric, a.approx != 0, a.e_inv, lst, vis);
+      vis.finish();
     } else {
       VisitRadiusCount<T> vis;
       vis.radius = r.radius;
@@ -1047,8 +1045,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, 2048 / kThreadsPerBlock) nn_
       load_node(a.nodes, node, na, nb, right, sd, lb, le);
     }
     Neighbor<T>* out = a.out + qi;
-    out->index = vis.idx;
-    out->distance = vis.best;
+    store_neighbor(out, vis.idx, vis.best);
     if (vis.tie || overflow) redo[qi] = 1;
   }
   __syncthreads();
@@ -1098,8 +1095,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock) nn_redo_kernel(KnnArgs<float
   VisitNn<T> vis;
   LocalStack<T, DIM, kLocalStack> st;
   traverse_packed<T, DIM, true, kPrimeFirstLeaf>(a.nodes, a.pts4, a.outer, q, a.metric, false, a.e_inv, st, vis);
-  a.out[qi].index = vis.idx;
-  a.out[qi].distance = vis.best;
+  store_neighbor(a.out + qi, vis.idx, vis.best);
 }
 
 // ---- order and traverse in one kernel (k = 1, metric_l2_squared, batches that arrive locally coherent)
@@ -1158,8 +1154,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, 2048 / kThreadsPerBlock) nn_
     LocalStack<T, DIM, kLocalStack> st;
     traverse_packed<T, DIM, true, kPrimeFirstLeaf>(a.nodes, a.pts4, a.outer, q, a.metric, false, a.e_inv, st, vis);
     Neighbor<T>* out = a.out + qi;
-    out->index = vis.idx;
-    out->distance = vis.best;
+    store_neighbor(out, vis.idx, vis.best);
   }
 }
 

@@ -395,6 +395,21 @@ __device__ __forceinline__ void traverse_packed(const typename NodeOf<T>::type* 
   }
 }
 
+// One neighbour record. {int, float} has an alignment of four, so the compiler writes it as two 4-byte stores; rows that
+// sit on an 8-byte boundary (every buffer a CUDA or host allocator hands out) take one 8-byte store instead — half
+// the store instructions and no half-written records on their way through L2.
+template <typename T>
+__device__ __forceinline__ void store_neighbor(Neighbor<T>* p, int idx, T d) {
+  if constexpr (sizeof(Neighbor<T>) == 8) {
+    if ((reinterpret_cast<uintptr_t>(p) & 7) == 0) {
+      *reinterpret_cast<int2*>(p) = make_int2(idx, __float_as_int(d));
+      return;
+    }
+  }
+  p->index = idx;
+  p->distance = d;
+}
+
 // ---------------------------------------------------------------- visitors (thread-local)
 // search_nn, search_visitor.hpp:41-65 (+ approximate :164-191; scaling done by the caller)
 template <typename T>
@@ -457,12 +472,20 @@ struct VisitKnn {
   }
   // row = k neighbour records, ascending
   __device__ __forceinline__ void store(Neighbor<T>* row) const {
+    if constexpr (sizeof(Neighbor<T>) == 8 && KMAX % 2 == 0) {
+      // a full list of 8-byte records at a 16-byte boundary leaves as KMAX / 2 16-byte stores
+      if (k == KMAX && (reinterpret_cast<uintptr_t>(row) & 15) == 0) {
+#pragma unroll
+        for (int i = 0; i < KMAX; i += 2)
+          reinterpret_cast<int4*>(row)[i / 2] = make_int4(id[i], __float_as_int(d[i]), id[i + 1], __float_as_int(d[i + 1]));
+        return;
+      }
+    }
     Neighbor<T>* shifted = row - (KMAX - k);
 #pragma unroll
     for (int i = 0; i < KMAX; ++i) {
       if (i >= KMAX - k) {
-        shifted[i].index = id[i];
-        shifted[i].distance = d[i];
+        store_neighbor(shifted + i, id[i], d[i]);
       }
     }
   }
@@ -476,16 +499,70 @@ struct VisitRadiusCount {
   __device__ __forceinline__ T max() const { return radius; }
   __device__ __forceinline__ void visit(int, T d) { count += (radius > d); }
 };
+// Fill pass. Every thread writes its query's hits one behind the other, so a store of one 8-byte neighbour touches a
+// quarter of a 32-byte sector, and 32 lanes touch 32 different sectors: the fill pass of cfg3 moved 3.8 GB to DRAM and
+// 2.1 GB from it for 1.7 GB of hits and took 2.2x the count pass (profiles/r2/late_search_ncu_summary.txt). For 8-byte
+// neighbours the hits of one SECTOR of the result are therefore collected in registers and leave as two 16-byte stores
+// when the sector is complete; only the first and the last sector of a query, which it may share with its
+// neighbours in the array, are written hit by hit (begin / finish). The order of the hits is untouched.
 template <typename T>
 struct VisitRadiusFill {
   T radius;
   Neighbor<T>* out;
+  int2 h0, h1, h2, h3;  // the hits of the current sector (8-byte neighbours only)
+  int first;            // slot of the first hit staged for it, 4 = none
+  static constexpr bool kStaged = sizeof(Neighbor<T>) == 8;
+  __device__ __forceinline__ void begin(Neighbor<T>* o) {
+    out = o;
+    first = 4;
+  }
   __device__ __forceinline__ T max() const { return radius; }
+  __device__ __forceinline__ int slot_of(const Neighbor<T>* p) const {
+    return (int)((reinterpret_cast<uintptr_t>(p) >> 3) & 3);
+  }
   __device__ __forceinline__ void visit(int i, T d) {
-    if (radius > d) {
+    if (!(radius > d)) return;
+    if constexpr (kStaged) {
+      const int slot = slot_of(out);
+      const int2 v = make_int2(i, __float_as_int(d));
+      if (slot == 0)
+        h0 = v;
+      else if (slot == 1)
+        h1 = v;
+      else if (slot == 2)
+        h2 = v;
+      else
+        h3 = v;
+      if (first == 4) first = slot;
+      ++out;
+      if (slot == 3) {
+        int2* b = reinterpret_cast<int2*>(out - 4);
+        if (first == 0) {
+          reinterpret_cast<int4*>(b)[0] = make_int4(h0.x, h0.y, h1.x, h1.y);
+          reinterpret_cast<int4*>(b)[1] = make_int4(h2.x, h2.y, h3.x, h3.y);
+        } else {  // the query's first sector: slots first .. 3
+          if (first <= 1) b[1] = h1;
+          if (first <= 2) b[2] = h2;
+          b[3] = h3;
+        }
+        first = 4;
+      }
+    } else {
       out->index = i;
       out->distance = d;
       ++out;
+    }
+  }
+  // the query's last, incomplete sector
+  __device__ __forceinline__ void finish() {
+    if constexpr (kStaged) {
+      if (first == 4) return;
+      const int end = slot_of(out);  // 1 .. 3: a complete sector has left already
+      int2* b = reinterpret_cast<int2*>(out - end);
+      if (first <= 0 && end > 0) b[0] = h0;
+      if (first <= 1 && end > 1) b[1] = h1;
+      if (first <= 2 && end > 2) b[2] = h2;
+      first = 4;
     }
   }
 };
@@ -796,6 +873,18 @@ struct BoxSlot {
   uint32_t node_stage;  // node | stage << 30
 };
 
+// The contiguous index range of a contained subtree (report_node) goes into the result row with 16-byte stores
+// once the row position is aligned; single hits are written as they come. (Collecting single hits per 16 bytes in
+// registers, as VisitRadiusFill does for its 8-byte records, cost the box kernel more in selects and registers than
+// the stores it saved: 13.0 -> 16.0 ms per million boxes.)
+__device__ __forceinline__ void copy_index_range(int32_t* __restrict__ dst, const int32_t* __restrict__ src, int n) {
+  int i = 0;
+  for (; i < n && (reinterpret_cast<uintptr_t>(dst + i) & 15) != 0; ++i) dst[i] = __ldg(src + i);
+  for (; i + 4 <= n; i += 4)
+    *reinterpret_cast<int4*>(dst + i) = make_int4(__ldg(src + i), __ldg(src + i + 1), __ldg(src + i + 2), __ldg(src + i + 3));
+  for (; i < n; ++i) dst[i] = __ldg(src + i);
+}
+
 template <typename T, int DIM>
 __device__ __forceinline__ uint32_t traverse_box_thread(const typename NodeOf<T>::type* __restrict__ nodes,
                                                         const typename Vec4Of<T>::type* __restrict__ pts4,
@@ -885,8 +974,7 @@ __device__ __forceinline__ uint32_t traverse_box_thread(const typename NodeOf<T>
         nr = rright;
         load_node(nodes, nr, ta, tb, rright, rsd, d1, re);
       }
-      if (out)
-        for (int i = rb; i < re; ++i) out[count + (uint32_t)(i - rb)] = __ldg(indices + i);
+      if (out) copy_index_range(out + count, indices + rb, re - rb);
       count += (uint32_t)(re - rb);
     } else {
       // intersects_left / intersects_right, kd_tree_search.hpp:310-328
