@@ -395,6 +395,19 @@ __device__ __forceinline__ void traverse_packed(const typename NodeOf<T>::type* 
   }
 }
 
+// Eight words to a 32-byte aligned address in ONE store (sm_100: STG.E.ENL2.256): a whole sector arrives at L2 at
+// once, which neither reads it from DRAM first nor writes it back in pieces.
+__device__ __forceinline__ void store_sector(void* p, int4 lo, int4 hi) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(lo.x), "r"(lo.y), "r"(lo.z),
+               "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w)
+               : "memory");
+#else
+  reinterpret_cast<int4*>(p)[0] = lo;
+  reinterpret_cast<int4*>(p)[1] = hi;
+#endif
+}
+
 // One neighbour record. {int, float} has an alignment of four, so the compiler writes it as two 4-byte stores; rows that
 // sit on an 8-byte boundary (every buffer a CUDA or host allocator hands out) take one 8-byte store instead — half
 // the store instructions and no half-written records on their way through L2.
@@ -472,8 +485,18 @@ struct VisitKnn {
   }
   // row = k neighbour records, ascending
   __device__ __forceinline__ void store(Neighbor<T>* row) const {
+    if constexpr (sizeof(Neighbor<T>) == 8 && KMAX % 4 == 0) {
+      // a full list of 8-byte records at a 32-byte boundary leaves as KMAX / 4 whole sectors
+      if (k == KMAX && (reinterpret_cast<uintptr_t>(row) & 31) == 0) {
+#pragma unroll
+        for (int i = 0; i < KMAX; i += 4)
+          store_sector(row + i, make_int4(id[i], __float_as_int(d[i]), id[i + 1], __float_as_int(d[i + 1])),
+                       make_int4(id[i + 2], __float_as_int(d[i + 2]), id[i + 3], __float_as_int(d[i + 3])));
+        return;
+      }
+    }
     if constexpr (sizeof(Neighbor<T>) == 8 && KMAX % 2 == 0) {
-      // a full list of 8-byte records at a 16-byte boundary leaves as KMAX / 2 16-byte stores
+      // ... at a 16-byte boundary as KMAX / 2 16-byte stores
       if (k == KMAX && (reinterpret_cast<uintptr_t>(row) & 15) == 0) {
 #pragma unroll
         for (int i = 0; i < KMAX; i += 2)
@@ -538,8 +561,7 @@ struct VisitRadiusFill {
       if (slot == 3) {
         int2* b = reinterpret_cast<int2*>(out - 4);
         if (first == 0) {
-          reinterpret_cast<int4*>(b)[0] = make_int4(h0.x, h0.y, h1.x, h1.y);
-          reinterpret_cast<int4*>(b)[1] = make_int4(h2.x, h2.y, h3.x, h3.y);
+          store_sector(b, make_int4(h0.x, h0.y, h1.x, h1.y), make_int4(h2.x, h2.y, h3.x, h3.y));
         } else {  // the query's first sector: slots first .. 3
           if (first <= 1) b[1] = h1;
           if (first <= 2) b[2] = h2;
