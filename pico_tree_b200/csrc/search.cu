@@ -806,8 +806,9 @@ int copy_out(cudaStream_t st, void* h_dst, const void* d_src, size_t bytes) {
     });
   int rc = 0;
   for (size_t i = 0; i < n_stages && !rc; ++i) {
-    while (i >= 2 && left[i - 2].load(std::memory_order_acquire) != 0 && !failed.load())
-      if (move_one() <= 0) std::this_thread::yield();
+    // (this thread does not move blocks while stages remain to be issued: a block it drew could belong to a stage
+    // that only it can issue)
+    while (i >= 2 && left[i - 2].load(std::memory_order_acquire) != 0 && !failed.load()) std::this_thread::yield();
     const size_t off = i * kStageBytes, len = std::min(kStageBytes, bytes - off);
     if (failed.load() || cudaMemcpyAsync(g_staging.buf[i & 1], src + off, len, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
         cudaEventRecord(ev[i & 1], st) != cudaSuccess) {
