@@ -518,6 +518,22 @@ def test_nth_element_heap_select_fallback(pt, oracle):
         assert_same_structure(nodes_from_export(nodes, pts.dtype), o.nodes)
 
 
+def test_small_host_batches_with_full_lists(pt, oracle):
+    """Small host batches are answered through a pinned, device-mapped buffer that the kernel writes over PCIe
+    (search.cu SmallBuffer); with k equal to a list size of the kernel (4, 8, 16, 32) the finished list leaves as
+    whole 32-byte sectors (traverse.cuh store_sector) — into host memory here. Other k take the record-wise path."""
+    from pico_tree_b200 import datasets as D
+    pts = D.lidar_shape(30_000, seed=4)
+    q = D.lidar_shape(64, seed=5, pose_shift=0.3)
+    t = pt.KdTree(pts, pt.Metric.L2Squared, 10)
+    o = oracle.OracleTree(pts, 10)
+    for k in (1, 3, 4, 8, 9, 16, 32):
+        for nq in (1, 5, 64):
+            got, want = t.search_knn(q[:nq], k), o.search_knn(q[:nq], k)
+            assert np.array_equal(got["index"], want["index"]), (k, nq)
+            assert np.array_equal(got["distance"], want["distance"]), (k, nq)
+
+
 def test_big_ragged_result_block_is_reused_correctly(pt):
     """A ragged host result of 64 MiB or more lives in a huge-page block that pico_b200_free keeps for the next big
     result (search.cu alloc_result / release_result). Results written into a reused block — bigger than, equal
